@@ -1,0 +1,600 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY -- see oracle.h.  Plain-C restatement of the reference's
+ * CPU algorithms for the hot path; compiled with -O2 -ffp-contract=off so that every float
+ * multiply/add rounds separately, exactly like the reference built for baseline x86-64.
+ * No code here is reachable from the product path. */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gr_tables.h" /* build/generated (tools/gen_tables.py) */
+
+/* ---------------------------------------------------------------------------------------- */
+static float g_mmse[129 * 8];
+static float g_atan[257];
+static int g_tables_ready = 0;
+static void tables_init(void) {
+  if (g_tables_ready) return;
+  memcpy(g_mmse, GR_MMSE_TAPS_BITS, sizeof g_mmse);
+  memcpy(g_atan, GR_FAST_ATAN_TABLE_BITS, sizeof g_atan);
+  g_tables_ready = 1;
+}
+const float* orc_mmse_table(void) { tables_init(); return g_mmse; }
+const float* orc_atan_table(void) { tables_init(); return g_atan; }
+
+/* ---- FIR kernels --------------------------------------------------------------------------
+ * gr_fir_XXX.h.t:51,65: d_taps = reverse(taps); filter(input) = sum_i d_taps[i]*input[i].
+ * generic ccf (gr_fir_XXX_generic.cc.t:57-81): two complex accumulators over even/odd i,
+ * tail into acc0, result acc0+acc1.  float*complex scales both parts. */
+static orc_cpx fir_ccf_one(const float* rt, int ntaps, const orc_cpx* in) {
+  float a0r = 0, a0i = 0, a1r = 0, a1i = 0;
+  int i = 0, n = (ntaps / 2) * 2;
+  for (; i < n; i += 2) {
+    a0r += rt[i] * in[i].re;         a0i += rt[i] * in[i].im;
+    a1r += rt[i + 1] * in[i + 1].re; a1i += rt[i + 1] * in[i + 1].im;
+  }
+  for (; i < ntaps; i++) { a0r += rt[i] * in[i].re; a0i += rt[i] * in[i].im; }
+  orc_cpx r = { a0r + a1r, a0i + a1i };
+  return r;
+}
+
+void orc_fir_ccf(const float* taps, int ntaps, int decim, const orc_cpx* in, long nout, orc_cpx* out) {
+  float* rt = (float*)malloc(sizeof(float) * (ntaps > 0 ? ntaps : 1));
+  for (int i = 0; i < ntaps; i++) rt[i] = taps[ntaps - 1 - i];
+  for (long o = 0; o < nout; o++) out[o] = fir_ccf_one(rt, ntaps, in + o * (long)decim); /* filterNdec :92-103 */
+  free(rt);
+}
+
+/* generic fff (gr_fir_XXX_generic.cc.t:28-55): four accumulators, ((a0+a1)+a2)+a3. */
+static float fir_fff_generic(const float* rt, int ntaps, const float* in) {
+  float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int i = 0, n = (ntaps / 4) * 4;
+  for (; i < n; i += 4) {
+    a0 += rt[i] * in[i]; a1 += rt[i + 1] * in[i + 1]; a2 += rt[i + 2] * in[i + 2]; a3 += rt[i + 3] * in[i + 3];
+  }
+  for (; i < ntaps; i++) a0 += rt[i] * in[i];
+  return a0 + a1 + a2 + a3;
+}
+
+/* SSE fff: gr_fir_fff_simd.cc:99-134 rounds the input pointer down to 16 bytes (al = number of
+ * floats skipped, 0..3), uses taps pre-shifted by al zeros, nblocks = (ntaps+al-1)/4+1 blocks of
+ * 4 floats.  float_dotprod_sse64.S:38-52: the first nblocks%4 blocks accumulate into xmm4;
+ * :60-86 the remaining groups of 4 blocks go to xmm4..xmm7 (block g*4+q -> accumulator q);
+ * :88-95 xmm4=(xmm4+xmm5)+(xmm7+xmm6) is only executed when at least one group ran (the
+ * `je .Lcleanup` at :57 skips it); :101-107 horizontal add (d0+d2)+(d1+d3).
+ * Items outside [0,ntaps) meet zero taps; their products are +-0 and do not change a sum
+ * (the harness guarantees finite slack), so they are skipped here. */
+static float fir_fff_sse(const float* rt, int ntaps, const float* in, int al) {
+  if (ntaps == 0) return 0.0f;
+  int nblocks = (ntaps + al - 1) / 4 + 1;
+  int nrem = nblocks & 3;
+  float acc[4][4];
+  memset(acc, 0, sizeof acc);
+  for (int b = 0; b < nblocks; b++) {
+    int a = (b < nrem) ? 0 : ((b - nrem) & 3);
+    for (int l = 0; l < 4; l++) {
+      int i = b * 4 + l - al; /* index into the un-padded taps/input */
+      if (i < 0 || i >= ntaps) continue;
+      acc[a][l] = acc[a][l] + rt[i] * in[i];
+    }
+  }
+  float d[4];
+  for (int l = 0; l < 4; l++) {
+    if (nblocks >> 2) d[l] = (acc[0][l] + acc[1][l]) + (acc[3][l] + acc[2][l]);
+    else d[l] = acc[0][l];
+  }
+  return (d[0] + d[2]) + (d[1] + d[3]);
+}
+
+static int mod4(long a) { return (int)(((a % 4) + 4) % 4); }
+
+void orc_fir_fff(const float* taps, int ntaps, int decim, const float* in, long nout, float* out, int order,
+                 long abs0) {
+  float* rt = (float*)malloc(sizeof(float) * (ntaps > 0 ? ntaps : 1));
+  for (int i = 0; i < ntaps; i++) rt[i] = taps[ntaps - 1 - i];
+  for (long o = 0; o < nout; o++) {
+    const float* p = in + o * (long)decim;
+    out[o] = (order == ORC_ORDER_SSE) ? fir_fff_sse(rt, ntaps, p, mod4(abs0 + o * (long)decim))
+                                      : fir_fff_generic(rt, ntaps, p);
+  }
+  free(rt);
+}
+
+/* complex * complex as gcc expands std::complex<float> operator* for finite operands:
+ * (ac - bd, ad + bc), each product and sum rounded separately. */
+static orc_cpx cmulf(orc_cpx a, orc_cpx b) {
+  orc_cpx r = { a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re };
+  return r;
+}
+
+static orc_cpx fir_ccc_one(const orc_cpx* rt, int ntaps, const orc_cpx* in) {
+  orc_cpx a0 = { 0, 0 }, a1 = { 0, 0 };
+  int i = 0, n = (ntaps / 2) * 2;
+  for (; i < n; i += 2) {
+    orc_cpx p0 = cmulf(rt[i], in[i]), p1 = cmulf(rt[i + 1], in[i + 1]);
+    a0.re += p0.re; a0.im += p0.im; a1.re += p1.re; a1.im += p1.im;
+  }
+  for (; i < ntaps; i++) { orc_cpx p = cmulf(rt[i], in[i]); a0.re += p.re; a0.im += p.im; }
+  orc_cpx r = { a0.re + a1.re, a0.im + a1.im };
+  return r;
+}
+
+void orc_fir_ccc(const orc_cpx* taps, int ntaps, int decim, const orc_cpx* in, long nout, orc_cpx* out) {
+  orc_cpx* rt = (orc_cpx*)malloc(sizeof(orc_cpx) * (ntaps > 0 ? ntaps : 1));
+  for (int i = 0; i < ntaps; i++) rt[i] = taps[ntaps - 1 - i];
+  for (long o = 0; o < nout; o++) out[o] = fir_ccc_one(rt, ntaps, in + o * (long)decim);
+  free(rt);
+}
+
+/* ---- rotator + freq-xlating FIR ------------------------------------------------------------ */
+static float cabs_f(orc_cpx z) { return hypotf(z.re, z.im); } /* std::abs(complex<float>) */
+
+void orc_rotator_init(orc_rotator* r, orc_cpx incr) {
+  r->phase.re = 1; r->phase.im = 0; r->counter = 0;
+  float a = cabs_f(incr); /* set_phase_incr: incr / abs(incr)  (gr_rotator.h:38) */
+  r->incr.re = incr.re / a; r->incr.im = incr.im / a;
+}
+
+void orc_rotator_init_f(orc_rotator* r, float re, float im) { orc_cpx z = { re, im }; orc_rotator_init(r, z); }
+
+orc_cpx orc_rotator_rotate(orc_rotator* r, orc_cpx in) { /* gr_rotator.h:40-50 */
+  r->counter++;
+  orc_cpx z = cmulf(in, r->phase);
+  r->phase = cmulf(r->phase, r->incr);
+  if ((r->counter % 512) == 0) {
+    float a = cabs_f(r->phase);
+    r->phase.re /= a; r->phase.im /= a;
+  }
+  return z;
+}
+
+void orc_rotate_n(orc_rotator* r, const orc_cpx* in, long n, orc_cpx* out) {
+  for (long i = 0; i < n; i++) out[i] = orc_rotator_rotate(r, in[i]);
+}
+
+void orc_freq_xlating_taps(const float* proto, int ntaps, double center_freq, double sampling_freq, int decim,
+                           orc_cpx* ctaps, orc_cpx* phase_incr) {
+  /* build_composite_fir (:72-83): float fwT0; ctaps[i] = proto[i] * exp(gr_complex(0, i*fwT0));
+   * the block then calls set_taps(gr_reverse(ctaps)), i.e. the FIR's forward taps are the
+   * REVERSED composite taps -- we return them in that (as-handed-to-set_taps) order. */
+  float fwT0 = (float)(2 * M_PI * center_freq / sampling_freq);
+  for (int i = 0; i < ntaps; i++) {
+    float ang = (float)i * fwT0; /* unsigned*float -> float */
+    orc_cpx e = { cosf(ang), sinf(ang) }; /* std::exp(complex<float>(0,a)) = polar(1,a) */
+    int dst = ntaps - 1 - i;
+    ctaps[dst].re = proto[i] * e.re;
+    ctaps[dst].im = proto[i] * e.im;
+  }
+  float ad = fwT0 * (float)decim;
+  phase_incr->re = cosf(ad); phase_incr->im = sinf(ad);
+}
+
+void orc_freq_xlating_fir_ccf(const float* proto, int ntaps, int decim, double center_freq, double sampling_freq,
+                              orc_rotator* rot, const orc_cpx* in, long nout, orc_cpx* out) {
+  orc_cpx* ct = (orc_cpx*)malloc(sizeof(orc_cpx) * (ntaps > 0 ? ntaps : 1));
+  orc_cpx incr;
+  orc_freq_xlating_taps(proto, ntaps, center_freq, sampling_freq, decim, ct, &incr);
+  /* filter() uses reversed forward taps -> rt[i] = ct[ntaps-1-i] = proto-order composite taps */
+  orc_cpx* rt = (orc_cpx*)malloc(sizeof(orc_cpx) * (ntaps > 0 ? ntaps : 1));
+  for (int i = 0; i < ntaps; i++) rt[i] = ct[ntaps - 1 - i];
+  for (long o = 0; o < nout; o++)
+    out[o] = orc_rotator_rotate(rot, fir_ccc_one(rt, ntaps, in + o * (long)decim)); /* :116-120 */
+  free(rt); free(ct);
+}
+
+/* ---- DFT (float64 mixed radix, exact per-prime butterflies) ------------------------------ */
+typedef struct { double re, im; } dcpx;
+static void dft_rec(dcpx* x, dcpx* tmp, int n, int stride, const dcpx* w, int N) {
+  if (n == 1) return;
+  int p = 2;
+  while (n % p) p++;
+  int m = n / p;
+  for (int r = 0; r < p; r++)
+    for (int i = 0; i < m; i++) tmp[r * m + i] = x[i * p + r];
+  for (int r = 0; r < p; r++) dft_rec(tmp + r * m, x, m, stride * p, w, N);
+  for (int k = 0; k < m; k++)
+    for (int q = 0; q < p; q++) {
+      int kk = k + q * m;
+      double ar = 0, ai = 0;
+      for (int r = 0; r < p; r++) {
+        const dcpx t = tmp[r * m + k];
+        const dcpx ww = w[(size_t)(((long long)r * kk) % n) * stride];
+        ar += t.re * ww.re - t.im * ww.im;
+        ai += t.re * ww.im + t.im * ww.re;
+      }
+      x[kk].re = ar; x[kk].im = ai;
+    }
+}
+
+void orc_dft(const orc_cpx* in, orc_cpx* out, int n, int forward) {
+  dcpx* w = (dcpx*)calloc((size_t)n * 3, sizeof(dcpx));
+  dcpx* a = w + n;
+  dcpx* b = a + n;
+  double s = forward ? -1.0 : 1.0;
+  for (int i = 0; i < n; i++) {
+    double ph = s * 2.0 * M_PI * (double)i / (double)n;
+    w[i].re = cos(ph); w[i].im = sin(ph);
+    a[i].re = in[i].re; a[i].im = in[i].im;
+  }
+  dft_rec(a, b, n, 1, w, n);
+  for (int i = 0; i < n; i++) { out[i].re = (float)a[i].re; out[i].im = (float)a[i].im; }
+  free(w);
+}
+
+/* ---- PFB channelizer ------------------------------------------------------------------------ */
+int orc_pfb_taps_per_filter(int numchans, int ntaps) {
+  return (int)ceil((double)ntaps / (double)numchans); /* :109 */
+}
+int orc_pfb_check_rate(int numchans, float oversample_rate) {
+  double intp = 0;
+  double fltp = modf(numchans / oversample_rate, &intp); /* :57-60 (float division) */
+  return fltp == 0.0;
+}
+int orc_pfb_output_multiple(int numchans, float oversample_rate) {
+  int rr = (int)rintf(numchans / oversample_rate); /* :81 */
+  int om = 1;
+  while ((om * rr) % numchans != 0) om++; /* :89-91 */
+  return om;
+}
+
+int orc_pfb_channelizer_ccf(int M, const float* taps, int ntaps, float os, const orc_cpx* const* ins, int noutput,
+                            orc_cpx* out, int* consumed) {
+  int T = orc_pfb_taps_per_filter(M, ntaps);
+  /* set_taps (:104-139): branch i gets taps[i + j*M], zero padded; gr_fir_ccf stores them reversed */
+  float* rt = (float*)calloc((size_t)M * T, sizeof(float));
+  for (int i = 0; i < M; i++)
+    for (int j = 0; j < T; j++) {
+      long idx = i + (long)j * M;
+      rt[(size_t)i * T + (T - 1 - j)] = idx < ntaps ? taps[idx] : 0.0f;
+    }
+  int rr = (int)rintf(M / os);
+  int* idxlut = (int*)malloc(sizeof(int) * M);
+  for (int i = 0; i < M; i++) idxlut[i] = M - ((i + rr) % M) - 1; /* :83-85 */
+  orc_cpx* fin = (orc_cpx*)malloc(sizeof(orc_cpx) * M);
+
+  int n = 1, i = -1, j = 0, last;
+  int toconsume = (int)rintf(noutput / os); /* :170 */
+  while (n <= toconsume) {                  /* :171-196 */
+    j = 0;
+    i = (i + rr) % M;
+    last = i;
+    while (i >= 0) {
+      fin[idxlut[j]] = fir_ccf_one(rt + (size_t)i * T, T, ins[j] + n);
+      j++; i--;
+    }
+    i = M - 1;
+    while (i > last) {
+      fin[idxlut[j]] = fir_ccf_one(rt + (size_t)i * T, T, ins[j] + (n - 1));
+      j++; i--;
+    }
+    n += (i + rr) >= M;
+    orc_dft(fin, out, M, 0);
+    out += M;
+  }
+  *consumed = toconsume;
+  free(fin); free(idxlut); free(rt);
+  return noutput;
+}
+
+/* ---- fft_vcc ------------------------------------------------------------------------------- */
+void orc_fft_vcc(int N, int forward, const float* window, int nwin, int shift, const orc_cpx* in, long nvec,
+                 orc_cpx* out) {
+  orc_cpx* a = (orc_cpx*)malloc(sizeof(orc_cpx) * N * 2);
+  orc_cpx* b = a + N;
+  for (long v = 0; v < nvec; v++, in += N, out += N) {
+    if (nwin) { /* :68-72 */
+      for (int i = 0; i < N; i++) { a[i].re = in[i].re * window[i]; a[i].im = in[i].im * window[i]; }
+    } else if (!forward && shift) { /* :74-79 */
+      int len = (int)floor(N / 2.0);
+      memcpy(a, in + len, sizeof(orc_cpx) * (N - len));
+      memcpy(a + (N - len), in, sizeof(orc_cpx) * len);
+    } else {
+      memcpy(a, in, sizeof(orc_cpx) * N);
+    }
+    orc_dft(a, b, N, forward);
+    if (forward && shift) { /* :89-93 */
+      int len = (int)ceil(N / 2.0);
+      memcpy(out, b + len, sizeof(orc_cpx) * (N - len));
+      memcpy(out + (N - len), b, sizeof(orc_cpx) * len);
+    } else {
+      memcpy(out, b, sizeof(orc_cpx) * N);
+    }
+  }
+  free(a);
+}
+
+/* ---- quadrature demod ----------------------------------------------------------------------- */
+float orc_fast_atan2f(float y, float x) { /* gr_fast_atan2f.cc:125-198 */
+  tables_init();
+  float x_abs, y_abs, z, alpha, angle, base_angle;
+  int index;
+  if ((y == 0.0) && (x == 0.0)) return 0.0f;
+  y_abs = fabsf(y);
+  x_abs = fabsf(x);
+  if (y_abs < x_abs) z = y_abs / x_abs; else z = x_abs / y_abs;
+  if ((double)z < 0.003921569) /* TAN_MAP_RES: float compared against a double literal (:32,147) */
+    base_angle = z;
+  else {
+    alpha = (float)((double)(z * (float)256) - .5); /* :151 evaluates in double, stores float */
+    index = (int)alpha;
+    alpha -= (float)index;
+    base_angle = g_atan[index];
+    base_angle += (g_atan[index + 1] - g_atan[index]) * alpha;
+  }
+  if (x_abs > y_abs) {
+    if (x >= 0.0) { angle = (y >= 0.0) ? base_angle : -base_angle; }
+    else {
+      angle = (float)3.14159265358979323846;
+      if (y >= 0.0) angle -= base_angle; else angle = base_angle - angle;
+    }
+  } else {
+    if (y >= 0.0) {
+      angle = (float)1.57079632679489661923;
+      if (x >= 0.0) angle -= base_angle; else angle += base_angle;
+    } else {
+      angle = (float)-1.57079632679489661923;
+      if (x >= 0.0) angle += base_angle; else angle -= base_angle;
+    }
+  }
+  return angle;
+}
+
+void orc_quadrature_demod_cf(float gain, const orc_cpx* in, long nout, float* out) {
+  in++; /* :53 */
+  for (long i = 0; i < nout; i++) {
+    orc_cpx c = { in[i - 1].re, -in[i - 1].im }; /* conj */
+    orc_cpx p = cmulf(in[i], c);
+    out[i] = gain * orc_fast_atan2f(p.im, p.re);
+  }
+}
+
+/* ---- MMSE interpolator + M&M ---------------------------------------------------------------- */
+float orc_mmse_interpolate(const float* in8, float mu, int order, long abs0) {
+  tables_init();
+  int imu = (int)rint(mu * 128); /* gri_mmse_fir_interpolator.cc:64 */
+  /* filters[imu] = gr_fir_fff(taps[imu]) -> reversed: rt[i] = taps[imu][7-i] (:38-41) */
+  float rt[8];
+  for (int i = 0; i < 8; i++) rt[i] = g_mmse[imu * 8 + (7 - i)];
+  return order == ORC_ORDER_SSE ? fir_fff_sse(rt, 8, in8, mod4(abs0)) : fir_fff_generic(rt, 8, in8);
+}
+
+int orc_mm_init(orc_mm_state* s, float omega, float gain_omega, float mu, float gain_mu, float lim) {
+  if (omega < 1) return -1;                     /* :58-59 std::out_of_range */
+  if (gain_mu < 0 || gain_omega < 0) return -1; /* :60-61 */
+  s->mu = mu; s->gain_omega = gain_omega; s->gain_mu = gain_mu; s->last_sample = 0;
+  s->omega_relative_limit = lim;
+  /* set_omega (digital_clock_recovery_mm_ff.h:75-80): double expressions stored to float */
+  s->omega = omega;
+  s->min_omega = (float)(omega * (1.0 - lim));
+  s->max_omega = (float)(omega * (1.0 + lim));
+  s->omega_mid = (float)(0.5 * (s->min_omega + s->max_omega));
+  return 0;
+}
+
+int orc_mm_forecast(const orc_mm_state* s, int noutput) { /* :80-87 */
+  return (int)ceil((noutput * s->omega) + 8);
+}
+
+static float slice_pm1(float x) { return x < 0 ? -1.0F : 1.0F; } /* :89-93 */
+static float branchless_clip(float x, float clip) {              /* gr_math.h:63-69 */
+  float x1 = fabsf(x + clip);
+  float x2 = fabsf(x - clip);
+  x1 -= x2;
+  return (float)(0.5 * x1);
+}
+
+int orc_mm_general_work(orc_mm_state* s, const float* in, int ninput, float* out, int noutput, int* consumed,
+                        int order, long abs0) {
+  int ii = 0, oo = 0;
+  int ni = ninput - 8; /* :112 */
+  float mm_val;
+  while (oo < noutput && ii < ni) { /* :116-134 */
+    out[oo] = orc_mmse_interpolate(&in[ii], s->mu, order, abs0 + ii);
+    mm_val = slice_pm1(s->last_sample) * out[oo] - slice_pm1(out[oo]) * s->last_sample;
+    s->last_sample = out[oo];
+    s->omega = s->omega + s->gain_omega * mm_val;
+    s->omega = s->omega_mid + branchless_clip(s->omega - s->omega_mid, s->omega_relative_limit);
+    s->mu = s->mu + s->omega + s->gain_mu * mm_val;
+    ii += (int)floor(s->mu);
+    s->mu = (float)(s->mu - floor(s->mu));
+    oo++;
+  }
+  *consumed = ii;
+  return oo;
+}
+
+/* ---- slicers ---------------------------------------------------------------------------------- */
+void orc_slicer4_init(orc_slicer4_state* s, float alpha) { /* pager_slicer_fb.cc:39-41 */
+  s->alpha = alpha; s->beta = (float)(1.0 - alpha); s->avg = 0.0f;
+}
+void orc_slicer4(orc_slicer4_state* s, const float* in, long n, unsigned char* out) { /* :47-69 */
+  for (long i = 0; i < n; i++) {
+    float sample = in[i];
+    s->avg = s->avg * s->beta + sample * s->alpha;
+    sample -= s->avg;
+    unsigned char d;
+    if (sample > 0) d = (sample > 2.0) ? 3 : 2;
+    else d = (sample < -2.0) ? 0 : 1;
+    out[i] = d;
+  }
+}
+void orc_binary_slicer(const float* in, long n, unsigned char* out) { /* gr_math.h:82-88 */
+  for (long i = 0; i < n; i++) out[i] = in[i] >= 0 ? 1 : 0;
+}
+
+/* ---- byte plumbing ---------------------------------------------------------------------------- */
+void orc_map_bb(const int* map, int nmap, const unsigned char* in, long n, unsigned char* out) {
+  unsigned char m[256];
+  for (int i = 0; i < 256; i++) m[i] = (unsigned char)i; /* gr_map_bb.cc:40-46 */
+  int size = nmap < 256 ? nmap : 256;
+  for (int i = 0; i < size; i++) m[i] = (unsigned char)map[i];
+  for (long i = 0; i < n; i++) out[i] = m[in[i]];
+}
+void orc_unpack_k_bits_bb(unsigned k, const unsigned char* in, long nin, unsigned char* out) {
+  long n = 0;
+  for (long i = 0; i < nin; i++) { /* gr_unpack_k_bits_bb.cc:63-67: MSB first */
+    unsigned t = in[i];
+    for (int j = (int)k - 1; j >= 0; j--) out[n++] = (t >> j) & 0x01;
+  }
+}
+
+/* ---- access-code correlator -------------------------------------------------------------------- */
+unsigned orc_count_bits64(unsigned long long x) { /* gr_count_bits.cc:75-93 (SWAR popcount) */
+  unsigned c = 0;
+  while (x) { x &= x - 1; c++; }
+  return c;
+}
+int orc_corr_init(orc_corr_state* s, const char* code, int threshold) { /* :64-85 */
+  unsigned len = (unsigned)strlen(code);
+  if (len > 64) return -1;
+  memset(s, 0, sizeof *s);
+  s->threshold = (unsigned)threshold;
+  s->mask = len ? ((~0ULL) >> (64 - len)) << (64 - len) : 0ULL;
+  s->flag_bit = len ? 1ULL << (64 - len) : 0ULL;
+  s->access_code = 0;
+  for (unsigned i = 0; i < 64; i++) {
+    s->access_code <<= 1;
+    if (i < len) s->access_code |= (unsigned long long)(code[i] & 1);
+  }
+  return 0;
+}
+void orc_corr_work(orc_corr_state* s, const unsigned char* in, long n, unsigned char* out) { /* :87-133 */
+  for (long i = 0; i < n; i++) {
+    unsigned t = 0;
+    t |= (unsigned)((s->data_reg >> 63) & 0x1) << 0;
+    t |= (unsigned)((s->flag_reg >> 63) & 0x1) << 1;
+    out[i] = (unsigned char)t;
+    unsigned long long wrong = (s->data_reg ^ s->access_code) & s->mask;
+    unsigned nwrong = orc_count_bits64(wrong);
+    int new_flag = (nwrong <= s->threshold);
+    s->data_reg = (s->data_reg << 1) | (in[i] & 0x1);
+    s->flag_reg = (s->flag_reg << 1);
+    if (new_flag) s->flag_reg |= s->flag_bit;
+  }
+}
+
+/* ---- gr_firdes ------------------------------------------------------------------------------ */
+static double izero(double x) { /* gr_firdes.cc:35-51 */
+  double sum, u, halfx, temp;
+  int n;
+  sum = u = n = 1;
+  halfx = x / 2.0;
+  do {
+    temp = halfx / (double)n;
+    n += 1;
+    temp *= temp;
+    u *= temp;
+    sum += u;
+  } while (u >= 1E-21 * sum);
+  return sum;
+}
+
+int orc_firdes_window(int type, int ntaps, double beta, float* taps) { /* :720-782 */
+  int M = ntaps - 1;
+  switch (type) {
+    case 3: /* WIN_RECTANGULAR falls through into HAMMING in the reference (missing break, :727-731) */
+    case 0:
+      for (int n = 0; n < ntaps; n++) taps[n] = (float)(0.54 - 0.46 * cos((2 * M_PI * n) / M));
+      break;
+    case 1:
+      for (int n = 0; n < ntaps; n++) taps[n] = (float)(0.5 - 0.5 * cos((2 * M_PI * n) / M));
+      break;
+    case 2:
+      for (int n = 0; n < ntaps; n++)
+        taps[n] = (float)(0.42 - 0.50 * cos((2 * M_PI * n) / (M - 1)) - 0.08 * cos((4 * M_PI * n) / (M - 1)));
+      break;
+    case 5:
+      for (int n = -ntaps / 2; n < ntaps / 2; n++)
+        taps[n + ntaps / 2] = (float)(0.35875 + 0.48829 * cos((2 * M_PI * n) / (float)M) +
+                                      0.14128 * cos((4 * M_PI * n) / (float)M) +
+                                      0.01168 * cos((6 * M_PI * n) / (float)M));
+      if (ntaps & 1) taps[ntaps - 1] = 0.0f; /* loop never writes the last tap of an odd window: vector<float> zero-init */
+      break;
+    case 4: {
+      double IBeta = 1.0 / izero(beta);
+      double inm1 = 1.0 / ((double)(ntaps));
+      for (int i = 0; i < ntaps; i++) {
+        double temp = i * inm1;
+        taps[i] = (float)(izero(beta * sqrt(1.0 - temp * temp)) * IBeta);
+      }
+      break;
+    }
+    default:
+      return -1;
+  }
+  return ntaps;
+}
+
+static int lowpass_common(double gain, double fs, double fc, int ntaps, int win, double beta, float* taps) {
+  float* w = (float*)calloc(ntaps, sizeof(float));
+  if (orc_firdes_window(win, ntaps, beta, w) < 0) { free(w); return -1; }
+  int M = (ntaps - 1) / 2;
+  double fwT0 = 2 * M_PI * fc / fs;
+  for (int n = -M; n <= M; n++) {
+    if (n == 0) taps[n + M] = (float)(fwT0 / M_PI * w[n + M]);
+    else taps[n + M] = (float)(sin(n * fwT0) / (n * M_PI) * w[n + M]);
+  }
+  double fmax = taps[0 + M];
+  for (int n = 1; n <= M; n++) fmax += 2 * taps[n + M];
+  gain /= fmax;
+  for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain);
+  free(w);
+  return ntaps;
+}
+
+static int sanity_1f(double fs, double fa, double tw) { /* :784-797 */
+  if (fs <= 0.0) return 0;
+  if (fa <= 0.0 || fa > fs / 2) return 0;
+  if (tw <= 0) return 0;
+  return 1;
+}
+
+int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win, double beta, float* out, int cap) {
+  static const float width_factor[5] = { 3.3f, 3.1f, 5.5f, 2.0f, 10.0f }; /* :657-665 */
+  if (!sanity_1f(fs, fc, tw)) return -1;
+  if (win < 0 || win > 4) return -1; /* reference indexes out of bounds for BLACKMAN_hARRIS: not reproduced */
+  double delta_f = tw / fs;
+  int ntaps = (int)(width_factor[win] / delta_f + 0.5);
+  if ((ntaps & 1) == 0) ntaps++;
+  if (ntaps > cap) return -ntaps;
+  return lowpass_common(gain, fs, fc, ntaps, win, beta, out);
+}
+
+int orc_firdes_low_pass_2(double gain, double fs, double fc, double tw, double atten, int win, double beta,
+                          float* out, int cap) {
+  if (!sanity_1f(fs, fc, tw)) return -1;
+  int ntaps = (int)(atten * fs / (22.0 * tw)); /* compute_ntaps_windes :668-679 */
+  if ((ntaps & 1) == 0) ntaps++;
+  if (ntaps > cap) return -ntaps;
+  return lowpass_common(gain, fs, fc, ntaps, win, beta, out);
+}
+
+int orc_firdes_root_raised_cosine(double gain, double fs, double sym, double alpha, int ntaps, float* taps) {
+  ntaps |= 1; /* :608 */
+  double spb = fs / sym;
+  double scale = 0;
+  for (int i = 0; i < ntaps; i++) {
+    double x1, x2, x3, num, den;
+    double xindx = i - ntaps / 2;
+    x1 = M_PI * xindx / spb;
+    x2 = 4 * alpha * xindx / spb;
+    x3 = x2 * x2 - 1;
+    if (fabs(x3) >= 0.000001) {
+      if (i != ntaps / 2) num = cos((1 + alpha) * x1) + sin((1 - alpha) * x1) / (4 * alpha * xindx / spb);
+      else num = cos((1 + alpha) * x1) + (1 - alpha) * M_PI / (4 * alpha);
+      den = x3 * M_PI;
+    } else {
+      if (alpha == 1) { taps[i] = -1; continue; }
+      x3 = (1 - alpha) * x1;
+      x2 = (1 + alpha) * x1;
+      num = (sin(x2) * (1 + alpha) * M_PI - cos(x3) * ((1 - alpha) * M_PI * spb) / (4 * alpha * xindx) +
+             sin(x3) * spb * spb / (4 * alpha * xindx * xindx));
+      den = -32 * M_PI * alpha * alpha * xindx / spb;
+    }
+    taps[i] = (float)(4 * alpha * num / den);
+    scale += taps[i];
+  }
+  for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain / scale);
+  return ntaps;
+}

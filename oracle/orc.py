@@ -1,0 +1,298 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product package (grb200).
+
+numpy/ctypes front end of oracle/liboracle.so (oracle.c: the plain-C restatement of the
+reference algorithms).  Stream helpers take NEW items only and prepend the zero history the
+reference runtime pre-loads (gr_buffer.cc:201-214)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+ORDER_GENERIC, ORDER_SSE = 0, 1
+
+
+class MMState(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("mu", "omega", "min_omega", "omega_mid", "max_omega", "gain_omega",
+                                         "gain_mu", "last_sample", "omega_relative_limit")]
+
+
+class Slicer4State(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("avg", C.c_float)]
+
+
+class CorrState(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in ("access_code", "data_reg", "flag_reg", "flag_bit", "mask")] + \
+               [("threshold", C.c_uint)]
+
+
+class Rotator(C.Structure):
+    _fields_ = [("phase", C.c_float * 2), ("incr", C.c_float * 2), ("counter", C.c_uint)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_fast_atan2f.restype = C.c_float
+        L.orc_fast_atan2f.argtypes = [C.c_float, C.c_float]
+        L.orc_mmse_interpolate.restype = C.c_float
+        L.orc_mmse_table.restype = C.POINTER(C.c_float)
+        L.orc_atan_table.restype = C.POINTER(C.c_float)
+        L.orc_count_bits64.argtypes = [C.c_ulonglong]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _hist(x, h, dtype):
+    x = np.ascontiguousarray(x, dtype)
+    return np.concatenate([np.zeros(h, dtype), x])
+
+
+def fir_ccf(taps, decim, x, hist_prefixed=False):
+    t = np.ascontiguousarray(taps, np.float32)
+    xin = np.ascontiguousarray(x, np.complex64) if hist_prefixed else _hist(x, max(len(t) - 1, 0), np.complex64)
+    nout = (len(xin) - max(len(t) - 1, 0)) // decim
+    out = np.zeros(nout, np.complex64)
+    lib().orc_fir_ccf(_p(t), len(t), int(decim), _p(xin), C.c_long(nout), _p(out))
+    return out
+
+
+def fir_fff(taps, decim, x, order=ORDER_GENERIC, abs0=None, hist_prefixed=False):
+    t = np.ascontiguousarray(taps, np.float32)
+    h = max(len(t) - 1, 0)
+    xin = np.ascontiguousarray(x, np.float32) if hist_prefixed else _hist(x, h, np.float32)
+    nout = (len(xin) - h) // decim
+    out = np.zeros(nout, np.float32)
+    a0 = -h if abs0 is None else abs0
+    lib().orc_fir_fff(_p(t), len(t), int(decim), _p(xin), C.c_long(nout), _p(out), int(order), C.c_long(a0))
+    return out
+
+
+def fir_ccc(taps, decim, x):
+    t = np.ascontiguousarray(taps, np.complex64)
+    xin = _hist(x, max(len(t) - 1, 0), np.complex64)
+    nout = (len(xin) - max(len(t) - 1, 0)) // decim
+    out = np.zeros(nout, np.complex64)
+    lib().orc_fir_ccc(_p(t), len(t), int(decim), _p(xin), C.c_long(nout), _p(out))
+    return out
+
+
+def rotator_new(incr):
+    r = Rotator()
+    lib().orc_rotator_init_f(C.byref(r), C.c_float(np.float32(incr.real)), C.c_float(np.float32(incr.imag)))
+    return r
+
+
+def rotate(incr, x):
+    r = rotator_new(incr)
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().orc_rotate_n(C.byref(r), _p(x), C.c_long(len(x)), _p(out))
+    return out
+
+
+def freq_xlating_taps(proto, center_freq, sampling_freq, decim):
+    p = np.ascontiguousarray(proto, np.float32)
+    ct = np.zeros(len(p), np.complex64)
+    inc = np.zeros(1, np.complex64)
+    lib().orc_freq_xlating_taps(_p(p), len(p), C.c_double(center_freq), C.c_double(sampling_freq), int(decim),
+                                _p(ct), _p(inc))
+    return ct, inc[0]
+
+
+def freq_xlating_fir_ccf(proto, decim, center_freq, sampling_freq, x, rot=None):
+    p = np.ascontiguousarray(proto, np.float32)
+    xin = _hist(x, max(len(p) - 1, 0), np.complex64)
+    nout = (len(xin) - max(len(p) - 1, 0)) // decim
+    out = np.zeros(nout, np.complex64)
+    if rot is None:
+        _, inc = freq_xlating_taps(p, center_freq, sampling_freq, decim)
+        rot = rotator_new(complex(inc))
+    lib().orc_freq_xlating_fir_ccf(_p(p), len(p), int(decim), C.c_double(center_freq), C.c_double(sampling_freq),
+                                   C.byref(rot), _p(xin), C.c_long(nout), _p(out))
+    return out
+
+
+def dft(x, forward=True):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().orc_dft(_p(x), _p(out), len(x), int(bool(forward)))
+    return out
+
+
+def pfb_taps_per_filter(M, ntaps):
+    return lib().orc_pfb_taps_per_filter(int(M), int(ntaps))
+
+
+def pfb_output_multiple(M, os_rate):
+    return lib().orc_pfb_output_multiple(int(M), C.c_float(os_rate))
+
+
+def pfb_check_rate(M, os_rate):
+    return bool(lib().orc_pfb_check_rate(int(M), C.c_float(os_rate)))
+
+
+def pfb_channelizer_ccf(M, taps, x, oversample_rate=1.0):
+    """x: interleaved wideband stream; returns (out[rows_out][M], consumed_per_stream)."""
+    t = np.ascontiguousarray(taps, np.float32)
+    T = pfb_taps_per_filter(M, len(t))
+    x = np.ascontiguousarray(x, np.complex64)
+    rows = len(x) // M
+    xs = x[:rows * M].reshape(rows, M)
+    streams = [np.ascontiguousarray(np.concatenate([np.zeros(T, np.complex64), xs[:, j]])) for j in range(M)]
+    ptrs = (C.c_void_p * M)(*[s.ctypes.data for s in streams])
+    om = pfb_output_multiple(M, oversample_rate)
+    nout = int(round(rows * oversample_rate))
+    nout -= nout % om
+    out = np.zeros(nout * M, np.complex64)
+    consumed = C.c_int(0)
+    r = lib().orc_pfb_channelizer_ccf(int(M), _p(t), len(t), C.c_float(oversample_rate), ptrs, nout, _p(out),
+                                      C.byref(consumed))
+    return out.reshape(r, M), consumed.value
+
+
+def fft_vcc(N, forward, window, shift, x):
+    x = np.ascontiguousarray(x, np.complex64)
+    w = np.ascontiguousarray(window if window is not None else [], np.float32)
+    nvec = len(x) // N
+    out = np.zeros(nvec * N, np.complex64)
+    lib().orc_fft_vcc(int(N), int(bool(forward)), _p(w) if len(w) else None, len(w), int(bool(shift)), _p(x),
+                      C.c_long(nvec), _p(out))
+    return out
+
+
+def fast_atan2f(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    f = lib().orc_fast_atan2f
+    return np.array([f(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+
+
+def quadrature_demod_cf(gain, x, prev=0j):
+    xin = np.concatenate([np.array([prev], np.complex64), np.ascontiguousarray(x, np.complex64)])
+    out = np.zeros(len(xin) - 1, np.float32)
+    lib().orc_quadrature_demod_cf(C.c_float(gain), _p(xin), C.c_long(len(out)), _p(out))
+    return out
+
+
+def mmse_interpolate(in8, mu, order=ORDER_GENERIC, abs0=0):
+    a = np.ascontiguousarray(in8, np.float32)
+    return lib().orc_mmse_interpolate(_p(a), C.c_float(mu), int(order), C.c_long(abs0))
+
+
+def mm_new(omega, gain_omega, mu, gain_mu, omega_relative_limit=0.001):
+    s = MMState()
+    if lib().orc_mm_init(C.byref(s), C.c_float(omega), C.c_float(gain_omega), C.c_float(mu), C.c_float(gain_mu),
+                         C.c_float(omega_relative_limit)) != 0:
+        raise IndexError("out_of_range")
+    return s
+
+
+def mm_work(state, x, noutput=None, order=ORDER_GENERIC, abs0=0):
+    x = np.ascontiguousarray(x, np.float32)
+    nout = len(x) if noutput is None else noutput
+    out = np.zeros(max(nout, 1), np.float32)
+    consumed = C.c_int(0)
+    r = lib().orc_mm_general_work(C.byref(state), _p(x), len(x), _p(out), int(nout), C.byref(consumed), int(order),
+                                  C.c_long(abs0))
+    return out[:r], consumed.value
+
+
+def slicer4(x, alpha=0.0, state=None):
+    s = state or Slicer4State()
+    if state is None:
+        lib().orc_slicer4_init(C.byref(s), C.c_float(alpha))
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(len(x), np.uint8)
+    lib().orc_slicer4(C.byref(s), _p(x), C.c_long(len(x)), _p(out))
+    return out
+
+
+def binary_slicer(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(len(x), np.uint8)
+    lib().orc_binary_slicer(_p(x), C.c_long(len(x)), _p(out))
+    return out
+
+
+def map_bb(m, x):
+    x = np.ascontiguousarray(x, np.uint8)
+    mm = (C.c_int * len(m))(*[int(v) for v in m])
+    out = np.zeros(len(x), np.uint8)
+    lib().orc_map_bb(mm, len(m), _p(x), C.c_long(len(x)), _p(out))
+    return out
+
+
+def unpack_k_bits_bb(k, x):
+    x = np.ascontiguousarray(x, np.uint8)
+    out = np.zeros(len(x) * k, np.uint8)
+    lib().orc_unpack_k_bits_bb(int(k), _p(x), C.c_long(len(x)), _p(out))
+    return out
+
+
+def corr_new(code, threshold):
+    s = CorrState()
+    if lib().orc_corr_init(C.byref(s), code.encode(), int(threshold)) != 0:
+        raise IndexError("out_of_range: access_code is > 64 bits")
+    return s
+
+
+def corr_work(state, bits):
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(len(b), np.uint8)
+    lib().orc_corr_work(C.byref(state), _p(b), C.c_long(len(b)), _p(out))
+    return out
+
+
+def firdes_window(win, ntaps, beta=6.76):
+    out = np.zeros(ntaps, np.float32)
+    if lib().orc_firdes_window(int(win), int(ntaps), C.c_double(beta), _p(out)) < 0:
+        raise IndexError("gr_firdes:window: type out of range")
+    return out
+
+
+def firdes_low_pass(gain, fs, fc, tw, win=0, beta=6.76):
+    out = np.zeros(1 << 20, np.float32)
+    n = lib().orc_firdes_low_pass(C.c_double(gain), C.c_double(fs), C.c_double(fc), C.c_double(tw), int(win),
+                                  C.c_double(beta), _p(out), len(out))
+    if n <= 0:
+        raise ValueError("firdes check failed")
+    return out[:n].copy()
+
+
+def firdes_low_pass_2(gain, fs, fc, tw, atten, win=0, beta=6.76):
+    out = np.zeros(1 << 20, np.float32)
+    n = lib().orc_firdes_low_pass_2(C.c_double(gain), C.c_double(fs), C.c_double(fc), C.c_double(tw),
+                                    C.c_double(atten), int(win), C.c_double(beta), _p(out), len(out))
+    if n <= 0:
+        raise ValueError("firdes check failed")
+    return out[:n].copy()
+
+
+def firdes_root_raised_cosine(gain, fs, sym, alpha, ntaps):
+    out = np.zeros(ntaps | 1, np.float32)
+    n = lib().orc_firdes_root_raised_cosine(C.c_double(gain), C.c_double(fs), C.c_double(sym), C.c_double(alpha),
+                                            int(ntaps), _p(out))
+    return out[:n]
+
+
+def mmse_table():
+    return np.ctypeslib.as_array(lib().orc_mmse_table(), shape=(129, 8)).copy()
+
+
+def atan_table():
+    return np.ctypeslib.as_array(lib().orc_atan_table(), shape=(257,)).copy()

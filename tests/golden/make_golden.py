@@ -1,0 +1,182 @@
+#!/usr/bin/env python3
+"""Generates the committed fixtures in tests/golden/ (run HERE, where /root/reference is mounted).
+
+  kats.json          known-answer vectors lifted from the reference's OWN tests for this path
+                     (parsed out of the mounted test sources; file:line recorded per entry).
+  ref_fixtures.npz   outputs of the reference's own classes (oracle/_ref/libgrref.so, i.e. the
+                     unmodified sources compiled in place) on small seeded inputs, for the rows
+                     no reference test pins (PFB channelizer, freq-xlating FIR, quadrature demod /
+                     fast_atan2f, 4-level slicer, full demod chain) -- SURVEY.md 8c.
+
+Neither file is read by the product; tests/ compare the oracle restatement AND the CUDA path to them.
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("GR_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200"))
+
+
+def rd(rel):
+    return open(os.path.join(REF, rel)).read()
+
+
+def c_array(src, name):
+    m = re.search(name + r"\s*\[[^\]]*\]\s*=\s*\{([^}]*)\}", src)
+    return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", m.group(1))]
+
+
+def kats():
+    k = {}
+    # --- qa_gr_fir_fff.cc:58-76 ------------------------------------------------------------
+    s = rd("gnuradio-core/src/lib/filter/qa_gr_fir_fff.cc")
+    k["fir_fff"] = {
+        "source": "gnuradio-core/src/lib/filter/qa_gr_fir_fff.cc:58-76",
+        "input_1": c_array(s, "input_1"), "taps_1a": c_array(s, "taps_1a"), "expected_1a": c_array(s, "expected_1a"),
+        "taps_1b": c_array(s, "taps_1b"), "expected_1b": c_array(s, "expected_1b"),
+    }
+    # --- qa_fft.py:26-33,50-100 -------------------------------------------------------------
+    s = rd("gnuradio-core/src/python/gnuradio/gr/qa_fft.py")
+    primes = [int(v) for v in re.findall(r"\d+", s[s.index("primes = ("):s.index(")", s.index("primes = ("))])]
+    t1 = s[s.index("def test_001"):s.index("def test_002")]
+    exp = t1[t1.index("expected_result = ("):t1.index("src = gr.vector_source_c")]
+    vals = re.findall(r"\(([-+]?[\d.]+)([-+][\d.]+)j\)", exp)
+    k["fft_vcc_32"] = {
+        "source": "gnuradio-core/src/python/gnuradio/gr/qa_fft.py:50-100 (forward) and :101-158 (inverse)",
+        "rel_eps": 4e-4, "abs_eps": 1e-9, "primes": primes[:64],
+        "expected_re": [float(a) for a, b in vals], "expected_im": [float(b) for a, b in vals],
+    }
+    assert len(vals) == 32
+    # --- qa_gr_firdes.cc t1 / t4 -------------------------------------------------------------
+    s = rd("gnuradio-core/src/lib/general/qa_gr_firdes.cc")
+    k["firdes_low_pass"] = {"source": "gnuradio-core/src/lib/general/qa_gr_firdes.cc:57-112,486-503",
+                            "args": [1.0, 8000, 1750, 500], "win": 0, "expected": c_array(s, "t1_exp")}
+    k["firdes_low_pass_2"] = {"source": "gnuradio-core/src/lib/general/qa_gr_firdes.cc:549-566",
+                              "args": [1.0, 8000, 1750, 500, 66], "win": 0, "expected": c_array(s, "t4_exp")}
+    # --- qa_correlate_access_code.py:50-78 ----------------------------------------------------
+    k["correlate_access_code"] = {
+        "source": "gr-digital/python/qa_correlate_access_code.py:27,50-78",
+        "t1_code": "1011", "t1_src": [1, 0, 1, 1, 1, 1, 0, 1, 1] + [0] * 64 + [0] * 7,
+        "t1_expected": [0] * 64 + [1, 0, 1, 1, 3, 1, 0, 1, 1, 2] + [0] * 6,
+        "default_access_code_bytes": [0xAC, 0xDD, 0xA4, 0xE2, 0xF2, 0x8C, 0x20, 0xFC],
+    }
+    # --- qa_clock_recovery_mm.py:70-102,140-172 ------------------------------------------------
+    k["clock_recovery_mm_ff"] = {
+        "source": "gr-digital/python/qa_clock_recovery_mm.py:70-102,140-172",
+        "test02": {"args": [2, 0.01, 0.5, 0.01, 0.001], "input": "100 x 1.0", "expected_last30": 0.99972,
+                   "places": 5},
+        "test04": {"args": [2, 0.01, 0.25, 0.1, 0.001], "input": "1000 x [1,1,-1,-1]", "expected_pm": 1.31,
+                   "places": 1},
+    }
+    # --- qa_gr_math.cc:27-50 -----------------------------------------------------------------
+    k["binary_slicer"] = {"source": "gnuradio-core/src/lib/general/qa_gr_math.cc:27-50",
+                          "x": [-1, -0.5, 0, 0.5, 1.0], "z": [0, 0, 1, 1, 1]}
+    k["binary_slicer_fb"] = {"source": "gr-digital/python/qa_binary_slicer_fb.py:35-50",
+                             "src_sign": [-1, 1, -1, -1, 1, 1, -1, -1, -1, 1, 1, 1, -1, 1, 1, 1, 1],
+                             "expected": [0, 1, 0, 0, 1, 1, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1]}
+    k["rotator"] = {"source": "gnuradio-core/src/lib/filter/qa_gr_rotator.cc:43-75", "N": 100000,
+                    "phase_incr": "2*pi/1003", "tol": 1e-4}
+    k["mmse_interpolator"] = {"source": "gnuradio-core/src/lib/filter/qa_gri_mmse_fir_interpolator.cc:37-61",
+                              "tol": 0.004}
+    return k
+
+
+def fixtures():
+    import refharness as R
+    from grb200 import synth
+    fx = {}
+    rng = np.random.default_rng(20261018)
+
+    def crandn(n):
+        return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+    # a1: fir_filter_ccf, 64 taps, decim 4 (cfg1 shape, small), SSE and generic witnesses
+    taps = rng.uniform(-1, 1, 64).astype(np.float32)
+    x = crandn(4096)
+    fx["fir_ccf_taps"], fx["fir_ccf_x"] = taps, x
+    for impl, nm in ((1, "sse"), (0, "generic")):
+        R.set_fir_impl(impl)
+        fx["fir_ccf_y_" + nm] = R.run_sync(R.fir_filter_ccf(4, taps), x, decim=4)
+    # a2: fir_filter_fff RRC
+    rrc = R.firdes_root_raised_cosine(1.0, 12500.0, 4800.0, 0.2, 29)
+    xf = rng.standard_normal(3000).astype(np.float32)
+    fx["fir_fff_taps"], fx["fir_fff_x"] = rrc, xf
+    for impl, nm in ((1, "sse"), (0, "generic")):
+        R.set_fir_impl(impl)
+        fx["fir_fff_y_" + nm] = R.run_sync(R.fir_filter_fff(1, rrc), xf)
+    R.set_fir_impl(1)
+    # a3: freq_xlating_fir_filter_ccf
+    proto = R.firdes_low_pass(1.0, 2e6, 6000.0, 4000.0)[:257]
+    xx = crandn(8192)
+    fx["fx_proto"], fx["fx_x"] = proto, xx
+    fx["fx_args"] = np.array([16, 250e3, 2e6])
+    fx["fx_y"] = R.run_sync(R.freq_xlating_fir_filter_ccf(16, proto, 250e3, 2e6), xx, decim=16)
+    # a4: pfb channelizer: M=160 T=16 (cfg3 shape), M=20 ragged taps, M=8 oversampled x2
+    for tag, M, ntaps, osr, rows in (("m160", 160, 2560, 1.0, 40), ("m20", 20, 173, 1.0, 64), ("m8os2", 8, 32, 2.0, 48),
+                                     ("m10os5", 10, 57, 5.0, 30)):
+        t = (rng.standard_normal(ntaps) / ntaps).astype(np.float32)
+        xin = crandn(M * rows)
+        y, c = R.run_pfb(R.pfb_channelizer_ccf(M, t, osr), xin, M)
+        fx["pfb_%s_taps" % tag], fx["pfb_%s_x" % tag], fx["pfb_%s_y" % tag] = t, xin, y
+        fx["pfb_%s_meta" % tag] = np.array([M, osr, c])
+    # a6: fft_vcc 4096 Blackman-Harris (window from gr_firdes::window, recorded choice), fwd shift on/off
+    w = R.firdes_window(R.WIN_BLACKMAN_HARRIS, 4096)
+    xv = crandn(4096 * 2)
+    fx["fft4096_win"], fx["fft4096_x"] = w, xv
+    fx["fft4096_y"] = R.run_sync(R.fft_vcc(4096, True, w, False), xv, vlen_in=4096)
+    fx["fft4096_y_shift"] = R.run_sync(R.fft_vcc(4096, True, w, True), xv, vlen_in=4096)
+    xs = crandn(160 * 3)
+    fx["fft160_x"] = xs
+    fx["fft160_y_inv_shift"] = R.run_sync(R.fft_vcc(160, False, [], True), xs, vlen_in=160)
+    # a7/a8: quadrature demod + fast atan2 (incl. axes, zeros, tiny ratios, octant edges)
+    yy = np.concatenate([rng.standard_normal(4000), [0, 0, 1, -1, 0, 0, 1e-3, 1, -1, 1, 3e-3, 1.0]]).astype(np.float32)
+    xa = np.concatenate([rng.standard_normal(4000), [0, 1, 0, 0, -1, -0.0, 1, 1e-3, -1, -1, 1.0, 3.9e-3]]).astype(np.float32)
+    fx["atan_y"], fx["atan_x"], fx["atan_out"] = yy, xa, R.fast_atan2f(yy, xa)
+    xq = crandn(5000)
+    fx["quad_x"], fx["quad_gain"] = xq, np.float32(12500.0 / (2 * np.pi * 648.0))
+    fx["quad_y"] = R.run_sync(R.quadrature_demod_cf(float(fx["quad_gain"])), xq)
+    # a9/a10: M&M on a noisy 4-level signal at 2.604 sps, SSE + generic
+    sym = rng.integers(0, 4, 1500) * 2 - 3
+    sig = synth.shape_symbols(sym, 12500.0 / 4800.0, rrc) + 0.05 * rng.standard_normal(int(1500 * 12500 / 4800) + 1)[: None]
+    sig = sig.astype(np.float32)
+    fx["mm_x"] = sig
+    fx["mm_args"] = np.array([12500.0 / 4800.0, 0.25 * 0.175 * 0.175, 0.5, 0.175, 0.005], np.float32)
+    for impl, nm in ((1, "sse"), (0, "generic")):
+        R.set_fir_impl(impl)
+        o, c = R.run_mm(R.clock_recovery_mm_ff(*[float(v) for v in fx["mm_args"]]), sig)
+        fx["mm_y_" + nm], fx["mm_consumed_" + nm] = o, np.int64(c)
+    R.set_fir_impl(1)
+    # a11: 4-level slicer with and without DC tracking
+    sl = (rng.standard_normal(2000) * 2.0).astype(np.float32)
+    fx["slicer_x"] = sl
+    fx["slicer_y_a0"] = R.run_sync(R.pager_slicer_fb(0.0), sl)
+    fx["slicer_y_a01"] = R.run_sync(R.pager_slicer_fb(0.01), sl)
+    # a13: correlator with a 48-bit DMR-style sync word and threshold 2
+    code = synth.DMR_BS_DATA_SYNC_BITS
+    bits = rng.integers(0, 2, 3000).astype(np.uint8)
+    for pos in (100, 1000, 2500):
+        bits[pos:pos + 48] = code
+    bits[1010] ^= 1
+    bits[2503] ^= 1; bits[2520] ^= 1; bits[2530] ^= 1
+    fx["corr_bits"] = bits
+    fx["corr_out_t2"] = R.run_sync(R.correlate_access_code_bb("".join(str(b) for b in code), 2), bits)
+    return fx
+
+
+def main():
+    with open(os.path.join(HERE, "kats.json"), "w") as f:
+        json.dump(kats(), f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "ref_fixtures.npz"), **fixtures())
+    print("wrote kats.json, ref_fixtures.npz",
+          os.path.getsize(os.path.join(HERE, "ref_fixtures.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
