@@ -1,0 +1,222 @@
+// Batched shared-memory FFT engine (device side).  Replaces gri_fft_complex::execute +
+// the window / fftshift loops of gr_fft_vcc_fftw::work
+// (gnuradio-core/src/lib/general/gri_fft.cc:142-146, gr_fft_vcc_fftw.cc:64-96) and the
+// M-point despinning FFT of gr_pfb_channelizer_ccf::general_work (gr_pfb_channelizer_ccf.cc:193).
+//
+// Algorithm: Stockham autosort, decimation in time, up to FFT_MAX_PASSES passes of radix
+// R_p in {2,3,4,5,8,10,16,20}.  Pass p (Ns = R_0*...*R_{p-1}) for butterfly j in [0, N/R):
+//     k = j mod Ns;  v[r] = src[j + r*N/R] * W_{Ns*R}^{k*r};  v = DFT_R(v);
+//     dst[(j-k)*R + k + r*Ns] = v[r]
+// The first pass reads straight from HBM (coalesced: consecutive j), applies the window /
+// ifftshift; the last pass writes straight to HBM (coalesced) with the fftshift rotation;
+// only the passes in between touch shared memory, in place, one row = N (+ padding) float2.
+// One thread owns one butterfly per pass, so a row lives in registers across each barrier.
+//
+// HBM traffic = 8 B read + 8 B written per point: the algorithmic minimum (16 B/sample).
+#pragma once
+#include "fft_radix.cuh"
+
+namespace grb {
+
+#define FFT_MAX_PASSES 6
+
+struct FftArgs {
+  const float2* in;      // [nrows][N]
+  float2* out;           // [nrows][N]
+  long nrows;
+  const float* window;   // N floats or nullptr (gr_fft_vcc_fftw.cc:68-72)
+  int in_rot;            // src element = in[(i + in_rot) % N]   (ifftshift, :74-79)
+  int out_rot;           // out[(o + out_rot) % N] = X[o]        (fftshift, :89-93)
+  const float2* tw[FFT_MAX_PASSES];  // per pass: Ns entries e^{DIR 2 pi j k/(Ns R)}
+  int n;                 // N
+  int npass;
+  int radix[FFT_MAX_PASSES];
+  int rows_per_cta;
+  int threads_per_row;
+  int row_stride;        // smem float2 per row (N + padding)
+  int pad_div;           // phys(i) = i + i / pad_div  (0 = no padding)
+};
+
+__device__ __forceinline__ int fft_phys(int i, int pad_div) { return pad_div ? i + i / pad_div : i; }
+
+template <int PADDIV> __device__ __forceinline__ int fft_phys_c(int i) { return PADDIV ? i + i / (PADDIV ? PADDIV : 1) : i; }
+
+// ---- one pass, compile-time radix; N / Ns may be compile-time (fixed kernels) or runtime ------
+template <int R, int DIR, bool FROM_GLOBAL, bool TO_GLOBAL, int PADDIV>
+__device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j, bool row_ok, long row,
+                                         float2* __restrict__ srow, const float2* __restrict__ tw) {
+  const int nb = N / R;
+  const bool active = row_ok && j < nb;
+  float2 v[R];
+  if (active) {
+    if (FROM_GLOBAL) {
+      const float2* __restrict__ g = a.in + row * (long)N;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int i = j + r * nb;
+        int gi = i + a.in_rot;
+        if (gi >= N) gi -= N;
+        float2 x = __ldg(g + gi);
+        if (a.window) {
+          const float w = __ldg(a.window + i);
+          x.x *= w;
+          x.y *= w;
+        }
+        v[r] = x;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = srow[fft_phys_c<PADDIV>(j + r * nb)];
+    }
+  }
+  if (!FROM_GLOBAL && !TO_GLOBAL) __syncthreads();  // in-place: every read precedes every write
+  if (active) {
+    const int k = j % Ns;
+    if (Ns > 1) apply_twiddle_powers<R>(v, __ldg(tw + k));
+    butterfly<R, DIR>(v);
+    const int o0 = (j - k) * R + k;
+    if (TO_GLOBAL) {
+      float2* __restrict__ g = a.out + row * (long)N;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        int o = o0 + r * Ns + a.out_rot;
+        if (o >= N) o -= N;
+        g[o] = v[r];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; r++) srow[fft_phys_c<PADDIV>(o0 + r * Ns)] = v[r];
+    }
+  }
+  if (!TO_GLOBAL) __syncthreads();
+}
+
+// ---- fixed plans: N = R0*R1*R2 (R1, R2 may be 1) -----------------------------------------------
+template <int DIR, int R0, int R1, int R2>
+__global__ void __launch_bounds__(512) fft_fixed_kernel(const FftArgs a) {
+  constexpr int N = R0 * R1 * R2;
+  constexpr int NP = (R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1);
+  constexpr int PADDIV = (NP > 1 && (R0 % 2 == 0)) ? R0 : 0;
+  extern __shared__ float2 fft_smem[];
+  const int tpr = a.threads_per_row;
+  const int lrow = threadIdx.x / tpr;
+  const int j = threadIdx.x - lrow * tpr;
+  float2* srow = fft_smem + (size_t)lrow * a.row_stride;
+  const long ngroups = (a.nrows + a.rows_per_cta - 1) / a.rows_per_cta;
+  for (long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const long row = g * a.rows_per_cta + lrow;
+    const bool row_ok = lrow < a.rows_per_cta && row < a.nrows;
+    if (NP == 1) {
+      fft_pass<R0, DIR, true, true, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
+    } else if (NP == 2) {
+      fft_pass<R0, DIR, true, false, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
+      fft_pass<R1, DIR, false, true, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
+      __syncthreads();  // next group's pass 0 overwrites the rows read above
+    } else {
+      fft_pass<R0, DIR, true, false, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
+      fft_pass<R1, DIR, false, false, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
+      fft_pass<R2, DIR, false, true, PADDIV>(a, N, R0 * R1, j, row_ok, row, srow, a.tw[2]);
+      __syncthreads();
+    }
+  }
+}
+
+// ---- generic plan: runtime radices, ping-pong rows, any thread count ---------------------------
+template <int R, int DIR>
+__device__ __forceinline__ void fft_generic_pass(const FftArgs& a, int p, int Ns, long row, const float2* src,
+                                                 float2* dst, bool from_global, bool to_global, int j0, int jstep) {
+  const int N = a.n, nb = N / R;
+  for (int j = j0; j < nb; j += jstep) {
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int i = j + r * nb;
+      if (from_global) {
+        int gi = i + a.in_rot;
+        if (gi >= N) gi -= N;
+        float2 x = __ldg(a.in + row * (long)N + gi);
+        if (a.window) { const float w = __ldg(a.window + i); x.x *= w; x.y *= w; }
+        v[r] = x;
+      } else {
+        v[r] = src[i];
+      }
+    }
+    const int k = j % Ns;
+    if (Ns > 1) apply_twiddle_powers<R>(v, __ldg(a.tw[p] + k));
+    butterfly<R, DIR>(v);
+    const int o0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (to_global) {
+        int o = o0 + r * Ns + a.out_rot;
+        if (o >= N) o -= N;
+        a.out[row * (long)N + o] = v[r];
+      } else {
+        dst[o0 + r * Ns] = v[r];
+      }
+    }
+  }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256) fft_generic_kernel(const FftArgs a) {
+  extern __shared__ float2 fft_smem[];
+  const int tpr = a.threads_per_row;
+  const int lrow = threadIdx.x / tpr;
+  const int j0 = threadIdx.x - lrow * tpr;
+  float2* buf0 = fft_smem + (size_t)lrow * 2 * a.n;
+  float2* buf1 = buf0 + a.n;
+  const long ngroups = (a.nrows + a.rows_per_cta - 1) / a.rows_per_cta;
+  for (long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const long row = g * a.rows_per_cta + lrow;
+    const bool row_ok = lrow < a.rows_per_cta && row < a.nrows;
+    int Ns = 1;
+    float2* src = buf0;
+    float2* dst = buf1;
+    for (int p = 0; p < a.npass; p++) {
+      const bool fg = (p == 0), tg = (p == a.npass - 1);
+      if (row_ok) {
+        switch (a.radix[p]) {
+          case 2: fft_generic_pass<2, DIR>(a, p, Ns, row, src, dst, fg, tg, j0, tpr); break;
+          case 3: fft_generic_pass<3, DIR>(a, p, Ns, row, src, dst, fg, tg, j0, tpr); break;
+          case 4: fft_generic_pass<4, DIR>(a, p, Ns, row, src, dst, fg, tg, j0, tpr); break;
+          case 5: fft_generic_pass<5, DIR>(a, p, Ns, row, src, dst, fg, tg, j0, tpr); break;
+          case 8: fft_generic_pass<8, DIR>(a, p, Ns, row, src, dst, fg, tg, j0, tpr); break;
+          default: break;
+        }
+      }
+      Ns *= a.radix[p];
+      __syncthreads();
+      float2* t = src; src = dst; dst = t;
+    }
+  }
+}
+
+// ---- fallback for lengths with a prime factor > 5: direct O(N^2) DFT, one thread per output ---
+// tw[0] = e^{DIR 2 pi j k / N}, k in [0, N).
+template <int DIR>
+__global__ void fft_naive_kernel(const FftArgs a) {
+  const int N = a.n;
+  for (long row = blockIdx.y; row < a.nrows; row += gridDim.y) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+      float2 acc = make_float2(0.f, 0.f);
+      int idx = 0;
+      for (int n = 0; n < N; n++) {
+        int gi = n + a.in_rot;
+        if (gi >= N) gi -= N;
+        float2 x = __ldg(a.in + row * (long)N + gi);
+        if (a.window) { const float w = __ldg(a.window + n); x.x *= w; x.y *= w; }
+        const float2 w = __ldg(a.tw[0] + idx);
+        acc.x += x.x * w.x - x.y * w.y;
+        acc.y += x.x * w.y + x.y * w.x;
+        idx += k;
+        if (idx >= N) idx -= N;
+      }
+      int o = k + a.out_rot;
+      if (o >= N) o -= N;
+      a.out[row * (long)N + o] = acc;
+    }
+  }
+}
+
+}  // namespace grb

@@ -1,0 +1,231 @@
+// Per-thread arithmetic of the demod tail, written once for device code (and compiled for the
+// host by tests/emul, which replays single "threads" on the CPU to check the logic without a GPU;
+// the product never runs these on the host).
+//
+// Everything here that feeds a slicer decision reproduces the reference's float arithmetic
+// operation by operation: separate IEEE multiply and add (never an FMA), the reference's
+// summation trees and its two lookup tables (SURVEY.md section 7 "Bit-exact demod").
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define GR_HD __host__ __device__ __forceinline__
+
+#ifdef __CUDA_ARCH__
+#define GR_FMUL(a, b) __fmul_rn((a), (b))
+#define GR_FADD(a, b) __fadd_rn((a), (b))
+#define GR_FSUB(a, b) __fsub_rn((a), (b))
+#define GR_FDIV(a, b) __fdiv_rn((a), (b))
+#else  // host emulation: the TU is compiled with -ffp-contract=off
+#define GR_FMUL(a, b) ((float)(a) * (float)(b))
+#define GR_FADD(a, b) ((float)(a) + (float)(b))
+#define GR_FSUB(a, b) ((float)(a) - (float)(b))
+#define GR_FDIV(a, b) ((float)(a) / (float)(b))
+#endif
+
+#define GR_ORDER_GENERIC 0
+#define GR_ORDER_SSE 1
+
+namespace grb {
+
+// ---- gr_fast_atan2f (gnuradio-core/src/lib/general/gr_fast_atan2f.cc:125-198) ---------------
+// `table` = the reference's 257-entry arctangent table (build/generated/gr_tables.h).
+GR_HD float fast_atan2f(float y, float x, const float* __restrict__ table) {
+  if (y == 0.0f && x == 0.0f) return 0.0f;  // :131-132
+  const float y_abs = fabsf(y), x_abs = fabsf(x);
+  const float z = (y_abs < x_abs) ? GR_FDIV(y_abs, x_abs) : GR_FDIV(x_abs, y_abs);  // :138-141
+  float base_angle;
+  if ((double)z < 0.003921569) {  // TAN_MAP_RES is a double literal (:32,147)
+    base_angle = z;
+  } else {
+    // alpha = z*256 - .5 is evaluated in double and stored to float (:151); z*256 is exact and
+    // the float subtraction rounds the same exact value once, so this is bit identical.
+    float alpha = GR_FSUB(GR_FMUL(z, 256.0f), 0.5f);
+    const int index = (int)alpha;
+    alpha = GR_FSUB(alpha, (float)index);
+    const float t0 = table[index], t1 = table[index + 1];
+    base_angle = GR_FADD(t0, GR_FMUL(GR_FSUB(t1, t0), alpha));  // :155-157
+  }
+  float angle;
+  if (x_abs > y_abs) {  // :160-171
+    if (x >= 0.0f) {
+      angle = (y >= 0.0f) ? base_angle : -base_angle;
+    } else {
+      const float pi = 3.14159265358979323846f;
+      angle = (y >= 0.0f) ? GR_FSUB(pi, base_angle) : GR_FSUB(base_angle, pi);
+    }
+  } else {  // :172-186
+    const float hp = 1.57079632679489661923f;
+    if (y >= 0.0f) angle = (x >= 0.0f) ? GR_FSUB(hp, base_angle) : GR_FADD(hp, base_angle);
+    else angle = (x >= 0.0f) ? GR_FADD(-hp, base_angle) : GR_FSUB(-hp, base_angle);
+  }
+  return angle;
+}
+
+// gr_quadrature_demod_cf::work (gr_quadrature_demod_cf.cc:56-59):
+// product = cur * conj(prev) expanded as gcc expands std::complex<float> operator*.
+GR_HD float quad_demod(float2 cur, float2 prev, float gain, const float* __restrict__ table) {
+  const float cr = prev.x, ci = -prev.y;
+  const float re = GR_FSUB(GR_FMUL(cur.x, cr), GR_FMUL(cur.y, ci));
+  const float im = GR_FADD(GR_FMUL(cur.x, ci), GR_FMUL(cur.y, cr));
+  return GR_FMUL(gain, fast_atan2f(im, re, table));
+}
+
+// ---- float dot products in the reference's summation orders ---------------------------------
+// `in` is addressed as in[i * stride]; rt = reversed taps (gr_fir_XXX.h.t:51,65).
+// generic: gr_fir_XXX_generic.cc.t:28-55.
+GR_HD float dot_generic(const float* __restrict__ rt, int ntaps, const float* __restrict__ in, long stride) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = 0;
+  const int n = ntaps & ~3;
+  for (; i < n; i += 4) {
+    a0 = GR_FADD(a0, GR_FMUL(rt[i], in[(long)i * stride]));
+    a1 = GR_FADD(a1, GR_FMUL(rt[i + 1], in[(long)(i + 1) * stride]));
+    a2 = GR_FADD(a2, GR_FMUL(rt[i + 2], in[(long)(i + 2) * stride]));
+    a3 = GR_FADD(a3, GR_FMUL(rt[i + 3], in[(long)(i + 3) * stride]));
+  }
+  for (; i < ntaps; i++) a0 = GR_FADD(a0, GR_FMUL(rt[i], in[(long)i * stride]));
+  return GR_FADD(GR_FADD(GR_FADD(a0, a1), a2), a3);
+}
+
+// SSE: gr_fir_fff_simd.cc:99-134 + float_dotprod_sse64.S:27-108.  `al` = (absolute index of
+// in[0]) mod 4.  Lane l holds absolute positions == l (mod 4); the first nblocks%4 aligned
+// blocks go to accumulator 0, the rest round-robin over accumulators 0..3; the four
+// accumulators are combined as (a0+a1)+(a3+a2) only when at least one full group of four
+// blocks ran, then lanes as (d0+d2)+(d1+d3).  Zero-tap positions contribute +-0 and are skipped.
+GR_HD float dot_sse(const float* __restrict__ rt, int ntaps, const float* __restrict__ in, long stride, int al) {
+  if (ntaps == 0) return 0.0f;
+  const int nblocks = (ntaps + al - 1) / 4 + 1;
+  const int nrem = nblocks & 3;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) acc[a][l] = 0.f;
+  int b = 0;
+  for (; b < nrem; b++) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int i = b * 4 + l - al;
+      if (i >= 0 && i < ntaps) acc[0][l] = GR_FADD(acc[0][l], GR_FMUL(rt[i], in[(long)i * stride]));
+    }
+  }
+  for (; b < nblocks; b += 4) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const int i = (b + a) * 4 + l - al;
+        if (i >= 0 && i < ntaps) acc[a][l] = GR_FADD(acc[a][l], GR_FMUL(rt[i], in[(long)i * stride]));
+      }
+    }
+  }
+  float d[4];
+  const bool grouped = (nblocks >> 2) != 0;
+#pragma unroll
+  for (int l = 0; l < 4; l++)
+    d[l] = grouped ? GR_FADD(GR_FADD(acc[0][l], acc[1][l]), GR_FADD(acc[3][l], acc[2][l])) : acc[0][l];
+  return GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3]));
+}
+
+GR_HD int mod4(long a) { return (int)(a & 3); }  // two's complement: correct for negative a
+
+// ---- 8-tap MMSE interpolator (gri_mmse_fir_interpolator.cc:61-71) ---------------------------
+// c[0..7] = coefficients applied to v[0..7] (= reference taps[imu][7-i]); v[i] = in[ii+i].
+GR_HD float mmse8(const float c[8], const float v[8], int order, int al) {
+  float p[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) p[i] = GR_FMUL(c[i], v[i]);
+  if (order == GR_ORDER_GENERIC) {
+    const float a0 = GR_FADD(p[0], p[4]), a1 = GR_FADD(p[1], p[5]);
+    const float a2 = GR_FADD(p[2], p[6]), a3 = GR_FADD(p[3], p[7]);
+    return GR_FADD(GR_FADD(GR_FADD(a0, a1), a2), a3);
+  }
+  // SSE order.  Element i sits in lane (i+al)&3 of block (i+al)>>2; nblocks = 2 (al=0) or 3,
+  // always < 4, so every block accumulates into xmm4 in order and the result is (d0+d2)+(d1+d3).
+  float d[4];
+  if (al == 0) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) d[l] = GR_FADD(p[l], p[l + 4]);
+  } else {
+    // lanes: block0 has lanes al..3 (elements 0..3-al), block1 elements 4-al..7-al, block2 the rest
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int i0 = l - al, i1 = l + 4 - al, i2 = l + 8 - al;
+      float s = 0.f;
+      bool first = true;
+      if (i0 >= 0) { s = p[i0]; first = false; }
+      if (i1 >= 0 && i1 < 8) { s = first ? p[i1] : GR_FADD(s, p[i1]); first = false; }
+      if (i2 < 8) { s = first ? p[i2] : GR_FADD(s, p[i2]); }
+      d[l] = s;
+    }
+  }
+  return GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3]));
+}
+
+// ---- Mueller & Mueller loop state (digital_clock_recovery_mm_ff.cc:102-139) ------------------
+struct MMParams {
+  float gain_omega, gain_mu, omega_mid, omega_relative_limit;
+};
+struct MMState {
+  float mu, omega, last_sample;
+};
+GR_HD float slice_pm1(float x) { return x < 0.f ? -1.0f : 1.0f; }  // :89-93
+GR_HD float branchless_clip(float x, float clip) {                 // gr_math.h:63-69
+  const float x1 = fabsf(GR_FADD(x, clip));
+  const float x2 = fabsf(GR_FSUB(x, clip));
+  return GR_FMUL(0.5f, GR_FSUB(x1, x2));  // 0.5*x1 in double then to float: exact either way
+}
+// One loop iteration after out = interp(&in[ii], mu): returns the input advance floor(mu).
+GR_HD int mm_update(MMState& s, const MMParams& p, float out) {
+  const float mm_val = GR_FSUB(GR_FMUL(slice_pm1(s.last_sample), out), GR_FMUL(slice_pm1(out), s.last_sample));
+  s.last_sample = out;
+  s.omega = GR_FADD(s.omega, GR_FMUL(p.gain_omega, mm_val));
+  s.omega = GR_FADD(p.omega_mid, branchless_clip(GR_FSUB(s.omega, p.omega_mid), p.omega_relative_limit));
+  s.mu = GR_FADD(GR_FADD(s.mu, s.omega), GR_FMUL(p.gain_mu, mm_val));
+  const float fl = floorf(s.mu);
+  s.mu = GR_FSUB(s.mu, fl);
+  return (int)fl;
+}
+GR_HD int mm_imu(float mu) {  // (int) rint(mu * NSTEPS), round half to even (:64)
+#ifdef __CUDA_ARCH__
+  return __float2int_rn(GR_FMUL(mu, 128.0f));
+#else
+  return (int)rintf(mu * 128.0f);
+#endif
+}
+
+// ---- slicers ----------------------------------------------------------------------------------
+// pager_slicer_fb::slice (gr-pager/lib/pager_slicer_fb.cc:47-69)
+GR_HD unsigned char slice4(float sample, float& avg, float alpha, float beta) {
+  avg = GR_FADD(GR_FMUL(avg, beta), GR_FMUL(sample, alpha));
+  sample = GR_FSUB(sample, avg);
+  if (sample > 0.f) return sample > 2.0f ? 3 : 2;
+  return sample < -2.0f ? 0 : 1;
+}
+GR_HD unsigned char slice2(float x) { return x >= 0.f ? 1 : 0; }  // gr_math.h:82-88
+
+// ---- access-code correlator step (digital_correlate_access_code_bb.cc:97-130) -----------------
+struct CorrParams {
+  unsigned long long access_code, mask, flag_bit;
+  unsigned threshold;
+};
+GR_HD unsigned popc64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+  return (unsigned)__popcll(x);
+#else
+  return (unsigned)__builtin_popcountll(x);
+#endif
+}
+GR_HD unsigned char corr_step(unsigned long long& data_reg, unsigned long long& flag_reg, const CorrParams& p,
+                              unsigned bit) {
+  const unsigned char t = (unsigned char)(((data_reg >> 63) & 1ull) | (((flag_reg >> 63) & 1ull) << 1));
+  const unsigned nwrong = popc64((data_reg ^ p.access_code) & p.mask);
+  data_reg = (data_reg << 1) | (unsigned long long)(bit & 1u);
+  flag_reg <<= 1;
+  if (nwrong <= p.threshold) flag_reg |= p.flag_bit;
+  return t;
+}
+
+}  // namespace grb

@@ -1,0 +1,285 @@
+/* libgr_cuda -- C ABI of the B200-native channelize + DMR-demod hot path.
+ *
+ * This header is the drop-in boundary: every entry point is what a
+ * GNU Radio 3.5 block on this path would bind instead of its CPU primitive.  Plain pointers
+ * and sizes only; no C++ / torch types; no exception crosses the ABI.
+ *
+ * Conventions
+ *  - Every block family is an opaque plan handle: *_create / *_destroy / setters / getters /
+ *    *_work (HOST pointers, reference buffer layout, staged through pinned double buffers) /
+ *    *_work_device (DEVICE pointers, same layout, for HBM-resident pipelines).
+ *  - Buffer layout = the reference runtime's: the input pointer addresses the first HISTORY
+ *    item, i.e. history()-1 items before the first new item
+ *    (gnuradio-core/src/lib/runtime/gr_flat_flowgraph.cc:150, gr_buffer.cc:201-214).
+ *  - *_work returns the number of items produced (>= 0) or a negative GRCUDA_E* code.
+ *    Setters are thread safe and take effect at the next work() boundary; the first work()
+ *    after set_taps returns 0 exactly like the reference ("history requirements may have
+ *    changed", gr_fir_filter_XXX.cc.t:74-79, gr_pfb_channelizer_ccf.cc:164-167).
+ *  - *_create returns NULL on error; grcuda_last_error() / grcuda_last_error_code() tell why.
+ *    GRCUDA_EINVAL maps to std::invalid_argument, GRCUDA_ERANGE to std::out_of_range,
+ *    GRCUDA_ECUDA to std::runtime_error in the C++ block wrappers (blocks/gr_b200_blocks.h).
+ *  - `stream` arguments are cudaStream_t passed as void* (NULL = the plan's own stream).
+ *  - There is NO CPU fallback: without a CUDA device every create/work fails with GRCUDA_ECUDA.
+ */
+#ifndef INCLUDED_GR_CUDA_H
+#define INCLUDED_GR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRCUDA_OK 0
+#define GRCUDA_EINVAL (-1) /* std::invalid_argument in the reference */
+#define GRCUDA_ERANGE (-2) /* std::out_of_range in the reference */
+#define GRCUDA_ECUDA (-3)  /* CUDA runtime / launch failure, or no device */
+#define GRCUDA_ENOMEM (-4)
+#define GRCUDA_EUNSUPPORTED (-5)
+
+/* summation order of the float dot products in the demod tail (see oracle/oracle.h) */
+#define GRCUDA_ORDER_GENERIC 0 /* gr_fir_fff_generic: 4 accumulators, ((a0+a1)+a2)+a3 */
+#define GRCUDA_ORDER_SSE 1     /* float_dotprod_sse64.S order = what x86-64 GNU Radio runs */
+
+typedef struct { float re, im; } grcuda_complex; /* == gr_complex (runtime/gr_complex.h:26) */
+
+/* ---- library / device -------------------------------------------------------------------- */
+const char* grcuda_version(void);
+const char* grcuda_last_error(void);
+int grcuda_last_error_code(void);
+int grcuda_device_count(void);
+int grcuda_set_device(int device);
+int grcuda_device_synchronize(void);
+/* device / pinned memory helpers for HBM-resident callers that do not use torch */
+void* grcuda_malloc_device(size_t bytes);
+void grcuda_free_device(void* p);
+void* grcuda_malloc_pinned(size_t bytes);
+void grcuda_free_pinned(void* p);
+int grcuda_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int grcuda_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int grcuda_stream_synchronize(void* stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long grcuda_kernel_launch_count(void);
+/* CUDA IPC: export / open a device allocation in another process of the same node (multi-GPU
+ * shards exchange halos and results through peer memory). handle = 64 bytes. */
+int grcuda_ipc_export(void* dptr, unsigned char handle[64]);
+void* grcuda_ipc_open(const unsigned char handle[64]);
+int grcuda_ipc_close(void* dptr);
+
+/* ---- a1  gr_fir_filter_ccf -----------------------------------------------------------------
+ * replaces gr_fir_filter_ccf / gr_fir_ccf{,_simd,_x86} + fcomplex_dotprod_sse64.S
+ * (gnuradio-core/src/lib/filter/gr_fir_filter_XXX.cc.t:37-88, gr_fir_ccf_simd.cc:101-141).
+ * out[i] = sum_k taps[k] * x[i*D - k];  history = ntaps. */
+typedef struct grcuda_fir_ccf grcuda_fir_ccf;
+grcuda_fir_ccf* grcuda_fir_filter_ccf_create(int decimation, const float* taps, int ntaps);
+void grcuda_fir_filter_ccf_destroy(grcuda_fir_ccf* h);
+int grcuda_fir_filter_ccf_set_taps(grcuda_fir_ccf* h, const float* taps, int ntaps);
+unsigned grcuda_fir_filter_ccf_history(grcuda_fir_ccf* h);
+int grcuda_fir_filter_ccf_decimation(grcuda_fir_ccf* h);
+int grcuda_fir_filter_ccf_work(grcuda_fir_ccf* h, int noutput_items, const grcuda_complex* in, grcuda_complex* out);
+int grcuda_fir_filter_ccf_work_device(grcuda_fir_ccf* h, long noutput_items, const grcuda_complex* d_in,
+                                      grcuda_complex* d_out, void* stream);
+
+/* ---- a2  gr_fir_filter_fff -----------------------------------------------------------------
+ * replaces gr_fir_filter_fff / gr_fir_fff{,_simd} + float_dotprod_sse64.S
+ * (gr_fir_fff_simd.cc:99-134).  `order` selects the reference summation order reproduced
+ * bit for bit; `abs_index0` = absolute stream index of in[0] (the SSE order depends on it). */
+typedef struct grcuda_fir_fff grcuda_fir_fff;
+grcuda_fir_fff* grcuda_fir_filter_fff_create(int decimation, const float* taps, int ntaps, int order);
+void grcuda_fir_filter_fff_destroy(grcuda_fir_fff* h);
+int grcuda_fir_filter_fff_set_taps(grcuda_fir_fff* h, const float* taps, int ntaps);
+unsigned grcuda_fir_filter_fff_history(grcuda_fir_fff* h);
+int grcuda_fir_filter_fff_work(grcuda_fir_fff* h, int noutput_items, const float* in, float* out, long abs_index0);
+/* batched: nchan independent streams laid out [time][channel] (row stride = nchan floats) */
+int grcuda_fir_filter_fff_work_device(grcuda_fir_fff* h, long noutput_items, int nchan, const float* d_in,
+                                      float* d_out, long abs_index0, void* stream);
+
+/* ---- a3  gr_freq_xlating_fir_filter_ccf ----------------------------------------------------
+ * replaces gr_freq_xlating_fir_filter_ccf + gr_fir_ccc + gr_rotator
+ * (gr_freq_xlating_fir_filter_XXX.cc.t:38-123, gr_rotator.h:40-50). */
+typedef struct grcuda_fxlat grcuda_fxlat;
+grcuda_fxlat* grcuda_freq_xlating_fir_filter_ccf_create(int decimation, const float* taps, int ntaps,
+                                                       double center_freq, double sampling_freq);
+void grcuda_freq_xlating_fir_filter_ccf_destroy(grcuda_fxlat* h);
+int grcuda_freq_xlating_fir_filter_ccf_set_taps(grcuda_fxlat* h, const float* taps, int ntaps);
+int grcuda_freq_xlating_fir_filter_ccf_set_center_freq(grcuda_fxlat* h, double center_freq);
+unsigned grcuda_freq_xlating_fir_filter_ccf_history(grcuda_fxlat* h);
+int grcuda_freq_xlating_fir_filter_ccf_work(grcuda_fxlat* h, int noutput_items, const grcuda_complex* in,
+                                            grcuda_complex* out);
+int grcuda_freq_xlating_fir_filter_ccf_work_device(grcuda_fxlat* h, long noutput_items, const grcuda_complex* d_in,
+                                                   grcuda_complex* d_out, void* stream);
+
+/* ---- a4/a5/a14  gr_pfb_channelizer_ccf -----------------------------------------------------
+ * replaces gr_pfb_channelizer_ccf::general_work, its numchans gr_fir_ccf objects and the
+ * FFTW-backed gri_fft_complex (gr_pfb_channelizer_ccf.cc:35-200, gri_fft.cc:97-146).
+ * create() fails with GRCUDA_EINVAL when numchans/oversample_rate is not an integer (:57-60).
+ * history = taps_per_filter + 1, output_multiple and relative_rate as the reference computes. */
+typedef struct grcuda_pfb grcuda_pfb;
+grcuda_pfb* grcuda_pfb_channelizer_ccf_create(unsigned numchans, const float* taps, int ntaps, float oversample_rate);
+void grcuda_pfb_channelizer_ccf_destroy(grcuda_pfb* h);
+int grcuda_pfb_channelizer_ccf_set_taps(grcuda_pfb* h, const float* taps, int ntaps);
+unsigned grcuda_pfb_channelizer_ccf_history(grcuda_pfb* h);
+int grcuda_pfb_channelizer_ccf_output_multiple(grcuda_pfb* h);
+double grcuda_pfb_channelizer_ccf_relative_rate(grcuda_pfb* h);
+int grcuda_pfb_channelizer_ccf_taps_per_filter(grcuda_pfb* h);
+/* general_work: `in` = numchans host stream pointers (each history-prefixed), out = one stream
+ * of numchans-wide vectors; *consumed = items consumed per input stream. */
+int grcuda_pfb_channelizer_ccf_work(grcuda_pfb* h, int noutput_items, const grcuda_complex* const* in,
+                                    grcuda_complex* out, int* consumed);
+/* blks2.pfb_channelizer_ccf hier-block form (blks2impl/pfb_channelizer.py:61-75): ONE
+ * interleaved wideband stream in (what gr_stream_to_streams would split), [time][channel] out.
+ * `in` addresses the first history ROW ((history-1) rows of numchans items before the new rows). */
+int grcuda_pfb_channelizer_ccf_work_interleaved(grcuda_pfb* h, int noutput_items, const grcuda_complex* in,
+                                                grcuda_complex* out, int* consumed);
+int grcuda_pfb_channelizer_ccf_work_device(grcuda_pfb* h, long noutput_items, const grcuda_complex* d_in_rows,
+                                           grcuda_complex* d_out, void* stream);
+
+/* ---- a5/a6  gr_fft_vcc ---------------------------------------------------------------------
+ * replaces gr_fft_vcc_fftw::work + gri_fft_complex (gr_fft_vcc_fftw.cc:51-103, gr_fft_vcc.cc:34-64).
+ * fft_size <= 0 -> GRCUDA_ERANGE (gri_fft.cc:104-105). set_window returns 0 (false) unless the
+ * window is empty or fft_size long (gr_fft_vcc.cc:55-64). */
+typedef struct grcuda_fft grcuda_fft;
+grcuda_fft* grcuda_fft_vcc_create(int fft_size, int forward, const float* window, int nwindow, int shift);
+void grcuda_fft_vcc_destroy(grcuda_fft* h);
+int grcuda_fft_vcc_set_window(grcuda_fft* h, const float* window, int nwindow);
+int grcuda_fft_vcc_work(grcuda_fft* h, int noutput_items, const grcuda_complex* in, grcuda_complex* out);
+int grcuda_fft_vcc_work_device(grcuda_fft* h, long noutput_items, const grcuda_complex* d_in, grcuda_complex* d_out,
+                               void* stream);
+
+/* ---- a7/a8  gr_quadrature_demod_cf (+ gr_fast_atan2f) --------------------------------------
+ * replaces gr_quadrature_demod_cf::work (gr_quadrature_demod_cf.cc:46-62) with the reference's
+ * 257-entry table arctangent (gr_fast_atan2f.cc:125-198), bit exact.  history = 2. */
+typedef struct grcuda_quad grcuda_quad;
+grcuda_quad* grcuda_quadrature_demod_cf_create(float gain);
+void grcuda_quadrature_demod_cf_destroy(grcuda_quad* h);
+int grcuda_quadrature_demod_cf_set_gain(grcuda_quad* h, float gain);
+float grcuda_quadrature_demod_cf_gain(grcuda_quad* h);
+int grcuda_quadrature_demod_cf_work(grcuda_quad* h, int noutput_items, const grcuda_complex* in, float* out);
+/* batched [time][channel]; d_in addresses the history row */
+int grcuda_quadrature_demod_cf_work_device(grcuda_quad* h, long noutput_items, int nchan, const grcuda_complex* d_in,
+                                           float* d_out, void* stream);
+int grcuda_fast_atan2f_device(const float* d_y, const float* d_x, float* d_out, long n, void* stream);
+
+/* ---- a9/a10/a11  digital_clock_recovery_mm_ff (+ gri_mmse_fir_interpolator, slicers) --------
+ * replaces digital_clock_recovery_mm_ff::general_work (digital_clock_recovery_mm_ff.cc:102-139)
+ * and gri_mmse_fir_interpolator::interpolate (gri_mmse_fir_interpolator.cc:61-71), batched over
+ * nchan independent channels.  create() fails with GRCUDA_ERANGE for omega < 1 or negative gains
+ * (:58-61).  The loop state (mu, omega, last_sample, next input index) lives on the device per
+ * channel and persists across work calls, like the block's members do. */
+typedef struct grcuda_mm grcuda_mm;
+grcuda_mm* grcuda_clock_recovery_mm_ff_create(int nchan, float omega, float gain_omega, float mu, float gain_mu,
+                                             float omega_relative_limit, int order);
+void grcuda_clock_recovery_mm_ff_destroy(grcuda_mm* h);
+int grcuda_clock_recovery_mm_ff_forecast(grcuda_mm* h, int noutput_items);
+/* per-channel state readback / overwrite (mirrors mu(), omega(), set_mu(), set_omega()) */
+int grcuda_clock_recovery_mm_ff_get_state(grcuda_mm* h, int chan, float* mu, float* omega, float* last_sample);
+int grcuda_clock_recovery_mm_ff_set_mu(grcuda_mm* h, float mu);
+int grcuda_clock_recovery_mm_ff_set_omega(grcuda_mm* h, float omega);
+int grcuda_clock_recovery_mm_ff_set_gain_mu(grcuda_mm* h, float gain_mu);
+int grcuda_clock_recovery_mm_ff_set_gain_omega(grcuda_mm* h, float gain_omega);
+/* single-stream general_work (nchan must be 1): returns produced, *consumed = items consumed.
+ * abs_index0 = absolute stream index of in[0]. */
+int grcuda_clock_recovery_mm_ff_work(grcuda_mm* h, int noutput_items, int ninput_items, const float* in, float* out,
+                                     int* consumed, long abs_index0);
+/* batched device form.  d_in: [time][channel] floats, ninput rows; row 0 has absolute index
+ * abs_row0.  Channel c starts reading at its own carried position (>= abs_row0) and stops when
+ * fewer than 8 look-ahead rows remain (:112,116).  Symbols are written time-major to
+ * d_out[sym][channel] (row capacity max_out); d_counts[c] receives the number produced.
+ * If d_slice_out != NULL the 4-level (or 2-level) slicer decision is stored alongside. */
+int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long abs_row0, const float* d_in,
+                                            float* d_out, unsigned char* d_slice_out, int max_out, int* d_counts,
+                                            void* stream);
+/* slicer fused into the M&M epilogue: mode 0 none, 2 = gr_binary_slicer (gr_math.h:82-88),
+ * 4 = pager_slicer_fb::slice with DC-tracking alpha (pager_slicer_fb.cc:47-69). */
+int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha);
+
+/* stand-alone slicer blocks (host pointers) */
+typedef struct grcuda_slicer grcuda_slicer;
+grcuda_slicer* grcuda_pager_slicer_fb_create(float alpha);
+grcuda_slicer* grcuda_binary_slicer_fb_create(void);
+void grcuda_slicer_destroy(grcuda_slicer* h);
+float grcuda_pager_slicer_fb_dc_offset(grcuda_slicer* h);
+int grcuda_slicer_work(grcuda_slicer* h, int noutput_items, const float* in, unsigned char* out);
+
+/* ---- a12/a13  gr_map_bb + gr_unpack_k_bits_bb + digital_correlate_access_code_bb ------------
+ * replaces digital_correlate_access_code_bb::work + gr_count_bits64
+ * (digital_correlate_access_code_bb.cc:64-133, gr_count_bits.cc:75-93).  access_code: <= 64
+ * chars, LSB of each char (else GRCUDA_ERANGE, :54-57).  Output byte = data bit delayed 64 |
+ * flag << 1, identical to the reference byte stream; sync hits are also compacted to a list. */
+typedef struct grcuda_corr grcuda_corr;
+grcuda_corr* grcuda_correlate_access_code_bb_create(int nchan, const char* access_code, int threshold);
+void grcuda_correlate_access_code_bb_destroy(grcuda_corr* h);
+int grcuda_correlate_access_code_bb_set_access_code(grcuda_corr* h, const char* access_code);
+int grcuda_correlate_access_code_bb_work(grcuda_corr* h, int noutput_items, const unsigned char* in,
+                                         unsigned char* out);
+/* batched device form fed by the slicer: symbols [sym][channel] (values 0..3, d_counts[c] valid
+ * per channel) -> gr_map_bb(map, nmap) -> gr_unpack_k_bits_bb(bits_per_symbol) -> correlator.
+ * d_out: [bit][channel] bytes (may be NULL to skip the byte stream).  Hits are appended to
+ * d_hits as {channel, absolute bit index of the flagged byte} pairs, *d_nhits counts them. */
+typedef struct { int channel; int pad; long long bit_index; } grcuda_hit;
+int grcuda_correlate_access_code_bb_work_symbols_device(grcuda_corr* h, const unsigned char* d_symbols, int sym_rows,
+                                                        const int* d_counts, const int* map, int nmap,
+                                                        int bits_per_symbol, unsigned char* d_out, int out_rows,
+                                                        grcuda_hit* d_hits, int max_hits, int* d_nhits,
+                                                        void* stream);
+
+/* ---- flagship pipeline: wideband -> PFB -> batched 4FSK demod -> sync search ---------------
+ * One object that owns the HBM-resident intermediates and per-channel loop state and runs
+ *   pfb_channelizer_ccf -> quadrature_demod_cf -> fir_filter_fff(RRC) -> clock_recovery_mm_ff
+ *   -> 4-level slicer -> map_bb -> unpack_k_bits_bb(2) -> correlate_access_code_bb
+ * over successive contiguous time blocks of the wideband stream. */
+typedef struct grcuda_dmr_chain grcuda_dmr_chain;
+typedef struct {
+  unsigned numchans;        /* M */
+  const float* pfb_taps;    /* prototype filter */
+  int pfb_ntaps;
+  float quad_gain;          /* fs_chan / (2 pi 648) for DMR */
+  const float* rrc_taps;
+  int rrc_ntaps;
+  float omega, gain_omega, mu, gain_mu, omega_relative_limit;
+  float slicer_alpha;       /* pager_slicer_fb alpha (0 = fixed thresholds) */
+  const int* symbol_map;    /* gr_map_bb table applied to the slicer decision */
+  int symbol_map_len;
+  const char* access_code;  /* e.g. a 48-bit DMR sync pattern */
+  int threshold;
+  int order;                /* GRCUDA_ORDER_* */
+  int max_rows_per_block;   /* sizing of the intermediates */
+  int keep_bytes;           /* 1: also produce the reference-format correlator byte stream */
+} grcuda_dmr_chain_params;
+grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p);
+void grcuda_dmr_chain_destroy(grcuda_dmr_chain* h);
+/* rows of history the chain wants in front of each block's new rows (pfb taps_per_filter) */
+int grcuda_dmr_chain_history_rows(grcuda_dmr_chain* h);
+/* Process nrows new wideband rows (numchans samples each).  d_in addresses the first of
+ * history_rows() rows that precede them (zeros at stream start, or the neighbour shard's halo).
+ * Per-channel demod state is carried inside the handle from block to block. */
+int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream);
+/* same through host memory: pinned double-buffered staging, H2D of the block, D2H of results */
+int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in, int nrows);
+/* results of the last processed block (device pointers valid until the next process call) */
+typedef struct {
+  const grcuda_complex* d_channels; /* [nrows][M] channelizer output */
+  const float* d_soft;              /* [max_sym][M] M&M output */
+  const unsigned char* d_symbols;   /* [max_sym][M] slicer decisions */
+  const int* d_sym_counts;          /* [M] */
+  const unsigned char* d_bytes;     /* [max_sym*2][M] correlator bytes or NULL */
+  const grcuda_hit* d_hits;
+  const int* d_nhits;
+  int max_sym;
+  int nrows;
+} grcuda_dmr_chain_result;
+int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r);
+/* copy the compacted sync hits of the last block to the host; returns their number */
+int grcuda_dmr_chain_read_hits(grcuda_dmr_chain* h, grcuda_hit* hits, int max_hits);
+/* shard hand-off: export / import the per-channel loop state
+ * {mu, omega, last_sample, next input index, slicer avg, correlator registers} so that the next
+ * time shard continues exactly where this one stopped.  Buffer = state_bytes() bytes (device). */
+size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h);
+int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream);
+int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INCLUDED_GR_CUDA_H */
