@@ -1,0 +1,211 @@
+// Flagship pipeline object: wideband interleaved stream -> gr_pfb_channelizer_ccf ->
+// gr_quadrature_demod_cf -> gr_fir_filter_fff (RRC) -> digital_clock_recovery_mm_ff ->
+// pager_slicer_fb -> gr_map_bb -> gr_unpack_k_bits_bb(2) -> digital_correlate_access_code_bb,
+// batched over all M channels, with every intermediate resident in HBM and the per-channel loop
+// state carried from block to block.
+//
+// Data layout in HBM (row = one channel-rate time step, M channels wide):
+//   Y  [1 + R][M] complex   channelizer output; row 0 = last row of the previous block (quad history)
+//   D  [nrrc-1 + R][M] f32  discriminator output; first nrrc-1 rows = carried history of the RRC FIR
+//   F  [KEEP + R][M] f32    matched-filter output; first KEEP rows = carry for the M&M interpolator
+//   soft/sym [max_sym][M], bytes [2*max_sym][M], hits[], per-channel state arrays
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "internal.h"
+
+using namespace grb;
+
+namespace {
+const int KEEP = 64;  // rows of F kept in front of each block (M&M look-back, see mm_kernel)
+}
+
+struct grcuda_dmr_chain {
+  unsigned M = 0;
+  int T = 0, nrrc = 0, max_rows = 0, max_sym = 0, max_hits = 0, keep_bytes = 0;
+  grcuda_pfb* pfb = nullptr;
+  grcuda_quad* quad = nullptr;
+  grcuda_fir_fff* rrc = nullptr;
+  grcuda_mm* mm = nullptr;
+  grcuda_corr* corr = nullptr;
+  std::vector<int> symbol_map;
+  DevBuf Y, D, F, soft, sym, counts, bytes, hits, nhits, d_in_host;
+  cudaStream_t stream = nullptr;
+  Stager stager;
+  long long abs_row = 0;  // absolute channel-rate row index of the next new row
+  int last_rows = 0;
+  ~grcuda_dmr_chain() {
+    if (pfb) grcuda_pfb_channelizer_ccf_destroy(pfb);
+    if (quad) grcuda_quadrature_demod_cf_destroy(quad);
+    if (rrc) grcuda_fir_filter_fff_destroy(rrc);
+    if (mm) grcuda_clock_recovery_mm_ff_destroy(mm);
+    if (corr) grcuda_correlate_access_code_bb_destroy(corr);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" {
+
+grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
+  if (!p || p->numchans < 1 || p->max_rows_per_block < 1 || p->rrc_ntaps < 1) {
+    set_error(GRCUDA_EINVAL, "dmr_chain: bad parameters");
+    return nullptr;
+  }
+  grcuda_dmr_chain* h = new grcuda_dmr_chain;
+  h->M = p->numchans;
+  h->max_rows = p->max_rows_per_block;
+  h->nrrc = p->rrc_ntaps;
+  h->keep_bytes = p->keep_bytes;
+  h->pfb = grcuda_pfb_channelizer_ccf_create(p->numchans, p->pfb_taps, p->pfb_ntaps, 1.0f);
+  h->quad = h->pfb ? grcuda_quadrature_demod_cf_create(p->quad_gain) : nullptr;
+  h->rrc = h->quad ? grcuda_fir_filter_fff_create(1, p->rrc_taps, p->rrc_ntaps, p->order) : nullptr;
+  h->mm = h->rrc ? grcuda_clock_recovery_mm_ff_create((int)p->numchans, p->omega, p->gain_omega, p->mu, p->gain_mu,
+                                                      p->omega_relative_limit, p->order)
+                 : nullptr;
+  h->corr = h->mm ? grcuda_correlate_access_code_bb_create((int)p->numchans, p->access_code, p->threshold) : nullptr;
+  if (!h->corr) { delete h; return nullptr; }
+  grcuda_clock_recovery_mm_ff_set_slicer(h->mm, 4, p->slicer_alpha);
+  h->symbol_map.assign(p->symbol_map, p->symbol_map + p->symbol_map_len);
+  h->T = grcuda_pfb_channelizer_ccf_taps_per_filter(h->pfb);
+  const size_t M = h->M, R = h->max_rows;
+  h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)p->omega * 1.25) + 64;
+  h->max_hits = std::max<int>(4096, (int)(M * (size_t)h->max_sym / 32));
+  int rc = 0;
+  rc = rc ? rc : h->Y.reserve((1 + R) * M * sizeof(float2));
+  rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
+  rc = rc ? rc : h->F.reserve((KEEP + R) * M * sizeof(float));
+  rc = rc ? rc : h->soft.reserve((size_t)h->max_sym * M * sizeof(float));
+  rc = rc ? rc : h->sym.reserve((size_t)h->max_sym * M);
+  rc = rc ? rc : h->counts.reserve(M * sizeof(int));
+  rc = rc ? rc : h->hits.reserve((size_t)h->max_hits * sizeof(grcuda_hit));
+  rc = rc ? rc : h->nhits.reserve(sizeof(int));
+  if (!rc && h->keep_bytes) rc = h->bytes.reserve((size_t)2 * h->max_sym * M);
+  if (rc) { delete h; return nullptr; }
+  // stream start: all histories are the zeros the reference runtime pre-loads (gr_buffer.cc:201-214)
+  if (cudaMemset(h->Y.p, 0, M * sizeof(float2)) != cudaSuccess ||
+      cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4) != cudaSuccess ||
+      cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
+      cudaMemset(h->nhits.p, 0, sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error(GRCUDA_ECUDA, "dmr_chain: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void grcuda_dmr_chain_destroy(grcuda_dmr_chain* h) { delete h; }
+int grcuda_dmr_chain_history_rows(grcuda_dmr_chain* h) { return h->T; }
+
+int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h) { return std::max(KEEP, h->nrrc - 1); }
+int grcuda_dmr_chain_warmup_rows(grcuda_dmr_chain* h) {
+  // rows a fresh chain must process before its F rows are those of the continuous stream:
+  // PFB transient (T) + quad history (1) + RRC history (nrrc-1) + M&M look-back (KEEP) + look-ahead (8)
+  const int w = h->T + h->nrrc + KEEP + 8;
+  return std::max(w, grcuda_dmr_chain_min_rows(h));
+}
+int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
+  const size_t M = h->M;
+  GRB_CUDA(cudaDeviceSynchronize());
+  GRB_CUDA(cudaMemset(h->Y.p, 0, M * sizeof(float2)));
+  GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
+  GRB_CUDA(cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)));
+  h->abs_row = abs_row;
+  return GRCUDA_OK;
+}
+long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h) { return h->abs_row; }
+
+size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h) { return mm_state_bytes(h->mm) + corr_state_bytes(h->corr); }
+int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream_) {
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  GRB_CUDA(cudaMemcpyAsync(d_state, mm_state_ptr(h->mm), mm_state_bytes(h->mm), cudaMemcpyDeviceToDevice, s));
+  GRB_CUDA(cudaMemcpyAsync((char*)d_state + mm_state_bytes(h->mm), corr_state_ptr(h->corr), corr_state_bytes(h->corr),
+                           cudaMemcpyDeviceToDevice, s));
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void* stream_) {
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  GRB_CUDA(cudaMemcpyAsync(mm_state_ptr(h->mm), d_state, mm_state_bytes(h->mm), cudaMemcpyDeviceToDevice, s));
+  GRB_CUDA(cudaMemcpyAsync(corr_state_ptr(h->corr), (const char*)d_state + mm_state_bytes(h->mm), corr_state_bytes(h->corr),
+                           cudaMemcpyDeviceToDevice, s));
+  return GRCUDA_OK;
+}
+
+int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
+  if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
+    return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  const size_t M = h->M;
+  const long R = nrows;
+  int rc;
+  float2* Y = h->Y.as<float2>();
+  float* D = h->D.as<float>();
+  float* F = h->F.as<float>();
+  // 1. channelizer: [T + R][M] -> Y rows 1..R
+  if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + M), s))) return rc;
+  // 2. discriminator: Y rows 0..R -> D rows (nrrc-1)..
+  if ((rc = grcuda_quadrature_demod_cf_work_device(h->quad, R, (int)M, (const grcuda_complex*)Y, D + (size_t)(h->nrrc - 1) * M, s))) return rc;
+  // 3. matched filter: D (history-prefixed; row 0 is absolute row abs_row-(nrrc-1)) -> F rows KEEP..
+  if ((rc = grcuda_fir_filter_fff_work_device(h->rrc, R, (int)M, D, F + (size_t)KEEP * M, (long)(h->abs_row - (h->nrrc - 1)), s))) return rc;
+  // 4. clock recovery + slicer over F rows [abs_row-KEEP, abs_row+R)
+  if ((rc = grcuda_clock_recovery_mm_ff_work_device(h->mm, KEEP + R, (long)(h->abs_row - KEEP), F, h->soft.as<float>(),
+                                                    h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), s)))
+    return rc;
+  // 5. dibits -> bits -> sync correlation
+  GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  if ((rc = grcuda_correlate_access_code_bb_work_symbols_device(
+           h->corr, h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), h->symbol_map.data(),
+           (int)h->symbol_map.size(), 2, h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr, 2 * h->max_sym,
+           (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
+    return rc;
+  // 6. carries for the next block (small device-to-device copies, stream ordered)
+  // (nrows >= min_rows guarantees that source and destination never overlap)
+  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  if (h->nrrc > 1)
+    GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  GRB_CUDA(cudaMemcpyAsync(F, F + (size_t)R * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  h->abs_row += R;
+  h->last_rows = nrows;
+  return GRCUDA_OK;
+}
+
+int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in, int nrows) {
+  if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
+    return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
+  const size_t bytes = (size_t)(h->T + nrows) * h->M * sizeof(float2);
+  int rc;
+  if ((rc = h->d_in_host.reserve((size_t)(h->T + h->max_rows) * h->M * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in_host.p, in, bytes, h->stream))) return rc;
+  if ((rc = grcuda_dmr_chain_process_device(h, (const grcuda_complex*)h->d_in_host.p, nrows, h->stream))) return rc;
+  GRB_CUDA(cudaStreamSynchronize(h->stream));
+  return GRCUDA_OK;
+}
+
+int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r) {
+  r->d_channels = (const grcuda_complex*)(h->Y.as<float2>() + h->M);
+  r->d_soft = h->soft.as<float>();
+  r->d_symbols = h->sym.as<unsigned char>();
+  r->d_sym_counts = h->counts.as<int>();
+  r->d_bytes = h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr;
+  r->d_hits = (const grcuda_hit*)h->hits.p;
+  r->d_nhits = h->nhits.as<int>();
+  r->max_sym = h->max_sym;
+  r->nrows = h->last_rows;
+  return GRCUDA_OK;
+}
+
+int grcuda_dmr_chain_read_hits(grcuda_dmr_chain* h, grcuda_hit* hits, int max_hits) {
+  int n = 0;
+  GRB_CUDA(cudaMemcpyAsync(&n, h->nhits.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  GRB_CUDA(cudaStreamSynchronize(h->stream));
+  n = std::min(n, h->max_hits);
+  const int m = std::min(n, max_hits);
+  if (m > 0) {
+    GRB_CUDA(cudaMemcpyAsync(hits, h->hits.p, (size_t)m * sizeof(grcuda_hit), cudaMemcpyDeviceToHost, h->stream));
+    GRB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -91,11 +91,23 @@ __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j,
   if (!TO_GLOBAL) __syncthreads();
 }
 
-// ---- fixed plans: N = R0*R1*R2 (R1, R2 may be 1) -----------------------------------------------
-template <int DIR, int R0, int R1, int R2>
-__global__ void __launch_bounds__(512) fft_fixed_kernel(const FftArgs a) {
-  constexpr int N = R0 * R1 * R2;
-  constexpr int NP = (R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1);
+// ---- fixed plans: N = R0*R1*R2*R3 (trailing radices may be 1) ----------------------------------
+template <int R0, int R1, int R2, int R3> struct FftFixedCfg {
+  static constexpr int N = R0 * R1 * R2 * R3;
+  static constexpr int NP = (R3 > 1) ? 4 : ((R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1));
+  static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+  static constexpr int TPR =
+      cmax(cmax(N / R0, R1 > 1 ? N / R1 : 1), cmax(R2 > 1 ? N / R2 : 1, R3 > 1 ? N / R3 : 1));
+  static constexpr int ROWS = cmax(1, 256 / TPR);
+  static constexpr int THREADS = ROWS * TPR;
+};
+
+// MINB = resident CTAs per SM the register allocation must allow (occupancy vs. spills trade-off,
+// chosen per plan from measurements; see profiles/).
+template <int DIR, int R0, int R1, int R2, int R3, int MINB>
+__global__ void __launch_bounds__(FftFixedCfg<R0, R1, R2, R3>::THREADS, MINB) fft_fixed_kernel(const FftArgs a) {
+  constexpr int N = R0 * R1 * R2 * R3;
+  constexpr int NP = FftFixedCfg<R0, R1, R2, R3>::NP;
   constexpr int PADDIV = (NP > 1 && (R0 % 2 == 0)) ? R0 : 0;
   extern __shared__ float2 fft_smem[];
   const int tpr = a.threads_per_row;
@@ -108,15 +120,20 @@ __global__ void __launch_bounds__(512) fft_fixed_kernel(const FftArgs a) {
     const bool row_ok = lrow < a.rows_per_cta && row < a.nrows;
     if (NP == 1) {
       fft_pass<R0, DIR, true, true, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
-    } else if (NP == 2) {
-      fft_pass<R0, DIR, true, false, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
-      fft_pass<R1, DIR, false, true, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
-      __syncthreads();  // next group's pass 0 overwrites the rows read above
     } else {
       fft_pass<R0, DIR, true, false, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
-      fft_pass<R1, DIR, false, false, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
-      fft_pass<R2, DIR, false, true, PADDIV>(a, N, R0 * R1, j, row_ok, row, srow, a.tw[2]);
-      __syncthreads();
+      if (NP == 2) {
+        fft_pass<R1, DIR, false, true, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
+      } else {
+        fft_pass<R1, DIR, false, false, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
+        if (NP == 3) {
+          fft_pass<R2, DIR, false, true, PADDIV>(a, N, R0 * R1, j, row_ok, row, srow, a.tw[2]);
+        } else {
+          fft_pass<R2, DIR, false, false, PADDIV>(a, N, R0 * R1, j, row_ok, row, srow, a.tw[2]);
+          fft_pass<R3, DIR, false, true, PADDIV>(a, N, R0 * R1 * R2, j, row_ok, row, srow, a.tw[3]);
+        }
+      }
+      __syncthreads();  // the next group's first pass overwrites the rows read above
     }
   }
 }

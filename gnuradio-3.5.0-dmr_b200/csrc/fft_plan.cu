@@ -1,0 +1,191 @@
+#include "fft_plan.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_engine.cuh"
+
+namespace grb {
+
+typedef void (*fft_kernel_t)(const FftArgs);
+
+struct FftPlan {
+  int n = 0, dir = -1;
+  int kind = 0;  // 0 fixed, 1 generic, 2 naive
+  int npass = 0;
+  int radix[FFT_MAX_PASSES] = {0};
+  fft_kernel_t kernel = nullptr;
+  float2* d_tw = nullptr;
+  const float2* tw[FFT_MAX_PASSES] = {nullptr};
+  int rows_per_cta = 1, threads_per_row = 1, row_stride = 0, pad_div = 0;
+  size_t smem = 0;
+  int threads = 0;
+  int max_ctas = 0;
+  std::string desc;
+};
+
+struct FixedEntry { int n, r0, r1, r2, r3, minb; fft_kernel_t fwd, bwd; };
+#define FX(R0, R1, R2, R3, MB)                                                                \
+  { (R0) * (R1) * (R2) * (R3), R0, R1, R2, R3, MB, fft_fixed_kernel<-1, R0, R1, R2, R3, MB>, \
+    fft_fixed_kernel<1, R0, R1, R2, R3, MB> }
+// For a given n the FIRST entry is the default; GRCUDA_FFT_VARIANT=<k> selects the k-th.
+static const FixedEntry kFixed[] = {
+    FX(20, 20, 20, 1, 1), FX(20, 20, 20, 1, 2), FX(10, 10, 10, 8, 1), FX(10, 10, 10, 8, 2),  // 8000
+    FX(16, 16, 16, 1, 2), FX(16, 16, 16, 1, 3), FX(16, 16, 16, 1, 1), FX(8, 8, 8, 8, 2), FX(8, 8, 8, 8, 4),  // 4096
+    FX(16, 10, 1, 1, 2), FX(16, 10, 1, 1, 3), FX(10, 4, 4, 1, 4),  // 160
+    FX(2, 1, 1, 1, 4), FX(4, 1, 1, 1, 4), FX(8, 1, 1, 1, 4), FX(16, 1, 1, 1, 4), FX(5, 1, 1, 1, 4),
+    FX(10, 1, 1, 1, 4), FX(20, 1, 1, 1, 4), FX(8, 4, 1, 1, 4), FX(8, 8, 1, 1, 4), FX(16, 8, 1, 1, 4),
+    FX(16, 16, 1, 1, 3), FX(8, 8, 8, 1, 4), FX(16, 8, 8, 1, 4), FX(16, 16, 8, 1, 3), FX(16, 5, 1, 1, 4),
+    FX(10, 10, 1, 1, 4), FX(20, 10, 1, 1, 3), FX(20, 20, 1, 1, 3), FX(10, 10, 10, 1, 4), FX(16, 10, 10, 1, 3),
+    FX(20, 10, 10, 1, 3), FX(20, 20, 10, 1, 2), FX(20, 20, 16, 1, 2),
+};
+#undef FX
+
+static int build_twiddles(FftPlan* p) {
+  // per pass p >= 1: Ns entries e^{dir 2 pi j k / (Ns R)}; naive: n entries e^{dir 2 pi j k / n}
+  std::vector<float2> host;
+  std::vector<size_t> off(FFT_MAX_PASSES, 0);
+  if (p->kind == 2) {
+    host.resize(p->n);
+    for (int k = 0; k < p->n; k++) {
+      const double ph = p->dir * 2.0 * M_PI * (double)k / (double)p->n;
+      host[k] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+  } else {
+    int Ns = 1;
+    for (int q = 0; q < p->npass; q++) {
+      off[q] = host.size();
+      if (q > 0) {
+        const double den = (double)Ns * p->radix[q];
+        for (int k = 0; k < Ns; k++) {
+          const double ph = p->dir * 2.0 * M_PI * (double)k / den;
+          host.push_back(make_float2((float)cos(ph), (float)sin(ph)));
+        }
+      }
+      Ns *= p->radix[q];
+    }
+  }
+  if (host.empty()) host.push_back(make_float2(1.f, 0.f));
+  GRB_CUDA(cudaMalloc(&p->d_tw, host.size() * sizeof(float2)));
+  GRB_CUDA(cudaMemcpy(p->d_tw, host.data(), host.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  for (int q = 0; q < FFT_MAX_PASSES; q++) p->tw[q] = p->d_tw + off[q];
+  return GRCUDA_OK;
+}
+
+FftPlan* fft_plan_create(int n, int dir) {
+  if (n <= 0) {
+    set_error(GRCUDA_ERANGE, "gri_fftw: invalid fft_size");  // gri_fft.cc:104-105
+    return nullptr;
+  }
+  FftPlan* p = new FftPlan;
+  p->n = n;
+  p->dir = dir < 0 ? -1 : 1;
+  const FixedEntry* fe = nullptr;
+  {
+    int want = 0, seen = 0;
+    if (const char* v = getenv("GRCUDA_FFT_VARIANT")) want = atoi(v);
+    for (const FixedEntry& e : kFixed)
+      if (e.n == n) {
+        if (!fe || seen == want) fe = &e;
+        seen++;
+      }
+  }
+  if (n == 1) {
+    p->kind = 2;  // trivial copy through the naive kernel
+  } else if (fe) {
+    p->kind = 0;
+    p->radix[0] = fe->r0; p->radix[1] = fe->r1; p->radix[2] = fe->r2; p->radix[3] = fe->r3;
+    p->npass = fe->r3 > 1 ? 4 : (fe->r2 > 1 ? 3 : (fe->r1 > 1 ? 2 : 1));
+    p->kernel = p->dir < 0 ? fe->fwd : fe->bwd;
+    int tpr = 1;
+    for (int q = 0; q < p->npass; q++) tpr = std::max(tpr, n / p->radix[q]);
+    p->threads_per_row = tpr;
+    p->rows_per_cta = std::max(1, 256 / tpr);
+    p->pad_div = (p->npass > 1 && (fe->r0 % 2 == 0)) ? fe->r0 : 0;
+    p->row_stride = n + (p->pad_div ? n / p->pad_div : 0) + 1;
+    p->threads = p->rows_per_cta * tpr;
+    p->smem = p->npass > 1 ? (size_t)p->rows_per_cta * p->row_stride * sizeof(float2) : 0;
+  } else {
+    int rem = n, np = 0;
+    const int cand[] = {8, 4, 2, 5, 3};
+    for (int c : cand)
+      while (rem % c == 0 && np < FFT_MAX_PASSES) { p->radix[np++] = c; rem /= c; }
+    const size_t row_bytes = (size_t)2 * n * sizeof(float2);
+    if (rem == 1 && row_bytes <= 200 * 1024) {
+      p->kind = 1;
+      p->npass = np;
+      p->kernel = p->dir < 0 ? fft_generic_kernel<-1> : fft_generic_kernel<1>;
+      int tpr = std::min(256, std::max(1, n / 2));
+      p->threads_per_row = tpr;
+      p->rows_per_cta = std::max(1, std::min(256 / tpr, (int)(96 * 1024 / row_bytes)));
+      if (p->rows_per_cta < 1) p->rows_per_cta = 1;
+      p->threads = p->rows_per_cta * tpr;
+      p->smem = (size_t)p->rows_per_cta * row_bytes;
+    } else {
+      p->kind = 2;
+    }
+  }
+  if (p->kind == 2) {
+    p->npass = 1;
+    p->kernel = p->dir < 0 ? fft_naive_kernel<-1> : fft_naive_kernel<1>;
+    p->threads = 128;
+  }
+  if (build_twiddles(p) != GRCUDA_OK) { delete p; return nullptr; }
+  if (p->smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e != cudaSuccess) {
+      set_error(GRCUDA_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", p->smem, cudaGetErrorString(e));
+      cudaFree(p->d_tw);
+      delete p;
+      return nullptr;
+    }
+  }
+  int per_sm = 1;
+  if (p->kind != 2) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)p->kernel, p->threads, p->smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  }
+  p->max_ctas = per_sm * sm_count();
+  char buf[256];
+  snprintf(buf, sizeof buf, "fft n=%d dir=%d kind=%s radices=%d,%d,%d,%d rows/cta=%d threads=%d smem=%zu ctas/sm=%d", n,
+           p->dir, p->kind == 0 ? "fixed" : (p->kind == 1 ? "generic" : "naive"), p->radix[0], p->radix[1], p->radix[2],
+           p->radix[3], p->rows_per_cta, p->threads, p->smem, per_sm);
+  p->desc = buf;
+  return p;
+}
+
+void fft_plan_destroy(FftPlan* p) {
+  if (!p) return;
+  if (p->d_tw) cudaFree(p->d_tw);
+  delete p;
+}
+
+const char* fft_plan_describe(FftPlan* p) { return p->desc.c_str(); }
+
+int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, const float* d_window, int in_rot,
+                  int out_rot, cudaStream_t stream) {
+  if (nrows <= 0) return GRCUDA_OK;
+  FftArgs a;
+  memset(&a, 0, sizeof a);
+  a.in = d_in; a.out = d_out; a.nrows = nrows; a.window = d_window;
+  a.in_rot = in_rot; a.out_rot = out_rot;
+  for (int q = 0; q < FFT_MAX_PASSES; q++) { a.tw[q] = p->tw[q]; a.radix[q] = p->radix[q]; }
+  a.n = p->n; a.npass = p->npass;
+  a.rows_per_cta = p->rows_per_cta; a.threads_per_row = p->threads_per_row;
+  a.row_stride = p->row_stride; a.pad_div = p->pad_div;
+  if (p->kind == 2) {
+    dim3 grid((p->n + 127) / 128, (unsigned)std::min<long>(nrows, 65535));
+    p->kernel<<<grid, 128, 0, stream>>>(a);
+  } else {
+    const long ngroups = (nrows + p->rows_per_cta - 1) / p->rows_per_cta;
+    const int grid = (int)std::min<long>(ngroups, p->max_ctas);
+    p->kernel<<<grid, p->threads, p->smem, stream>>>(a);
+  }
+  GRB_LAUNCH_CHECK();
+  return GRCUDA_OK;
+}
+
+}  // namespace grb

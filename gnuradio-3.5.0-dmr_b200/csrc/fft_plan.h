@@ -1,0 +1,19 @@
+// Host-side FFT plan (the GPU counterpart of gri_fft_complex's FFTW plan,
+// gnuradio-core/src/lib/general/gri_fft.cc:97-146): picks radices, builds twiddle tables,
+// launches the batched shared-memory engine of fft_engine.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace grb {
+
+struct FftPlan;
+// dir: -1 forward, +1 backward (unnormalised).  Returns nullptr with the error set.
+FftPlan* fft_plan_create(int n, int dir);
+void fft_plan_destroy(FftPlan* p);
+// rows: [nrows][n] complex.  window: n device floats or nullptr.  in_rot/out_rot: element
+// rotations implementing ifftshift on load / fftshift on store.
+int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, const float* d_window, int in_rot,
+                  int out_rot, cudaStream_t stream);
+const char* fft_plan_describe(FftPlan* p);
+
+}  // namespace grb

@@ -148,19 +148,25 @@ template <int R, int DIR> GR_HD void butterfly(float2* v) {
   else if (R == 20) fft20<DIR>(v);
 }
 
-// v[r] *= w^r, r = 1..R-1, with short dependency chains (w2 = w^2, w3, w4 = w2^2, then
-// w_r = w_{r-4} * w4): depth <= 2 + R/4 multiplications, i.e. <= ~7 ulp for R = 20.
+// v[r] *= w^r, r = 1..R-1.  Powers are produced four at a time (w^q, q = 4g+1..4g+4, each the
+// previous group's value times w^4) and consumed immediately, so only ~10 twiddle registers are
+// live next to the R data values; dependency depth <= 2 + R/4 multiplications (<= ~7 ulp at R=20).
 template <int R> GR_HD void apply_twiddle_powers(float2* v, float2 w1) {
   if (R < 2) return;
-  float2 w[R > 1 ? R : 2];
-  w[1] = w1;
-  if (R > 2) w[2] = cmul(w1, w1);
-  if (R > 3) w[3] = cmul(w[2], w1);
-  if (R > 4) w[4] = cmul(w[2], w[2]);
+  float2 a = w1, b = cmul(w1, w1), c = cmul(b, w1), d = cmul(b, b);
+  const float2 w4 = d;
+  v[1] = cmul(v[1], a);
+  if (R > 2) v[2] = cmul(v[2], b);
+  if (R > 3) v[3] = cmul(v[3], c);
+  if (R > 4) v[4] = cmul(v[4], d);
 #pragma unroll
-  for (int r = 5; r < R; r++) w[r] = cmul(w[r - 4], w[4]);
-#pragma unroll
-  for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
+  for (int g = 5; g < R; g += 4) {
+    a = cmul(a, w4);
+    v[g] = cmul(v[g], a);
+    if (g + 1 < R) { b = cmul(b, w4); v[g + 1] = cmul(v[g + 1], b); }
+    if (g + 2 < R) { c = cmul(c, w4); v[g + 2] = cmul(v[g + 2], c); }
+    if (g + 3 < R) { d = cmul(d, w4); v[g + 3] = cmul(v[g + 3], d); }
+  }
 }
 
 }  // namespace grb

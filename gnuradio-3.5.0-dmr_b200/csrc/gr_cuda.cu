@@ -1,0 +1,1009 @@
+// libgr_cuda: implementation of the C ABI declared in include/gr_cuda.h.
+// Host logic of the plans (tap bookkeeping, history/"updated" contracts of the reference blocks,
+// staging) + kernel launches.  No CPU compute path exists here: every work call runs CUDA
+// kernels or fails with GRCUDA_ECUDA.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "fft_plan.h"
+#include "kernels_demod.cuh"
+#include "kernels_fir.cuh"
+
+using namespace grb;
+
+namespace {
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return GRCUDA_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_error(GRCUDA_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cap = bytes;
+    return GRCUDA_OK;
+  }
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+struct PlanBase {
+  cudaStream_t stream = nullptr;
+  Stager stager;
+  DevBuf d_in, d_out;
+  std::mutex mu;  // guards setter-visible state (reference setters are unlocked; ours are not)
+  int base_init() {
+    GRB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return GRCUDA_OK;
+  }
+  cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : stream; }
+  virtual ~PlanBase() { if (stream) cudaStreamDestroy(stream); }
+};
+
+bool device_ok() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error(GRCUDA_ECUDA, "no CUDA device available (%s); libgr_cuda has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+int grid_for(long items, int threads, int per_sm = 8) {
+  long g = (items + threads - 1) / threads;
+  long cap = (long)sm_count() * per_sm;
+  return (int)std::max<long>(1, std::min(g, cap));
+}
+
+}  // namespace
+
+// =============================================================================================
+// library / device
+// =============================================================================================
+extern "C" {
+
+const char* grcuda_version(void) { return "gr-b200 0.1 (sm_100a)"; }
+const char* grcuda_last_error(void) { return g_last_error.c_str(); }
+int grcuda_last_error_code(void) { return g_last_error_code; }
+int grcuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int grcuda_set_device(int device) { GRB_CUDA(cudaSetDevice(device)); return GRCUDA_OK; }
+int grcuda_device_synchronize(void) { GRB_CUDA(cudaDeviceSynchronize()); return GRCUDA_OK; }
+void* grcuda_malloc_device(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) { set_error(GRCUDA_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+void grcuda_free_device(void* p) { if (p) cudaFree(p); }
+void* grcuda_malloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { set_error(GRCUDA_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+void grcuda_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int grcuda_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  GRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (!stream) GRB_CUDA(cudaStreamSynchronize(nullptr));
+  return GRCUDA_OK;
+}
+int grcuda_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  GRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (!stream) GRB_CUDA(cudaStreamSynchronize(nullptr));
+  return GRCUDA_OK;
+}
+int grcuda_stream_synchronize(void* stream) { GRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return GRCUDA_OK; }
+unsigned long long grcuda_kernel_launch_count(void) { return g_launches.load(); }
+int grcuda_ipc_export(void* dptr, unsigned char handle[64]) {
+  cudaIpcMemHandle_t h;
+  GRB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle, &h, 64);
+  return GRCUDA_OK;
+}
+void* grcuda_ipc_open(const unsigned char handle[64]) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error(GRCUDA_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+int grcuda_ipc_close(void* dptr) { GRB_CUDA(cudaIpcCloseMemHandle(dptr)); return GRCUDA_OK; }
+
+}  // extern "C"
+
+// =============================================================================================
+// a1 / a3: decimating FIR with real or complex taps
+// =============================================================================================
+struct FirCore {
+  int decim = 1, ntaps = 0, J = 8;
+  bool ctaps = false;
+  DevBuf d_rtp;
+  int threads = 128, tile_out = 1024, pitch = 0;
+  size_t smem = 0;
+  int max_ctas = 0;
+
+  // rt: reversed taps (float or complex<float>), polyphase-split and zero padded on upload
+  int upload(const float* rt, int n, bool complex_taps) {
+    ntaps = n;
+    ctaps = complex_taps;
+    const int D = decim;
+    const int jraw = std::max(1, (n + D - 1) / D);
+    J = ((jraw + FIR_R - 1) / FIR_R) * FIR_R;
+    const int w = complex_taps ? 2 : 1;
+    std::vector<float> rtp((size_t)D * J * w, 0.f);
+    for (int i = 0; i < n; i++) {
+      const int q = i / D, p = i % D;
+      for (int c = 0; c < w; c++) rtp[((size_t)p * J + q) * w + c] = rt[(size_t)i * w + c];
+    }
+    int rc = d_rtp.reserve(rtp.size() * sizeof(float));
+    if (rc) return rc;
+    GRB_CUDA(cudaMemcpy(d_rtp.p, rtp.data(), rtp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (threads = 128; threads >= 32; threads /= 2) {
+      tile_out = threads * FIR_R;
+      const int rows_n = tile_out + J + FIR_R;
+      pitch = rows_n + (rows_n >> 3) + 1;
+      pitch += (4 - (pitch % 16) + 16) % 16;  // pitch = 4 (mod 16): conflict-free phase-split fill
+      smem = (size_t)D * pitch * sizeof(float2) + rtp.size() * sizeof(float);
+      if (smem <= 200 * 1024) break;
+    }
+    if (smem > 200 * 1024)
+      return set_error(GRCUDA_EUNSUPPORTED, "FIR with %d taps x decimation %d exceeds the shared-memory tile", n, D);
+    const void* k = complex_taps ? (const void*)fir_decim_kernel<true> : (const void*)fir_decim_kernel<false>;
+    GRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
+    max_ctas = std::max(1, per_sm) * sm_count();
+    return GRCUDA_OK;
+  }
+
+  int launch(const float2* d_in, float2* d_out, long nout, bool rotate, double theta, long out_index0,
+             cudaStream_t s) {
+    if (nout <= 0) return GRCUDA_OK;
+    if (ntaps == 0) {  // gr_fir_ccf_simd::filter returns 0 for an empty filter (gr_fir_ccf_simd.cc:103-104)
+      GRB_CUDA(cudaMemsetAsync(d_out, 0, nout * sizeof(float2), s));
+      return GRCUDA_OK;
+    }
+    FirArgs a;
+    a.in = d_in; a.out = d_out; a.nout = nout; a.decim = decim; a.ntaps = ntaps; a.J = J;
+    a.rtp = d_rtp.as<float>(); a.tile_out = tile_out; a.pitch = pitch;
+    a.rotate = rotate ? 1 : 0; a.theta = theta; a.out_index0 = out_index0;
+    const long ntiles = (nout + tile_out - 1) / tile_out;
+    const int grid = (int)std::min<long>(ntiles, max_ctas);
+    if (ctaps) fir_decim_kernel<true><<<grid, threads, smem, s>>>(a);
+    else fir_decim_kernel<false><<<grid, threads, smem, s>>>(a);
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+struct grcuda_fir_ccf : PlanBase {
+  FirCore core;
+  std::vector<float> new_taps;
+  bool updated = false;
+  unsigned history = 1;
+  int set_now(const std::vector<float>& taps) {
+    cudaDeviceSynchronize();  // no kernel may still be reading the tap store we are replacing
+    std::vector<float> rt(taps.rbegin(), taps.rend());  // gr_fir_XXX.h.t:65 d_taps = reverse(taps)
+    history = (unsigned)taps.size();                     // gr_fir_filter_XXX.cc.t:51 set_history(ntaps)
+    return core.upload(rt.data(), (int)rt.size(), false);
+  }
+};
+
+extern "C" {
+
+grcuda_fir_ccf* grcuda_fir_filter_ccf_create(int decimation, const float* taps, int ntaps) {
+  if (!device_ok()) return nullptr;
+  if (decimation < 1 || ntaps < 0) { set_error(GRCUDA_EINVAL, "fir_filter_ccf: bad decimation/ntaps"); return nullptr; }
+  grcuda_fir_ccf* h = new grcuda_fir_ccf;
+  h->core.decim = decimation;
+  if (h->base_init() || h->set_now(std::vector<float>(taps, taps + ntaps))) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_fir_filter_ccf_destroy(grcuda_fir_ccf* h) { delete h; }
+int grcuda_fir_filter_ccf_set_taps(grcuda_fir_ccf* h, const float* taps, int ntaps) {
+  std::lock_guard<std::mutex> lk(h->mu);  // gr_fir_filter_XXX.cc.t:59-64: deferred to the next work()
+  h->new_taps.assign(taps, taps + ntaps);
+  h->updated = true;
+  return GRCUDA_OK;
+}
+unsigned grcuda_fir_filter_ccf_history(grcuda_fir_ccf* h) { return h->history; }
+int grcuda_fir_filter_ccf_decimation(grcuda_fir_ccf* h) { return h->core.decim; }
+int grcuda_fir_filter_ccf_work_device(grcuda_fir_ccf* h, long nout, const grcuda_complex* d_in, grcuda_complex* d_out,
+                                      void* stream) {
+  return h->core.launch((const float2*)d_in, (float2*)d_out, nout, false, 0.0, 0, h->pick(stream));
+}
+int grcuda_fir_filter_ccf_work(grcuda_fir_ccf* h, int nout, const grcuda_complex* in, grcuda_complex* out) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {  // gr_fir_filter_XXX.cc.t:74-79
+      h->updated = false;
+      int rc = h->set_now(h->new_taps);
+      return rc ? rc : 0;
+    }
+  }
+  if (nout <= 0) return 0;
+  const size_t nin = (size_t)(nout - 1) * h->core.decim + std::max(h->core.ntaps, 1);
+  int rc;
+  if ((rc = h->d_in.reserve(nin * sizeof(float2))) || (rc = h->d_out.reserve((size_t)nout * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, nin * sizeof(float2), h->stream))) return rc;
+  if ((rc = h->core.launch(h->d_in.as<float2>(), h->d_out.as<float2>(), nout, false, 0.0, 0, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * sizeof(float2), h->stream))) return rc;
+  return nout;
+}
+
+}  // extern "C"
+
+// ---- a3 gr_freq_xlating_fir_filter_ccf ------------------------------------------------------------
+struct grcuda_fxlat : PlanBase {
+  FirCore core;
+  std::vector<float> proto;
+  double center_freq = 0, sampling_freq = 1;
+  bool updated = false;
+  unsigned history = 1;
+  double theta = 0;      // angle of the normalised float phase increment (gr_rotator.h:38)
+  long out_count = 0;    // d_counter of the rotator = outputs produced so far
+
+  int build() {  // build_composite_fir (gr_freq_xlating_fir_filter_XXX.cc.t:72-83), same float ops
+    cudaDeviceSynchronize();
+    const int n = (int)proto.size();
+    std::vector<std::complex<float> > ctaps(n);
+    const float fwT0 = 2 * M_PI * center_freq / sampling_freq;
+    for (int i = 0; i < n; i++) ctaps[i] = proto[i] * std::exp(std::complex<float>(0, i * fwT0));
+    // set_taps(gr_reverse(ctaps)) and the FIR stores reverse(taps): filter() uses ctaps in proto order
+    std::vector<float> rt((size_t)n * 2);
+    for (int i = 0; i < n; i++) { rt[2 * i] = ctaps[i].real(); rt[2 * i + 1] = ctaps[i].imag(); }
+    std::complex<float> incr = std::exp(std::complex<float>(0, fwT0 * core.decim));
+    incr = incr / std::abs(incr);  // set_phase_incr
+    theta = std::atan2((double)incr.imag(), (double)incr.real());
+    history = (unsigned)n;
+    return core.upload(rt.data(), n, true);
+  }
+};
+
+extern "C" {
+
+grcuda_fxlat* grcuda_freq_xlating_fir_filter_ccf_create(int decimation, const float* taps, int ntaps,
+                                                       double center_freq, double sampling_freq) {
+  if (!device_ok()) return nullptr;
+  if (decimation < 1 || ntaps < 0) { set_error(GRCUDA_EINVAL, "freq_xlating_fir_filter_ccf: bad arguments"); return nullptr; }
+  grcuda_fxlat* h = new grcuda_fxlat;
+  h->core.decim = decimation;
+  h->proto.assign(taps, taps + ntaps);
+  h->center_freq = center_freq;
+  h->sampling_freq = sampling_freq;
+  if (h->base_init() || h->build()) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_freq_xlating_fir_filter_ccf_destroy(grcuda_fxlat* h) { delete h; }
+int grcuda_freq_xlating_fir_filter_ccf_set_taps(grcuda_fxlat* h, const float* taps, int ntaps) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->proto.assign(taps, taps + ntaps);
+  h->updated = true;
+  return GRCUDA_OK;
+}
+int grcuda_freq_xlating_fir_filter_ccf_set_center_freq(grcuda_fxlat* h, double f) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->center_freq = f;
+  h->updated = true;
+  return GRCUDA_OK;
+}
+unsigned grcuda_freq_xlating_fir_filter_ccf_history(grcuda_fxlat* h) { return h->history; }
+int grcuda_freq_xlating_fir_filter_ccf_work_device(grcuda_fxlat* h, long nout, const grcuda_complex* d_in,
+                                                   grcuda_complex* d_out, void* stream) {
+  int rc = h->core.launch((const float2*)d_in, (float2*)d_out, nout, true, h->theta, h->out_count, h->pick(stream));
+  if (rc == GRCUDA_OK) h->out_count += nout;
+  return rc;
+}
+int grcuda_freq_xlating_fir_filter_ccf_work(grcuda_fxlat* h, int nout, const grcuda_complex* in, grcuda_complex* out) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {  // :107-112 (the rotator keeps its phase across a rebuild: only incr changes)
+      h->updated = false;
+      int rc = h->build();
+      return rc ? rc : 0;
+    }
+  }
+  if (nout <= 0) return 0;
+  const size_t nin = (size_t)(nout - 1) * h->core.decim + std::max(h->core.ntaps, 1);
+  int rc;
+  if ((rc = h->d_in.reserve(nin * sizeof(float2))) || (rc = h->d_out.reserve((size_t)nout * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, nin * sizeof(float2), h->stream))) return rc;
+  if ((rc = grcuda_freq_xlating_fir_filter_ccf_work_device(h, nout, (const grcuda_complex*)h->d_in.p,
+                                                           (grcuda_complex*)h->d_out.p, h->stream)))
+    return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * sizeof(float2), h->stream))) return rc;
+  return nout;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a2: gr_fir_filter_fff (single stream and batched [time][channel])
+// =============================================================================================
+namespace grb {
+__global__ void fir_fff_stream_kernel(const float* __restrict__ in, float* __restrict__ out, long nout, int decim,
+                                      const float* __restrict__ rt_g, int ntaps, int order, long abs0) {
+  extern __shared__ float rt[];
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) rt[i] = rt_g[i];
+  __syncthreads();
+  for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < nout; o += (long)gridDim.x * blockDim.x) {
+    const float* p = in + o * decim;
+    out[o] = (order == GR_ORDER_SSE) ? dot_sse(rt, ntaps, p, 1, mod4(abs0 + o * decim)) : dot_generic(rt, ntaps, p, 1);
+  }
+}
+}  // namespace grb
+
+struct grcuda_fir_fff : PlanBase {
+  int decim = 1, ntaps = 0, order = GRCUDA_ORDER_SSE;
+  DevBuf d_rt;
+  std::vector<float> new_taps;
+  bool updated = false;
+  unsigned history = 1;
+  int set_now(const std::vector<float>& taps) {
+    cudaDeviceSynchronize();
+    std::vector<float> rt(taps.rbegin(), taps.rend());
+    ntaps = (int)rt.size();
+    history = (unsigned)ntaps;
+    if ((size_t)ntaps * sizeof(float) > 96 * 1024)
+      return set_error(GRCUDA_EUNSUPPORTED, "fir_filter_fff: %d taps exceed the shared-memory tap store", ntaps);
+    int rc = d_rt.reserve(std::max<size_t>(4, rt.size() * sizeof(float)));
+    if (rc) return rc;
+    if (ntaps) GRB_CUDA(cudaMemcpy(d_rt.p, rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if ((size_t)ntaps * sizeof(float) > 48 * 1024) {
+      GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    }
+    return GRCUDA_OK;
+  }
+  int launch(const float* d_in, float* d_out, long nout, int nchan, long abs0, cudaStream_t s) {
+    if (nout <= 0 || nchan <= 0) return GRCUDA_OK;
+    const size_t smem = std::max<size_t>(4, (size_t)ntaps * sizeof(float));
+    if (nchan == 1) {
+      fir_fff_stream_kernel<<<grid_for(nout, 256), 256, smem, s>>>(d_in, d_out, nout, decim, d_rt.as<float>(), ntaps,
+                                                                    order, abs0);
+    } else {
+      const int gx = (nchan + 127) / 128;
+      // enough row tiles to fill the machine ~4x, at least 16 rows each
+      long tiles = std::max<long>(1, (long)sm_count() * 16 / gx);
+      int rpt = (int)std::max<long>(16, (nout + tiles - 1) / tiles);
+      dim3 grid(gx, (unsigned)((nout + rpt - 1) / rpt));
+      fir_fff_kernel<<<grid, 128, smem, s>>>(d_in, d_out, nout, nchan, decim, d_rt.as<float>(), ntaps, order, abs0, rpt);
+    }
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_fir_fff* grcuda_fir_filter_fff_create(int decimation, const float* taps, int ntaps, int order) {
+  if (!device_ok()) return nullptr;
+  if (decimation < 1 || ntaps < 0 || (order != GRCUDA_ORDER_GENERIC && order != GRCUDA_ORDER_SSE)) {
+    set_error(GRCUDA_EINVAL, "fir_filter_fff: bad arguments");
+    return nullptr;
+  }
+  grcuda_fir_fff* h = new grcuda_fir_fff;
+  h->decim = decimation;
+  h->order = order;
+  if (h->base_init() || h->set_now(std::vector<float>(taps, taps + ntaps))) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_fir_filter_fff_destroy(grcuda_fir_fff* h) { delete h; }
+int grcuda_fir_filter_fff_set_taps(grcuda_fir_fff* h, const float* taps, int ntaps) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->new_taps.assign(taps, taps + ntaps);
+  h->updated = true;
+  return GRCUDA_OK;
+}
+unsigned grcuda_fir_filter_fff_history(grcuda_fir_fff* h) { return h->history; }
+int grcuda_fir_filter_fff_work_device(grcuda_fir_fff* h, long nout, int nchan, const float* d_in, float* d_out,
+                                      long abs_index0, void* stream) {
+  return h->launch(d_in, d_out, nout, nchan, abs_index0, h->pick(stream));
+}
+int grcuda_fir_filter_fff_work(grcuda_fir_fff* h, int nout, const float* in, float* out, long abs_index0) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {
+      h->updated = false;
+      int rc = h->set_now(h->new_taps);
+      return rc ? rc : 0;
+    }
+  }
+  if (nout <= 0) return 0;
+  const size_t nin = (size_t)(nout - 1) * h->decim + std::max(h->ntaps, 1);
+  int rc;
+  if ((rc = h->d_in.reserve(nin * sizeof(float))) || (rc = h->d_out.reserve((size_t)nout * sizeof(float)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, nin * sizeof(float), h->stream))) return rc;
+  if ((rc = h->launch(h->d_in.as<float>(), h->d_out.as<float>(), nout, 1, abs_index0, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * sizeof(float), h->stream))) return rc;
+  return nout;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a4 / a5 / a14: gr_pfb_channelizer_ccf
+// =============================================================================================
+struct grcuda_pfb : PlanBase {
+  unsigned M = 0;
+  float os = 1.f;
+  int rr = 0, output_multiple = 1, T = 0, TT = 0, ntaps = 0;
+  double relative_rate = 1.0;
+  unsigned history = 1;
+  bool updated = false;
+  std::vector<float> pending;
+  DevBuf d_taps_t, d_taps_plain, d_u, d_stage, d_rows;
+  PinBuf pin_in;
+  FftPlan* fft = nullptr;
+  long chunk_rows = 0;
+
+  ~grcuda_pfb() { fft_plan_destroy(fft); }
+
+  bool dirty = false;
+  // host-visible part of set_taps (:104-139): geometry changes immediately, like set_history (:136)
+  void set_geometry(const std::vector<float>& taps) {
+    pending = taps;
+    ntaps = (int)taps.size();
+    T = (int)std::ceil((double)ntaps / (double)M);
+    if (T < 1) T = 1;  // keeps the layout valid for an empty prototype (all-zero branches)
+    TT = T <= 4 ? 4 : (T <= 8 ? 8 : (T <= 16 ? 16 : (T <= 32 ? 32 : 0)));
+    history = (unsigned)T + 1;  // :136
+    dirty = true;
+  }
+  // device part, applied at the next work boundary so that no in-flight kernel sees a torn tap set
+  int upload_if_dirty() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!dirty) return GRCUDA_OK;
+    cudaDeviceSynchronize();
+    dirty = false;
+    const std::vector<float>& taps = pending;
+    std::vector<float> plain((size_t)T * M, 0.f);
+    for (int i = 0; i < ntaps; i++) plain[i] = taps[i];  // h[k + t*M] at plain[t*M + k]
+    int rc = d_taps_plain.reserve(plain.size() * sizeof(float));
+    if (rc) return rc;
+    GRB_CUDA(cudaMemcpy(d_taps_plain.p, plain.data(), plain.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (TT) {
+      std::vector<float> tt((size_t)TT * M, 0.f);
+      for (int t = 0; t < T; t++)
+        for (unsigned j = 0; j < M; j++) tt[(size_t)t * M + j] = plain[(size_t)t * M + (M - 1 - j)];
+      if ((rc = d_taps_t.reserve(tt.size() * sizeof(float)))) return rc;
+      GRB_CUDA(cudaMemcpy(d_taps_t.p, tt.data(), tt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return GRCUDA_OK;
+  }
+
+  // rows in: [T + nin][M]; out: [nout][M].  nout output vectors; os == 1 -> nin == nout.
+  int run(const float2* d_rows_in, float2* d_out, long nout, cudaStream_t s) {
+    int rc0 = upload_if_dirty();
+    if (rc0) return rc0;
+    if (nout <= 0) return GRCUDA_OK;
+    const bool fast = (rr == (int)M) && TT;
+    // The branch-filter output u is only an intermediate: process in row chunks small enough
+    // to stay resident in the 126 MB L2 between the FIR kernel and the FFT kernel.
+    long crow = chunk_rows;
+    if (crow <= 0) {
+      size_t mb = 24;
+      if (const char* e = getenv("GRCUDA_PFB_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e));
+      crow = std::max<long>(1, (long)(mb << 20) / (long)(M * sizeof(float2)));
+    }
+    if (!fast) crow = nout;  // the oversampled path indexes rows through the output number
+    crow = std::min(crow, nout);
+    int rc = d_u.reserve((size_t)crow * M * sizeof(float2));
+    if (rc) return rc;
+    for (long r0 = 0; r0 < nout; r0 += crow) {
+      const long n = std::min(crow, nout - r0);
+      if (fast) {
+        PfbFirArgs a;
+        a.x = d_rows_in + r0 * (long)M; a.u = d_u.as<float2>(); a.taps_t = d_taps_t.as<float>();
+        a.M = (int)M; a.T = T; a.nrows = n;
+        const int gx = ((int)M + 127) / 128;
+        long tiles = std::max<long>(1, (long)sm_count() * 12 / gx);
+        int rpt = (int)std::max<long>(4 * TT, (n + tiles - 1) / tiles);
+        rpt = ((rpt + TT - 1) / TT) * TT;
+        a.rows_per_thread = rpt;
+        dim3 grid(gx, (unsigned)((n + rpt - 1) / rpt));
+        switch (TT) {
+          case 4: pfb_fir_kernel<4><<<grid, 128, 0, s>>>(a); break;
+          case 8: pfb_fir_kernel<8><<<grid, 128, 0, s>>>(a); break;
+          case 16: pfb_fir_kernel<16><<<grid, 128, 0, s>>>(a); break;
+          default: pfb_fir_kernel<32><<<grid, 128, 0, s>>>(a); break;
+        }
+      } else {
+        PfbFirGenArgs a;
+        a.x = d_rows_in; a.u = d_u.as<float2>(); a.taps = d_taps_plain.as<float>();
+        a.M = (int)M; a.T = T; a.rr = rr; a.nout = n;
+        pfb_fir_generic_kernel<<<grid_for(n * (long)M, 256), 256, 0, s>>>(a);
+      }
+      GRB_LAUNCH_CHECK();
+      if ((rc = fft_plan_exec(fft, d_u.as<float2>(), d_out + r0 * (long)M, n, nullptr, 0, 0, s))) return rc;
+    }
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_pfb* grcuda_pfb_channelizer_ccf_create(unsigned numchans, const float* taps, int ntaps, float oversample_rate) {
+  if (!device_ok()) return nullptr;
+  if (numchans < 1 || ntaps < 0 || !(oversample_rate > 0)) { set_error(GRCUDA_EINVAL, "pfb_channelizer_ccf: bad arguments"); return nullptr; }
+  double intp = 0;
+  const double fltp = modf(numchans / oversample_rate, &intp);  // :56-60
+  if (fltp != 0.0) {
+    set_error(GRCUDA_EINVAL, "gr_pfb_channelizer: oversample rate must be N/i for i in [1, N]");
+    return nullptr;
+  }
+  grcuda_pfb* h = new grcuda_pfb;
+  h->M = numchans;
+  h->os = oversample_rate;
+  h->relative_rate = 1.0 / intp;                                  // :62
+  h->rr = (int)rintf(numchans / oversample_rate);                 // :81
+  h->output_multiple = 1;
+  while ((h->output_multiple * h->rr) % (int)numchans != 0) h->output_multiple++;  // :88-91
+  h->fft = fft_plan_create((int)numchans, +1);                   // gri_fft_complex(numchans, false) (:76)
+  if (!h->fft || h->base_init()) { delete h; return nullptr; }
+  h->set_geometry(std::vector<float>(taps, taps + ntaps));
+  if (h->upload_if_dirty()) { delete h; return nullptr; }
+  h->updated = true;  // the constructor calls set_taps (:74), so the first general_work returns 0
+  return h;
+}
+void grcuda_pfb_channelizer_ccf_destroy(grcuda_pfb* h) { delete h; }
+int grcuda_pfb_channelizer_ccf_set_taps(grcuda_pfb* h, const float* taps, int ntaps) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->set_geometry(std::vector<float>(taps, taps + ntaps));
+  h->updated = true;
+  return GRCUDA_OK;
+}
+unsigned grcuda_pfb_channelizer_ccf_history(grcuda_pfb* h) { return h->history; }
+int grcuda_pfb_channelizer_ccf_output_multiple(grcuda_pfb* h) { return h->output_multiple; }
+double grcuda_pfb_channelizer_ccf_relative_rate(grcuda_pfb* h) { return h->relative_rate; }
+int grcuda_pfb_channelizer_ccf_taps_per_filter(grcuda_pfb* h) { return h->T; }
+
+int grcuda_pfb_channelizer_ccf_work_device(grcuda_pfb* h, long nout, const grcuda_complex* d_in_rows,
+                                           grcuda_complex* d_out, void* stream) {
+  return h->run((const float2*)d_in_rows, (float2*)d_out, nout, h->pick(stream));
+}
+
+static int pfb_gate(grcuda_pfb* h) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->updated) { h->updated = false; return 1; }  // :164-167
+  return 0;
+}
+
+int grcuda_pfb_channelizer_ccf_work_interleaved(grcuda_pfb* h, int nout, const grcuda_complex* in, grcuda_complex* out,
+                                                int* consumed) {
+  if (consumed) *consumed = 0;
+  if (pfb_gate(h)) return 0;
+  if (nout <= 0) return 0;
+  const int toconsume = (int)rintf(nout / h->os);  // :170
+  const size_t rows_in = (size_t)toconsume + h->T;
+  const size_t M = h->M;
+  int rc;
+  if ((rc = h->d_in.reserve(rows_in * M * sizeof(float2))) || (rc = h->d_out.reserve((size_t)nout * M * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, rows_in * M * sizeof(float2), h->stream))) return rc;
+  if ((rc = h->run(h->d_in.as<float2>(), h->d_out.as<float2>(), nout, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * M * sizeof(float2), h->stream))) return rc;
+  if (consumed) *consumed = toconsume;
+  return nout;
+}
+
+int grcuda_pfb_channelizer_ccf_work(grcuda_pfb* h, int nout, const grcuda_complex* const* in, grcuda_complex* out,
+                                    int* consumed) {
+  if (consumed) *consumed = 0;
+  if (pfb_gate(h)) return 0;
+  if (nout <= 0) return 0;
+  const int toconsume = (int)rintf(nout / h->os);
+  const size_t len = (size_t)toconsume + h->T;  // items the reference may touch per stream
+  const size_t M = h->M;
+  int rc;
+  if ((rc = h->pin_in.reserve(M * len * sizeof(float2))) || (rc = h->d_stage.reserve(M * len * sizeof(float2))) ||
+      (rc = h->d_in.reserve(M * len * sizeof(float2))) || (rc = h->d_out.reserve((size_t)nout * M * sizeof(float2))))
+    return rc;
+  // gr_stream_to_streams in reverse: gather the M host streams (general/gr_stream_to_streams.cc:57-63)
+  for (size_t j = 0; j < M; j++) memcpy((char*)h->pin_in.p + j * len * sizeof(float2), in[j], len * sizeof(float2));
+  GRB_CUDA(cudaMemcpyAsync(h->d_stage.p, h->pin_in.p, M * len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  dim3 tb(32, 8), tg((unsigned)((len + 31) / 32), (unsigned)((M + 31) / 32));
+  transpose_streams_kernel<<<tg, tb, 0, h->stream>>>(h->d_stage.as<float2>(), h->d_in.as<float2>(), (int)M, (int)len);
+  GRB_LAUNCH_CHECK();
+  if ((rc = h->run(h->d_in.as<float2>(), h->d_out.as<float2>(), nout, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * M * sizeof(float2), h->stream))) return rc;
+  if (consumed) *consumed = toconsume;
+  return nout;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a5 / a6: gr_fft_vcc
+// =============================================================================================
+struct grcuda_fft : PlanBase {
+  int n = 0;
+  bool forward = true, shift = false;
+  FftPlan* plan = nullptr;
+  DevBuf d_window;
+  int nwindow = 0;
+  ~grcuda_fft() { fft_plan_destroy(plan); }
+  int set_window(const float* w, int nw) {  // gr_fft_vcc.cc:55-64
+    if (!(nw == 0 || nw == n)) return 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (nw) {
+      if (d_window.reserve((size_t)nw * sizeof(float))) return GRCUDA_ENOMEM;
+      if (cudaMemcpy(d_window.p, w, (size_t)nw * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return GRCUDA_ECUDA;
+    }
+    nwindow = nw;
+    return 1;
+  }
+  int run(const float2* d_in, float2* d_out, long nvec, cudaStream_t s) {
+    int in_rot = 0, out_rot = 0;
+    const float* win = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (nwindow) win = d_window.as<float>();                        // gr_fft_vcc_fftw.cc:68-72
+      else if (!forward && shift) in_rot = (int)floor(n / 2.0);       // :74-79
+      if (forward && shift) out_rot = n - (int)ceil(n / 2.0);         // :89-93
+    }
+    return fft_plan_exec(plan, d_in, d_out, nvec, win, in_rot % n, out_rot % n, s);
+  }
+};
+
+extern "C" {
+
+grcuda_fft* grcuda_fft_vcc_create(int fft_size, int forward, const float* window, int nwindow, int shift) {
+  if (!device_ok()) return nullptr;
+  if (fft_size <= 0) { set_error(GRCUDA_ERANGE, "gri_fftw: invalid fft_size"); return nullptr; }
+  grcuda_fft* h = new grcuda_fft;
+  h->n = fft_size;
+  h->forward = forward != 0;
+  h->shift = shift != 0;
+  h->plan = fft_plan_create(fft_size, forward ? -1 : +1);
+  if (!h->plan || h->base_init()) { delete h; return nullptr; }
+  h->set_window(window, nwindow);  // a wrong-sized window is ignored, like the reference constructor
+  return h;
+}
+void grcuda_fft_vcc_destroy(grcuda_fft* h) { delete h; }
+int grcuda_fft_vcc_set_window(grcuda_fft* h, const float* window, int nwindow) { return h->set_window(window, nwindow); }
+int grcuda_fft_vcc_work_device(grcuda_fft* h, long nvec, const grcuda_complex* d_in, grcuda_complex* d_out, void* stream) {
+  return h->run((const float2*)d_in, (float2*)d_out, nvec, h->pick(stream));
+}
+int grcuda_fft_vcc_work(grcuda_fft* h, int nvec, const grcuda_complex* in, grcuda_complex* out) {
+  if (nvec <= 0) return 0;
+  const size_t bytes = (size_t)nvec * h->n * sizeof(float2);
+  int rc;
+  if ((rc = h->d_in.reserve(bytes)) || (rc = h->d_out.reserve(bytes))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, bytes, h->stream))) return rc;
+  if ((rc = h->run(h->d_in.as<float2>(), h->d_out.as<float2>(), nvec, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, bytes, h->stream))) return rc;
+  return nvec;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a7 / a8: gr_quadrature_demod_cf
+// =============================================================================================
+struct grcuda_quad : PlanBase {
+  float gain = 1.f;
+  DeviceTables tabs;
+  int launch(const float2* d_in, float* d_out, long nrows, int nchan, cudaStream_t s) {
+    if (nrows <= 0 || nchan <= 0) return GRCUDA_OK;
+    float g;
+    { std::lock_guard<std::mutex> lk(mu); g = gain; }
+    quad_demod_kernel<<<grid_for(nrows * (long)nchan, 256, 16), 256, 0, s>>>(d_in, d_out, nrows, nchan, g, tabs.atan);
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_quad* grcuda_quadrature_demod_cf_create(float gain) {
+  if (!device_ok()) return nullptr;
+  grcuda_quad* h = new grcuda_quad;
+  h->gain = gain;
+  if (h->base_init() || get_tables(&h->tabs)) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_quadrature_demod_cf_destroy(grcuda_quad* h) { delete h; }
+int grcuda_quadrature_demod_cf_set_gain(grcuda_quad* h, float gain) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->gain = gain;
+  return GRCUDA_OK;
+}
+float grcuda_quadrature_demod_cf_gain(grcuda_quad* h) { return h->gain; }
+int grcuda_quadrature_demod_cf_work_device(grcuda_quad* h, long nrows, int nchan, const grcuda_complex* d_in,
+                                           float* d_out, void* stream) {
+  return h->launch((const float2*)d_in, d_out, nrows, nchan, h->pick(stream));
+}
+int grcuda_quadrature_demod_cf_work(grcuda_quad* h, int nout, const grcuda_complex* in, float* out) {
+  if (nout <= 0) return 0;
+  int rc;
+  if ((rc = h->d_in.reserve((size_t)(nout + 1) * sizeof(float2))) || (rc = h->d_out.reserve((size_t)nout * sizeof(float)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, (size_t)(nout + 1) * sizeof(float2), h->stream))) return rc;
+  if ((rc = h->launch(h->d_in.as<float2>(), h->d_out.as<float>(), nout, 1, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)nout * sizeof(float), h->stream))) return rc;
+  return nout;
+}
+int grcuda_fast_atan2f_device(const float* d_y, const float* d_x, float* d_out, long n, void* stream) {
+  if (!device_ok()) return GRCUDA_ECUDA;
+  DeviceTables t;
+  int rc = get_tables(&t);
+  if (rc) return rc;
+  if (n <= 0) return GRCUDA_OK;
+  fast_atan2f_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_y, d_x, d_out, n, t.atan);
+  GRB_LAUNCH_CHECK();
+  return GRCUDA_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a9 / a10 / a11: digital_clock_recovery_mm_ff (+ slicers)
+// =============================================================================================
+struct grcuda_mm : PlanBase {
+  int nchan = 1, order = GRCUDA_ORDER_SSE;
+  float omega0 = 2, gain_omega = 0, gain_mu = 0, mu0 = 0, limit = 0.001f;
+  float min_omega = 0, max_omega = 0, omega_mid = 0;
+  int slicer_levels = 0;
+  float slicer_alpha = 0, slicer_beta = 1;
+  DeviceTables tabs;
+  DevBuf d_state, d_counts, d_slice;
+  void calc_omega(float omega) {  // set_omega (digital_clock_recovery_mm_ff.h:75-80)
+    min_omega = (float)(omega * (1.0 - limit));
+    max_omega = (float)(omega * (1.0 + limit));
+    omega_mid = (float)(0.5 * (min_omega + max_omega));
+  }
+  int reset_state(bool only_mu, bool only_omega, float v) {
+    std::vector<MMChanState> st(nchan);
+    if (only_mu || only_omega) {
+      GRB_CUDA(cudaMemcpy(st.data(), d_state.p, st.size() * sizeof(MMChanState), cudaMemcpyDeviceToHost));
+      for (auto& s : st) { if (only_mu) s.mu = v; else s.omega = v; }
+    } else {
+      for (auto& s : st) { s.mu = mu0; s.omega = omega0; s.last_sample = 0.f; s.slicer_avg = 0.f; s.next_abs = 0; s.clamped = 0; s.overflow = 0; }
+    }
+    GRB_CUDA(cudaMemcpy(d_state.p, st.data(), st.size() * sizeof(MMChanState), cudaMemcpyHostToDevice));
+    return GRCUDA_OK;
+  }
+  int launch(const float* d_in, long ninput, long abs_row0, float* d_out, unsigned char* d_sl, int max_out, int* d_cnt,
+             cudaStream_t s) {
+    MMArgs a;
+    a.in = d_in; a.ninput = ninput; a.abs_row0 = abs_row0; a.nchan = nchan; a.out = d_out; a.sliced = d_sl;
+    a.max_out = max_out; a.counts = d_cnt; a.state = d_state.as<MMChanState>();
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      a.p.gain_omega = gain_omega; a.p.gain_mu = gain_mu; a.p.omega_mid = omega_mid; a.p.omega_relative_limit = limit;
+      a.slicer_levels = slicer_levels; a.slicer_alpha = slicer_alpha; a.slicer_beta = slicer_beta;
+    }
+    a.order = order; a.mmse_eff = tabs.mmse_eff;
+    const int threads = 64;
+    mm_kernel<<<(nchan + threads - 1) / threads, threads, 0, s>>>(a);
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_mm* grcuda_clock_recovery_mm_ff_create(int nchan, float omega, float gain_omega, float mu, float gain_mu,
+                                             float omega_relative_limit, int order) {
+  if (omega < 1) { set_error(GRCUDA_ERANGE, "clock rate must be > 0"); return nullptr; }                      // :58-59
+  if (gain_mu < 0 || gain_omega < 0) { set_error(GRCUDA_ERANGE, "Gains must be non-negative"); return nullptr; }  // :60-61
+  if (nchan < 1) { set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: nchan < 1"); return nullptr; }
+  if (!device_ok()) return nullptr;
+  grcuda_mm* h = new grcuda_mm;
+  h->nchan = nchan; h->order = order; h->omega0 = omega; h->gain_omega = gain_omega; h->mu0 = mu; h->gain_mu = gain_mu;
+  h->limit = omega_relative_limit;
+  h->calc_omega(omega);
+  if (h->base_init() || get_tables(&h->tabs) || h->d_state.reserve((size_t)nchan * sizeof(MMChanState)) ||
+      h->d_counts.reserve((size_t)nchan * sizeof(int)) || h->reset_state(false, false, 0.f)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void grcuda_clock_recovery_mm_ff_destroy(grcuda_mm* h) { delete h; }
+int grcuda_clock_recovery_mm_ff_forecast(grcuda_mm* h, int noutput_items) {  // :80-87 (uses the nominal omega)
+  float omega = h->omega0;
+  if (h->nchan == 1) {
+    MMChanState st;
+    if (cudaMemcpy(&st, h->d_state.p, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) omega = st.omega;
+  }
+  return (int)ceil((noutput_items * omega) + 8);
+}
+int grcuda_clock_recovery_mm_ff_get_state(grcuda_mm* h, int chan, float* mu, float* omega, float* last_sample) {
+  if (chan < 0 || chan >= h->nchan) return set_error(GRCUDA_EINVAL, "channel out of range");
+  MMChanState st;
+  GRB_CUDA(cudaMemcpy(&st, h->d_state.as<MMChanState>() + chan, sizeof st, cudaMemcpyDeviceToHost));
+  if (mu) *mu = st.mu;
+  if (omega) *omega = st.omega;
+  if (last_sample) *last_sample = st.last_sample;
+  return GRCUDA_OK;
+}
+int grcuda_clock_recovery_mm_ff_set_mu(grcuda_mm* h, float mu) { return h->reset_state(true, false, mu); }
+int grcuda_clock_recovery_mm_ff_set_omega(grcuda_mm* h, float omega) {
+  { std::lock_guard<std::mutex> lk(h->mu); h->calc_omega(omega); }
+  return h->reset_state(false, true, omega);
+}
+int grcuda_clock_recovery_mm_ff_set_gain_mu(grcuda_mm* h, float g) { std::lock_guard<std::mutex> lk(h->mu); h->gain_mu = g; return GRCUDA_OK; }
+int grcuda_clock_recovery_mm_ff_set_gain_omega(grcuda_mm* h, float g) { std::lock_guard<std::mutex> lk(h->mu); h->gain_omega = g; return GRCUDA_OK; }
+int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha) {
+  if (levels != 0 && levels != 2 && levels != 4) return set_error(GRCUDA_EINVAL, "slicer levels must be 0, 2 or 4");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->slicer_levels = levels;
+  h->slicer_alpha = alpha;
+  h->slicer_beta = (float)(1.0 - alpha);  // pager_slicer_fb.cc:40
+  return GRCUDA_OK;
+}
+int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long abs_row0, const float* d_in,
+                                            float* d_out, unsigned char* d_slice_out, int max_out, int* d_counts,
+                                            void* stream) {
+  return h->launch(d_in, ninput_rows, abs_row0, d_out, d_slice_out, max_out, d_counts, h->pick(stream));
+}
+int grcuda_clock_recovery_mm_ff_work(grcuda_mm* h, int noutput_items, int ninput_items, const float* in, float* out,
+                                     int* consumed, long abs_index0) {
+  if (consumed) *consumed = 0;
+  if (h->nchan != 1) return set_error(GRCUDA_EINVAL, "host work() is the single-stream form (nchan == 1)");
+  if (noutput_items <= 0 || ninput_items <= 0) return 0;
+  int rc;
+  if ((rc = h->d_in.reserve((size_t)ninput_items * sizeof(float))) || (rc = h->d_out.reserve((size_t)noutput_items * sizeof(float)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, (size_t)ninput_items * sizeof(float), h->stream))) return rc;
+  // the runtime re-presents unconsumed items at in[0]: the carried position is abs_index0
+  GRB_CUDA(cudaMemcpyAsync((char*)h->d_state.p + offsetof(MMChanState, next_abs), &abs_index0, sizeof(long long),
+                           cudaMemcpyHostToDevice, h->stream));
+  if ((rc = h->launch(h->d_in.as<float>(), ninput_items, abs_index0, h->d_out.as<float>(), nullptr, noutput_items,
+                      h->d_counts.as<int>(), h->stream)))
+    return rc;
+  int produced = 0;
+  MMChanState st;
+  GRB_CUDA(cudaMemcpyAsync(&produced, h->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  GRB_CUDA(cudaMemcpyAsync(&st, h->d_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+  GRB_CUDA(cudaStreamSynchronize(h->stream));
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)produced * sizeof(float), h->stream))) return rc;
+  if (consumed) *consumed = (int)(st.next_abs - abs_index0);
+  return produced;
+}
+
+}  // extern "C"
+
+struct grcuda_slicer : PlanBase {
+  int levels = 4;
+  float alpha = 0, beta = 1;
+  DevBuf d_avg;
+};
+
+extern "C" {
+
+static grcuda_slicer* slicer_new(int levels, float alpha) {
+  if (!device_ok()) return nullptr;
+  grcuda_slicer* h = new grcuda_slicer;
+  h->levels = levels;
+  h->alpha = alpha;
+  h->beta = (float)(1.0 - alpha);
+  if (h->base_init() || h->d_avg.reserve(sizeof(float)) || cudaMemset(h->d_avg.p, 0, sizeof(float)) != cudaSuccess) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+grcuda_slicer* grcuda_pager_slicer_fb_create(float alpha) { return slicer_new(4, alpha); }
+grcuda_slicer* grcuda_binary_slicer_fb_create(void) { return slicer_new(2, 0.f); }
+void grcuda_slicer_destroy(grcuda_slicer* h) { delete h; }
+float grcuda_pager_slicer_fb_dc_offset(grcuda_slicer* h) {
+  float v = 0.f;
+  cudaMemcpy(&v, h->d_avg.p, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
+}
+int grcuda_slicer_work(grcuda_slicer* h, int n, const float* in, unsigned char* out) {
+  if (n <= 0) return 0;
+  int rc;
+  if ((rc = h->d_in.reserve((size_t)n * sizeof(float))) || (rc = h->d_out.reserve((size_t)n))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, (size_t)n * sizeof(float), h->stream))) return rc;
+  slicer_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_in.as<float>(), h->d_out.as<unsigned char>(), n, h->levels,
+                                                         h->alpha, h->beta, h->d_avg.as<float>());
+  GRB_LAUNCH_CHECK();
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)n, h->stream))) return rc;
+  return n;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// a12 / a13: map_bb + unpack_k_bits_bb + digital_correlate_access_code_bb
+// =============================================================================================
+struct grcuda_corr : PlanBase {
+  int nchan = 1;
+  CorrParams p;
+  DevBuf d_state, d_hits, d_nhits;
+  int set_code(const char* code) {  // set_access_code (:64-85)
+    const size_t len = strlen(code);
+    if (len > 64) return set_error(GRCUDA_ERANGE, "access_code is > 64 bits");
+    std::lock_guard<std::mutex> lk(mu);
+    p.mask = len ? ((~0ULL) >> (64 - len)) << (64 - len) : 0ULL;
+    p.flag_bit = len ? 1ULL << (64 - len) : 0ULL;
+    p.access_code = 0;
+    for (unsigned i = 0; i < 64; i++) {
+      p.access_code <<= 1;
+      if (i < len) p.access_code |= (unsigned long long)(code[i] & 1);
+    }
+    return GRCUDA_OK;
+  }
+  int launch(const unsigned char* d_sym, const int* d_counts, int fixed_count, const int* map, int nmap, int k,
+             unsigned char* d_out, CorrHit* d_hits_, int max_hits, int* d_nhits_, cudaStream_t s) {
+    CorrArgs a;
+    a.symbols = d_sym; a.counts = d_counts; a.fixed_count = fixed_count; a.nchan = nchan;
+    for (int i = 0; i < 256; i++) a.map[i] = (unsigned char)i;  // gr_map_bb.cc:40-46
+    for (int i = 0; i < std::min(nmap, 256); i++) a.map[i] = (unsigned char)map[i];
+    a.bits_per_symbol = k; a.out = d_out; a.state = d_state.as<CorrChanState>();
+    { std::lock_guard<std::mutex> lk(mu); a.p = p; }
+    a.hits = d_hits_; a.max_hits = max_hits; a.nhits = d_nhits_;
+    const int threads = 64;
+    corr_kernel<<<(nchan + threads - 1) / threads, threads, 0, s>>>(a);
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_corr* grcuda_correlate_access_code_bb_create(int nchan, const char* access_code, int threshold) {
+  if (nchan < 1 || !access_code) { set_error(GRCUDA_EINVAL, "correlate_access_code_bb: bad arguments"); return nullptr; }
+  if (strlen(access_code) > 64) { set_error(GRCUDA_ERANGE, "access_code is > 64 bits"); return nullptr; }  // :54-57
+  if (!device_ok()) return nullptr;
+  grcuda_corr* h = new grcuda_corr;
+  h->nchan = nchan;
+  h->p.threshold = (unsigned)threshold;
+  if (h->base_init() || h->set_code(access_code) || h->d_state.reserve((size_t)nchan * sizeof(CorrChanState)) ||
+      h->d_nhits.reserve(sizeof(int)) || h->d_hits.reserve(1024 * sizeof(CorrHit)) ||
+      cudaMemset(h->d_state.p, 0, (size_t)nchan * sizeof(CorrChanState)) != cudaSuccess) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void grcuda_correlate_access_code_bb_destroy(grcuda_corr* h) { delete h; }
+int grcuda_correlate_access_code_bb_set_access_code(grcuda_corr* h, const char* code) { return h->set_code(code); }
+int grcuda_correlate_access_code_bb_work(grcuda_corr* h, int n, const unsigned char* in, unsigned char* out) {
+  if (h->nchan != 1) return set_error(GRCUDA_EINVAL, "host work() is the single-stream form (nchan == 1)");
+  if (n <= 0) return 0;
+  int rc;
+  if ((rc = h->d_in.reserve((size_t)n)) || (rc = h->d_out.reserve((size_t)n))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, (size_t)n, h->stream))) return rc;
+  GRB_CUDA(cudaMemsetAsync(h->d_nhits.p, 0, sizeof(int), h->stream));
+  if ((rc = h->launch(h->d_in.as<unsigned char>(), nullptr, n, nullptr, 0, 0, h->d_out.as<unsigned char>(),
+                      h->d_hits.as<CorrHit>(), 1024, h->d_nhits.as<int>(), h->stream)))
+    return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)n, h->stream))) return rc;
+  return n;
+}
+int grcuda_correlate_access_code_bb_work_symbols_device(grcuda_corr* h, const unsigned char* d_symbols, int sym_rows,
+                                                        const int* d_counts, const int* map, int nmap,
+                                                        int bits_per_symbol, unsigned char* d_out, int out_rows,
+                                                        grcuda_hit* d_hits, int max_hits, int* d_nhits, void* stream) {
+  (void)out_rows;
+  static_assert(sizeof(grcuda_hit) == sizeof(CorrHit), "hit record layout");
+  return h->launch(d_symbols, d_counts, sym_rows, map, nmap, bits_per_symbol, d_out, (CorrHit*)d_hits, max_hits,
+                   d_nhits, h->pick(stream));
+}
+
+}  // extern "C"
+
+// ---- internal accessors (chain.cu) -------------------------------------------------------------
+#include "internal.h"
+namespace grb {
+void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }
+size_t mm_state_bytes(grcuda_mm* h) { return (size_t)h->nchan * sizeof(MMChanState); }
+void* corr_state_ptr(grcuda_corr* h) { return h->d_state.p; }
+size_t corr_state_bytes(grcuda_corr* h) { return (size_t)h->nchan * sizeof(CorrChanState); }
+}  // namespace grb

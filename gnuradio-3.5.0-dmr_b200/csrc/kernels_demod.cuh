@@ -1,0 +1,202 @@
+// Batched per-channel demod tail on the channelizer output, layout [time][channel] so that a
+// warp's 32 lanes are 32 neighbouring channels at the same time step (coalesced 128/256 B rows).
+// Every kernel reproduces the reference arithmetic bit for bit (csrc/gr_math.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "gr_math.cuh"
+
+namespace grb {
+
+// ---- gr_quadrature_demod_cf::work, batched (gr_quadrature_demod_cf.cc:46-62) -------------------
+// in: [1 + nrows][nchan] complex (row 0 = history), out: [nrows][nchan].  12 B/sample of HBM.
+__global__ void __launch_bounds__(256) quad_demod_kernel(const float2* __restrict__ in, float* __restrict__ out,
+                                                         long nrows, int nchan, float gain,
+                                                         const float* __restrict__ atan_table) {
+  __shared__ float tab[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = atan_table[i];
+  __syncthreads();
+  const long total = nrows * nchan;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const float2 prev = __ldg(in + g);
+    const float2 cur = __ldg(in + g + nchan);
+    out[g] = quad_demod(cur, prev, gain, tab);
+  }
+}
+
+__global__ void fast_atan2f_kernel(const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out,
+                                   long n, const float* __restrict__ atan_table) {
+  __shared__ float tab[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = atan_table[i];
+  __syncthreads();
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < n; g += (long)gridDim.x * blockDim.x)
+    out[g] = fast_atan2f(y[g], x[g], tab);
+}
+
+// ---- gr_fir_filter_fff::work, batched over channels (gr_fir_filter_XXX.cc.t:66-88) ------------
+// in: [ntaps-1 + nout*decim][nchan] (history-prefixed), out: [nout][nchan]; out[o][c] =
+// dot(rt, in[o*decim .. +ntaps)[c]) in the selected reference summation order.
+// abs0 = absolute stream index of in row 0 (decides the SSE lane phase).
+#define FFF_MAX_TAPS_SMEM 4096
+__global__ void __launch_bounds__(128) fir_fff_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                      long nout, int nchan, int decim, const float* __restrict__ rt_g,
+                                                      int ntaps, int order, long abs0, int rows_per_thread) {
+  extern __shared__ float rt[];
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) rt[i] = rt_g[i];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchan) return;
+  const long o0 = (long)blockIdx.y * rows_per_thread;
+  const long o1 = min(nout, o0 + rows_per_thread);
+  for (long o = o0; o < o1; o++) {
+    const float* p = in + (o * decim) * (long)nchan + c;
+    const float v = (order == GR_ORDER_SSE) ? dot_sse(rt, ntaps, p, nchan, mod4(abs0 + o * decim))
+                                            : dot_generic(rt, ntaps, p, nchan);
+    out[o * (long)nchan + c] = v;
+  }
+}
+
+// ---- digital_clock_recovery_mm_ff::general_work, batched (digital_clock_recovery_mm_ff.cc:102-139)
+// One thread per channel: the loop is sequential in time (mu/omega/last_sample feed back), but
+// the channels are independent and, in [time][channel] layout, the lanes of a warp walk the
+// same rows at (nearly) the same pace, so their loads share 128 B lines.
+struct MMChanState {  // persists across work calls (the block's members d_mu, d_omega, ...)
+  float mu, omega, last_sample, slicer_avg;
+  long long next_abs;  // absolute input index of the next in[ii] for this channel
+  int clamped;         // times the loop tried to step before the first buffered row (see mm_kernel)
+  int overflow;        // times the per-call output capacity stopped the loop before the input did
+};
+
+struct MMArgs {
+  const float* in;       // [ninput][nchan], row 0 has absolute index abs_row0
+  long ninput;
+  long abs_row0;
+  int nchan;
+  float* out;            // [max_out][nchan] soft symbols
+  unsigned char* sliced; // [max_out][nchan] or nullptr
+  int max_out;
+  int* counts;           // [nchan]
+  MMChanState* state;    // [nchan]
+  MMParams p;
+  int order;
+  int slicer_levels;     // 0, 2 or 4
+  float slicer_alpha, slicer_beta;
+  const float* mmse_eff; // [129][8] coefficients applied to in[ii+0..7]
+};
+
+__global__ void __launch_bounds__(128) mm_kernel(const MMArgs a) {
+  __shared__ float tab[129 * 8];
+  for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) tab[i] = a.mmse_eff[i];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.nchan) return;
+  MMChanState st = a.state[c];
+  MMState s;
+  s.mu = st.mu; s.omega = st.omega; s.last_sample = st.last_sample;
+  float avg = st.slicer_avg;
+  long ii = (long)(st.next_abs - a.abs_row0);  // may be > 0: samples already consumed
+  const long ni = a.ninput - 8;                 // :112
+  int oo = 0;
+  const float* __restrict__ col = a.in + c;
+  // floor(mu) can be negative when gain_mu*mm_val < -omega (unnormalised input): the reference then
+  // re-reads older items of its circular buffer.  We keep a carry of older rows in front of each
+  // block for that; stepping even further back is clamped (and counted) instead of reading out
+  // of bounds, which is where the reference's behaviour is undefined anyway.
+  if (ii < 0) { ii = 0; st.clamped++; }
+  while (oo < a.max_out && ii < ni) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __ldg(col + (ii + i) * (long)a.nchan);
+    const float o = mmse8(tab + 8 * mm_imu(s.mu), v, a.order, mod4(a.abs_row0 + ii));
+    a.out[(long)oo * a.nchan + c] = o;
+    if (a.sliced) {
+      unsigned char d = 0;
+      if (a.slicer_levels == 4) d = slice4(o, avg, a.slicer_alpha, a.slicer_beta);
+      else if (a.slicer_levels == 2) d = slice2(o);
+      a.sliced[(long)oo * a.nchan + c] = d;
+    }
+    oo++;
+    ii += mm_update(s, a.p, o);
+    if (ii < 0) { ii = 0; st.clamped++; }
+  }
+  if (ii < ni) st.overflow++;
+  st.mu = s.mu; st.omega = s.omega; st.last_sample = s.last_sample; st.slicer_avg = avg;
+  st.next_abs = a.abs_row0 + ii;
+  a.state[c] = st;
+  a.counts[c] = oo;
+}
+
+// stand-alone slicer (single stream; the recurrence on d_avg is sequential when alpha != 0)
+__global__ void slicer_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long n, int levels,
+                              float alpha, float beta, float* avg_state) {
+  if (levels == 2 || alpha == 0.0f) {
+    // no state: fully parallel (avg stays avg*beta + 0 = avg*1 -> constant)
+    const float avg0 = *avg_state;
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < n; g += (long)gridDim.x * blockDim.x) {
+      if (levels == 2) out[g] = slice2(in[g]);
+      else { float avg = avg0; out[g] = slice4(in[g], avg, 0.0f, beta); }
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float avg = *avg_state;
+    for (long g = 0; g < n; g++) out[g] = slice4(in[g], avg, alpha, beta);
+    *avg_state = avg;
+  }
+}
+
+// ---- gr_map_bb -> gr_unpack_k_bits_bb -> digital_correlate_access_code_bb, batched ------------
+// (gr_map_bb.cc:49-61, gr_unpack_k_bits_bb.cc:53-70, digital_correlate_access_code_bb.cc:87-133)
+struct CorrChanState {
+  unsigned long long data_reg, flag_reg;
+  long long nbits;  // absolute number of bits already processed on this channel
+};
+struct CorrHit { int channel; int pad; long long bit_index; };
+
+struct CorrArgs {
+  const unsigned char* symbols;  // [sym_rows][nchan] (slicer decisions) or bits when bits_per_symbol == 0
+  const int* counts;             // [nchan] valid symbols per channel (nullptr: fixed_count)
+  int fixed_count;
+  int nchan;
+  unsigned char map[256];        // gr_map_bb table
+  int bits_per_symbol;           // k of gr_unpack_k_bits_bb (0: input already is one bit per byte)
+  unsigned char* out;            // [out_rows][nchan] or nullptr
+  CorrChanState* state;
+  CorrParams p;
+  CorrHit* hits;
+  int max_hits;
+  int* nhits;
+};
+
+__global__ void __launch_bounds__(128) corr_kernel(const CorrArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.nchan) return;
+  CorrChanState st = a.state[c];
+  const int n = a.counts ? a.counts[c] : a.fixed_count;
+  const int k = a.bits_per_symbol;
+  long ob = 0;
+  for (int s = 0; s < n; s++) {
+    const unsigned sym = a.symbols[(long)s * a.nchan + c];
+    if (k == 0) {
+      const unsigned char t = corr_step(st.data_reg, st.flag_reg, a.p, sym);
+      if (a.out) a.out[ob * a.nchan + c] = t;
+      if (t & 2) {
+        const int h = atomicAdd(a.nhits, 1);
+        if (h < a.max_hits) { a.hits[h].channel = c; a.hits[h].pad = 0; a.hits[h].bit_index = st.nbits + ob; }
+      }
+      ob++;
+    } else {
+      const unsigned d = a.map[sym];
+      for (int b = k - 1; b >= 0; b--) {  // MSB first
+        const unsigned char t = corr_step(st.data_reg, st.flag_reg, a.p, (d >> b) & 1u);
+        if (a.out) a.out[ob * a.nchan + c] = t;
+        if (t & 2) {
+          const int h = atomicAdd(a.nhits, 1);
+          if (h < a.max_hits) { a.hits[h].channel = c; a.hits[h].pad = 0; a.hits[h].bit_index = st.nbits + ob; }
+        }
+        ob++;
+      }
+    }
+  }
+  st.nbits += ob;
+  a.state[c] = st;
+}
+
+}  // namespace grb

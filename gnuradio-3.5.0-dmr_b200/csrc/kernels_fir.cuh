@@ -1,0 +1,244 @@
+// FIR-class kernels of the hot path: decimating complex FIR with real or complex taps
+// (gr_fir_filter_ccf, gr_freq_xlating_fir_filter_ccf) and the polyphase branch filters of
+// gr_pfb_channelizer_ccf.  All of them are HBM-bound by design: every
+// input sample is read from HBM once, every output written once; reuse lives in registers /
+// shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include "fft_radix.cuh"
+
+namespace grb {
+
+// ===========================================================================================
+// Decimating FIR, complex input, real (CTAPS=false) or complex (CTAPS=true) taps.
+//   out[o] = sum_{i<ntaps} rt[i] * in[o*D + i]        (in history-prefixed, rt = reversed taps;
+//   gr_fir_XXX_generic.cc.t:83-103, gr_fir_filter_XXX.cc.t:81-85)
+// Polyphase form so that a thread owns R CONSECUTIVE outputs and slides a register window:
+//   i = D*q + p  ->  out[o] = sum_p sum_q rtp[p][q] * xp[p][o + q],   xp[p][n] = in[n*D + p]
+// The CTA stages its input span once into shared memory, split by phase p (conflict-free both
+// for the coalesced fill and for the strided register-window reads: row pitch = 4 mod 16 float2,
+// in-row index padded n + n/8 so that threads R=8 apart hit distinct banks).
+// Per phase and tap the thread does R (x2, x4 for complex taps) FMAs for ONE new LDS.64.
+// Optional epilogue: multiply by the running rotator e^{j*(o_abs)*theta} (freq_xlating).
+// ===========================================================================================
+struct FirArgs {
+  const float2* in;   // history-prefixed input
+  float2* out;
+  long nout;
+  int decim;
+  int ntaps;
+  int J;              // taps per phase, padded to a multiple of FIR_R
+  const float* rtp;   // [decim][J] floats (real taps) or float2 (complex taps), zero padded
+  int tile_out;       // outputs per CTA tile = blockDim.x * FIR_R
+  int pitch;          // smem float2 per phase row (padded)
+  // rotator epilogue (freq_xlating): phase(o) = theta * (o + out_index0), evaluated in double
+  int rotate;
+  double theta;
+  long out_index0;
+};
+
+#define FIR_R 8
+
+__device__ __forceinline__ int fir_phys(int n) { return n + (n >> 3); }
+
+template <bool CTAPS>
+__global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
+  extern __shared__ float2 fir_smem[];
+  const int D = a.decim, J = a.J;
+  float2* xs = fir_smem;                                   // [D][pitch]
+  float* taps_s = reinterpret_cast<float*>(xs + (size_t)D * a.pitch);  // [D][J] (x2 if complex)
+  const int ntap_words = D * J * (CTAPS ? 2 : 1);
+  for (int i = threadIdx.x; i < ntap_words; i += blockDim.x) taps_s[i] = a.rtp[i];
+
+  const long ntiles = (a.nout + a.tile_out - 1) / a.tile_out;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long o_base = tile * a.tile_out;
+    const int tile_n = (int)min((long)a.tile_out, a.nout - o_base);
+    // input span: phase rows hold n in [0, tile_n_pad + J), idx = (o_base + n)*D + p
+    const int rows_n = a.tile_out + J;
+    const long in_base = o_base * D;
+    const long in_valid = (a.nout - 1) * (long)D + a.ntaps;  // number of valid input items
+    __syncthreads();  // previous tile fully consumed (also orders the taps fill)
+    const int span = rows_n * D;
+    for (int s = threadIdx.x; s < span; s += blockDim.x) {
+      const int n = s / D, p = s - n * D;
+      const long gi = in_base + s;
+      float2 v = make_float2(0.f, 0.f);
+      if (gi < in_valid) v = __ldg(a.in + gi);
+      xs[(size_t)p * a.pitch + fir_phys(n)] = v;
+    }
+    __syncthreads();
+
+    const int o0 = threadIdx.x * FIR_R;  // first output of this thread within the tile
+    float2 acc[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) acc[r] = make_float2(0.f, 0.f);
+    if (o0 < tile_n) {
+      for (int p = 0; p < D; p++) {
+        const float2* xrow = xs + (size_t)p * a.pitch;
+        float2 w[FIR_R];  // sliding window: w[r] = xp[p][o0 + q + r]
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) w[r] = xrow[fir_phys(o0 + r)];
+        for (int q0 = 0; q0 < J; q0 += FIR_R) {
+#pragma unroll
+          for (int u = 0; u < FIR_R; u++) {
+            // tap q = q0+u multiplies window slot (u + r) mod R for output r
+            if (CTAPS) {
+              const float2 t = reinterpret_cast<const float2*>(taps_s)[p * J + q0 + u];
+#pragma unroll
+              for (int r = 0; r < FIR_R; r++) {
+                const float2 x = w[(u + r) % FIR_R];
+                acc[r].x += t.x * x.x - t.y * x.y;
+                acc[r].y += t.x * x.y + t.y * x.x;
+              }
+            } else {
+              const float t = taps_s[p * J + q0 + u];
+#pragma unroll
+              for (int r = 0; r < FIR_R; r++) {
+                const float2 x = w[(u + r) % FIR_R];
+                acc[r].x += t * x.x;
+                acc[r].y += t * x.y;
+              }
+            }
+            // slot u (holding xp[o0+q0+u]) is dead now: refill with xp[o0 + q0 + u + R]
+            w[u] = xrow[fir_phys(o0 + q0 + u + FIR_R)];
+          }
+        }
+      }
+      if (a.rotate) {
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) {
+          const double ph = a.theta * (double)(a.out_index0 + o_base + o0 + r);
+          double s, c;
+          sincos(ph, &s, &c);
+          const float2 rot = make_float2((float)c, (float)s);
+          acc[r] = cmul(acc[r], rot);
+        }
+      }
+      // 8 consecutive float2 = 64 B per thread; neighbouring threads are contiguous
+      float2* o = a.out + o_base + o0;
+#pragma unroll
+      for (int r = 0; r < FIR_R; r++)
+        if (o0 + r < tile_n) o[r] = acc[r];
+    }
+  }
+}
+
+// ===========================================================================================
+// Polyphase branch FIR of gr_pfb_channelizer_ccf (oversample_rate == 1):
+//   u[m][k] = sum_{t<T} h[k + t*M] * X[m + H - t][M-1-k]          (gr_pfb_channelizer_ccf.cc:171-188)
+// X = interleaved input rows [time][M] with H = T history rows in front (history = T+1, :136).
+// One thread owns one column j = M-1-k and walks rows_per_thread consecutive rows keeping the
+// last TT samples of its column in registers (TT >= T, taps zero padded); neighbouring threads
+// read neighbouring columns, so every load/store is a fully coalesced 256 B warp access and each
+// input sample is fetched from HBM exactly once per row tile (+ T-1 halo rows per tile).
+// taps_t[t*M + j] = h[(M-1-j) + t*M]  (transposed so the per-thread tap fetch is coalesced too).
+// ===========================================================================================
+struct PfbFirArgs {
+  const float2* x;     // [H + nrows][M]
+  float2* u;           // [nrows][M]   FFT input order (index k)
+  const float* taps_t; // [TT][M]
+  int M;
+  int T;               // real taps per branch (history rows H = T)
+  long nrows;
+  int rows_per_thread;
+};
+
+template <int TT>
+__global__ void __launch_bounds__(128) pfb_fir_kernel(const PfbFirArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.M) return;
+  const long m0 = (long)blockIdx.y * a.rows_per_thread;
+  if (m0 >= a.nrows) return;
+  const long m1 = min(a.nrows, m0 + a.rows_per_thread);
+  const int M = a.M, H = a.T;
+  float h[TT];
+#pragma unroll
+  for (int t = 0; t < TT; t++) h[t] = __ldg(a.taps_t + (size_t)t * M + j);
+  // window slot s holds buffer row b with b % TT == s; output m needs buffer rows m+H-t, t<TT
+  float2 w[TT];
+  const float2* __restrict__ xc = a.x + j;
+  {
+    // preload the TT-1 rows preceding buffer row (m0 + H): rows m0+H-TT+1 .. m0+H-1
+#pragma unroll
+    for (int s = 0; s < TT; s++) w[s] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int d = 1; d < TT; d++) {
+      const long b = m0 + H - d;
+      if (b >= 0 && d < a.T + 0) {  // rows older than T-1 back only ever meet zero taps
+        w[(TT - d) % TT] = __ldg(xc + b * (long)M);
+      }
+    }
+  }
+  float2* __restrict__ uc = a.u + (M - 1 - j);
+  // process rows in groups of TT so that window indices are compile-time
+  for (long mb = m0; mb < m1; mb += TT) {
+#pragma unroll
+    for (int s = 0; s < TT; s++) {
+      const long m = mb + s;
+      if (m < m1) {
+        // slot for this row: relative index s in the group; the preload put row (m0+H-d) at
+        // slot (TT-d)%TT, i.e. row (mb+H+s) belongs to slot s.
+        w[s] = __ldg(xc + (m + H) * (long)M);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+          const float2 x = w[(s - t + TT) % TT];
+          acc.x += h[t] * x.x;
+          acc.y += h[t] * x.y;
+        }
+        uc[m * (long)M] = acc;
+      }
+    }
+  }
+}
+
+// Generic / oversampled branch FIR (any T, any oversample_rate = M/rr):  thread per (o, j).
+// Reference: gr_pfb_channelizer_ccf.cc:169-196.
+struct PfbFirGenArgs {
+  const float2* x;     // [H + nrows_in][M], H = T
+  float2* u;           // [nout][M]
+  const float* taps;   // h[k + t*M] zero padded to T*M
+  int M, T, rr;
+  long nout;
+};
+
+__global__ void pfb_fir_generic_kernel(const PfbFirGenArgs a) {
+  const int M = a.M, T = a.T;
+  const long total = a.nout * M;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long o = g / M;
+    const int j = (int)(g - o * M);
+    const long c = (o + 1) * (long)a.rr - 1;       // unwrapped filter phase
+    const int last = (int)(c % M);
+    const long n = 1 + c / M;                       // reference's n for this output
+    const int filt = (last - j + M) % M;            // filter index applied to stream j
+    const long nn = n - (j > last ? 1 : 0);         // &in[n] or &in[n-1]
+    const int dst = M - ((j + a.rr) % M) - 1;       // d_idxlut[j]
+    float2 acc = make_float2(0.f, 0.f);
+    for (int t = 0; t < T; t++) {
+      const float hv = __ldg(a.taps + filt + (size_t)t * M);
+      const float2 xv = __ldg(a.x + (nn + T - 1 - t) * (long)M + j);
+      acc.x += hv * xv.x;
+      acc.y += hv * xv.y;
+    }
+    a.u[o * (long)M + dst] = acc;
+  }
+}
+
+// gr_stream_to_streams layout change on the device: staging [stream][len] -> rows [len][M]
+__global__ void transpose_streams_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int M, int len) {
+  __shared__ float2 tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx: time, by: stream
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int s = by + r, t = bx + threadIdx.x;
+    if (s < M && t < len) tile[r][threadIdx.x] = src[(size_t)s * len + t];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int t = bx + r, s = by + threadIdx.x;
+    if (s < M && t < len) dst[(size_t)t * M + s] = tile[threadIdx.x][r];
+  }
+}
+
+}  // namespace grb

@@ -30,6 +30,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
 
 #define GRCUDA_OK 0
 #define GRCUDA_EINVAL (-1) /* std::invalid_argument in the reference */
@@ -272,6 +275,15 @@ typedef struct {
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r);
 /* copy the compacted sync hits of the last block to the host; returns their number */
 int grcuda_dmr_chain_read_hits(grcuda_dmr_chain* h, grcuda_hit* hits, int max_hits);
+/* smallest block process_* accepts (the carries of one block must not overlap the next) */
+int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h);
+/* Time-shard support.  A shard that does not start at stream row 0 creates its own
+ * chain, seek()s to (first_row - warmup_rows()), processes warmup_rows() rows of halo (results
+ * discarded) so that every FIR history is that of the continuous stream, then import_state()s the
+ * loop state its left neighbour exported and continues bit-identically to a single-GPU run. */
+int grcuda_dmr_chain_warmup_rows(grcuda_dmr_chain* h);
+int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row);
+long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h);
 /* shard hand-off: export / import the per-channel loop state
  * {mu, omega, last_sample, next input index, slicer avg, correlator registers} so that the next
  * time shard continues exactly where this one stopped.  Buffer = state_bytes() bytes (device). */
@@ -279,6 +291,9 @@ size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h);
 int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream);
 int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void* stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,390 @@
+"""GPU parity tests, block by block: the CUDA path, called through the
+C ABI (grb200 -> libgr_cuda.so), against the oracle restatement and the committed reference fixtures.
+
+Tolerances (BASELINE.json north_star): FIR / channelizer / FFT outputs max error <= 1e-4 relative to
+the output peak; everything in the demod tail (discriminator, RRC in either reference summation
+order, M&M, slicers, correlator) BIT EXACT."""
+import numpy as np
+import pytest
+
+from conftest import has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+TOL = 1e-4
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def B():
+    from grb200 import blocks
+    return blocks
+
+
+def crandn(rng, n):
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+# ---- a1 fir_filter_ccf ---------------------------------------------------------------------------
+def test_fir_ccf_fixture(B, golden):
+    fx = golden[1]
+    y = B.run(B.fir_filter_ccf(4, fx["fir_ccf_taps"]), fx["fir_ccf_x"])
+    assert relerr(y, fx["fir_ccf_y_sse"]) < TOL and relerr(y, fx["fir_ccf_y_generic"]) < TOL
+    assert relerr(y, fx["fir_ccf_y_sse"]) < 2e-6  # in practice float-rounding level
+
+
+def test_fir_ccf_small_shapes_like_reference_qa(B, orc):
+    # qa_gr_fir_ccf.cc:87-159: ntaps 0..9, output lengths 0..17, tol |expected| * 1e-5
+    rng = np.random.default_rng(0)
+    for ntaps in range(0, 10):
+        blk = B.fir_filter_ccf(1, rng.integers(-32767, 32768, ntaps).astype(np.float32)) if ntaps else B.fir_filter_ccf(1, [])
+        for nout in (0, 1, 2, 7, 17):
+            taps = rng.integers(-32767, 32768, ntaps).astype(np.float32)
+            blk.set_taps(taps)
+            x = (rng.integers(-32767, 32768, nout + max(ntaps - 1, 0)) +
+                 1j * rng.integers(-32767, 32768, nout + max(ntaps - 1, 0))).astype(np.complex64)
+            assert len(blk.work(nout, x)) == 0          # "return 0 once" after set_taps (:74-79)
+            assert blk.history() == ntaps
+            y = blk.work(nout, x)
+            exp = orc.fir_ccf(taps, 1, x, hist_prefixed=True) if nout else np.empty(0, np.complex64)
+            assert len(y) == nout
+            if nout:
+                assert np.all(np.abs(y - exp) <= np.abs(exp) * 1e-5 + 1e-3)
+
+
+@pytest.mark.parametrize("decim,ntaps,n", [(1, 64, 5000), (4, 64, 100003), (3, 17, 4099), (16, 257, 70000), (5, 1, 1000),
+                                           (2, 1000, 30000)])
+def test_fir_ccf_vs_oracle(B, orc, decim, ntaps, n):
+    rng = np.random.default_rng(ntaps * 131 + decim)
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    x = crandn(rng, n)
+    y = B.run(B.fir_filter_ccf(decim, taps), x)
+    assert relerr(y, orc.fir_ccf(taps, decim, x)) < 5e-6
+    # chunked work() calls give the same stream
+    y2 = B.run(B.fir_filter_ccf(decim, taps), x, chunk=777)
+    assert np.array_equal(y, y2)
+
+
+def test_fir_ccf_cfg1_full_size_properties(B, orc):
+    """BASELINE config 1 at full size: 64-tap low-pass, decimate by 4, 10 M complex samples."""
+    from grb200 import firdes
+    rng = np.random.default_rng(1)
+    n = 10_000_000
+    x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+    taps = firdes.low_pass(1.0, 1.0, 0.125, 0.11)[:64]
+    assert len(taps) == 64
+    blk = B.fir_filter_ccf(4, taps)
+    y = B.run(blk, x)
+    assert len(y) == n // 4
+    # oracle on three windows (start, middle, end)
+    for a in (0, 1_234_567 * 4, n - 4 * 50_000):
+        seg = x[max(a - 63, 0): a + 4 * 50_000]
+        ref = orc.fir_ccf(taps, 4, np.concatenate([np.zeros(63 - min(a, 63), np.complex64), seg]), hist_prefixed=True)
+        assert relerr(y[a // 4: a // 4 + len(ref)], ref) < 5e-6
+    # linearity: F(2x) == 2 F(x) exactly (power-of-two scaling commutes with rounding)
+    y2 = B.run(blk, 2 * x[:400_000])
+    assert np.array_equal(y2, 2 * y[:100_000])
+
+
+# ---- a2 fir_filter_fff -----------------------------------------------------------------------------
+def test_fir_fff_fixture_bit_exact(B, golden):
+    fx = golden[1]
+    for order, nm in ((B.ORDER_SSE, "sse"), (B.ORDER_GENERIC, "generic")):
+        y = B.run(B.fir_filter_fff(1, fx["fir_fff_taps"], order), fx["fir_fff_x"])
+        assert np.array_equal(y, fx["fir_fff_y_" + nm])
+
+
+def test_fir_fff_known_io(B, golden):
+    k = golden[0]["fir_fff"]  # qa_gr_fir_fff.cc:58-112
+    x = np.array(k["input_1"], np.float32)
+    for taps, exp in ((k["taps_1a"], k["expected_1a"]), (k["taps_1b"], k["expected_1b"])):
+        n = len(x) - len(taps) + 1
+        y = B.fir_filter_fff(1, taps).work(n, x, abs_index0=0)
+        np.testing.assert_allclose(y, exp[:n], atol=1e-3)
+
+
+@pytest.mark.parametrize("ntaps", [1, 2, 3, 4, 5, 8, 9, 29, 64, 111, 500])
+def test_fir_fff_bit_exact_vs_oracle(B, orc, ntaps):
+    rng = np.random.default_rng(ntaps)
+    taps = rng.standard_normal(ntaps).astype(np.float32)
+    x = rng.standard_normal(20011).astype(np.float32)
+    for decim in (1, 3):
+        for order in (B.ORDER_SSE, B.ORDER_GENERIC):
+            y = B.run(B.fir_filter_fff(decim, taps, order), x, chunk=4099)
+            assert np.array_equal(y, orc.fir_fff(taps, decim, x, order=order)), (ntaps, decim, order)
+
+
+def test_fir_fff_batched_device_layout(B, orc):
+    import torch
+    rng = np.random.default_rng(7)
+    nchan, n, ntaps = 37, 900, 29
+    taps = rng.standard_normal(ntaps).astype(np.float32)
+    x = rng.standard_normal((n, nchan)).astype(np.float32)
+    buf = np.concatenate([np.zeros((ntaps - 1, nchan), np.float32), x])
+    for order in (B.ORDER_SSE, B.ORDER_GENERIC):
+        d_in = torch.from_numpy(buf).cuda()
+        d_out = torch.empty((n, nchan), dtype=torch.float32, device="cuda")
+        B.fir_filter_fff(1, taps, order).work_device(n, nchan, d_in, d_out, -(ntaps - 1))
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        for c in range(nchan):
+            assert np.array_equal(got[:, c], orc.fir_fff(taps, 1, x[:, c], order=order)), c
+
+
+# ---- a3 freq_xlating_fir_filter_ccf -------------------------------------------------------------------
+def test_freq_xlating_fixture(B, golden, orc):
+    fx = golden[1]
+    d, fc, fs = fx["fx_args"]
+    blk = B.freq_xlating_fir_filter_ccf(int(d), fx["fx_proto"], float(fc), float(fs))
+    y = B.run(blk, fx["fx_x"], chunk=100)   # chunked: the rotator phase must carry across calls
+    assert relerr(y, fx["fx_y"]) < TOL
+    assert relerr(y, fx["fx_y"]) < 1e-5
+    # retune: set_center_freq -> work returns 0 once, then the new composite taps are live
+    blk.set_center_freq(-100e3)
+    x = fx["fx_x"][:4096]
+    hist = np.concatenate([np.zeros(blk.history() - 1, np.complex64), x])
+    assert len(blk.work(16, hist)) == 0
+    y2 = blk.work(len(x) // int(d), hist)
+    ct, inc = orc.freq_xlating_taps(fx["fx_proto"], -100e3, float(fs), int(d))
+    core = orc.fir_ccc(ct, int(d), x)  # ct = forward taps as handed to set_taps
+    # magnitude is rotation independent: checks the retuned composite filter
+    assert relerr(np.abs(y2), np.abs(core)) < 1e-4
+
+
+# ---- a4 / a14 pfb_channelizer_ccf -----------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["m160", "m20", "m8os2", "m10os5"])
+def test_pfb_fixture_both_entry_points(B, golden, tag):
+    fx = golden[1]
+    M, osr, consumed = fx["pfb_%s_meta" % tag]
+    M = int(M)
+    taps, x, want = fx["pfb_%s_taps" % tag], fx["pfb_%s_x" % tag], fx["pfb_%s_y" % tag]
+    blk = B.pfb_channelizer_ccf(M, taps, float(osr))
+    T = blk.taps_per_filter()
+    assert blk.history() == T + 1
+    rows = len(x) // M
+    xs = x.reshape(rows, M)
+    nout = want.shape[0]
+    streams = [np.concatenate([np.zeros(T, np.complex64), xs[:, j]]) for j in range(M)]
+    y0, c0 = blk.general_work(nout, streams)
+    assert len(y0) == 0 and c0 == 0          # first general_work after set_taps returns 0 (:164-167)
+    y, c = blk.general_work(nout, streams)
+    assert c == int(consumed) and relerr(y, want) < TOL and relerr(y, want) < 5e-6
+    inter = np.concatenate([np.zeros((T, M), np.complex64), xs])
+    y2, c2 = blk.general_work_interleaved(nout, inter)
+    assert c2 == c and np.array_equal(y2, y)
+    blk.set_taps(taps * 2)
+    assert len(blk.general_work_interleaved(nout, inter)[0]) == 0
+    y3, _ = blk.general_work_interleaved(nout, inter)
+    assert relerr(y3, 2 * want) < 5e-6
+
+
+def test_pfb_constructor_contract(B, orc):
+    with pytest.raises(ValueError):
+        B.pfb_channelizer_ccf(8, np.ones(32, np.float32), 3.0)   # std::invalid_argument (:57-60)
+    for M, osr in ((8, 1.0), (8, 2.0), (8, 4.0), (10, 5.0), (160, 1.0), (12, 1.5)):
+        blk = B.pfb_channelizer_ccf(M, np.ones(3 * M + 1, np.float32), osr)
+        assert blk.output_multiple() == orc.pfb_output_multiple(M, osr)
+        assert blk.taps_per_filter() == orc.pfb_taps_per_filter(M, 3 * M + 1) == 4
+        assert abs(blk.relative_rate() - 1.0 / (M / osr)) < 1e-12
+
+
+@pytest.mark.parametrize("M,T,rows", [(8000, 16, 40), (8000, 3, 24), (4096, 8, 32), (1000, 16, 64), (7, 5, 50), (2, 33, 80)])
+def test_pfb_vs_oracle_sizes(B, orc, M, T, rows):
+    rng = np.random.default_rng(M + T)
+    ntaps = M * T - (M // 3)                      # ragged: last branch taps are zero padded
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    x = crandn(rng, M * rows)
+    blk = B.pfb_channelizer_ccf(M, taps)
+    inter = np.concatenate([np.zeros((T, M), np.complex64), x.reshape(rows, M)])
+    blk.general_work_interleaved(rows, inter)
+    y, c = blk.general_work_interleaved(rows, inter)
+    want, wc = orc.pfb_channelizer_ccf(M, taps, x)
+    assert c == wc == rows and relerr(y, want) < 5e-6
+
+
+def test_pfb_tone_lands_in_bin(B):
+    M = 160
+    n = np.arange(M * 64)
+    x = np.exp(2j * np.pi * 5 / M * n).astype(np.complex64)
+    from grb200 import firdes
+    taps = firdes.low_pass_2(1.0, M * 12500.0, 6000.0, 2000.0, 60.0, firdes.WIN_BLACKMAN_hARRIS)
+    blk = B.pfb_channelizer_ccf(M, taps)
+    T = blk.taps_per_filter()
+    inter = np.concatenate([np.zeros((T, M), np.complex64), x.reshape(64, M)])
+    blk.general_work_interleaved(64, inter)
+    y, _ = blk.general_work_interleaved(64, inter)
+    p = np.abs(y[-1])
+    assert np.argmax(p) == 5 and p[5] > 100 * np.delete(p, 5).max()
+
+
+# ---- a5 / a6 fft_vcc ----------------------------------------------------------------------------------------
+def test_fft_32_known_answer(B, golden):
+    k = golden[0]["fft_vcc_32"]  # qa_fft.py:50-158
+    p = k["primes"]
+    src = np.array([complex(p[2 * i], p[2 * i + 1]) for i in range(32)], np.complex64)
+    exp = np.array(k["expected_re"]) + 1j * np.array(k["expected_im"])
+    y = B.fft_vcc(32, True, [], False).work(1, src)
+    assert np.all(np.abs(y - exp) <= k["abs_eps"] + k["rel_eps"] * np.abs(exp))
+    yi = B.fft_vcc(32, False, [], False).work(1, exp.astype(np.complex64))
+    assert np.all(np.abs(yi / 32 - src) <= 1e-9 + 4e-4 * np.abs(src))
+
+
+def test_fft_vcc_fixtures(B, golden):
+    fx = golden[1]
+    y = B.fft_vcc(4096, True, fx["fft4096_win"], False).work(2, fx["fft4096_x"])
+    assert relerr(y, fx["fft4096_y"]) < 2e-6
+    y = B.fft_vcc(4096, True, fx["fft4096_win"], True).work(2, fx["fft4096_x"])
+    assert relerr(y, fx["fft4096_y_shift"]) < 2e-6
+    y = B.fft_vcc(160, False, [], True).work(3, fx["fft160_x"])
+    assert relerr(y, fx["fft160_y_inv_shift"]) < 2e-6
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 7, 8, 10, 12, 16, 20, 30, 32, 60, 64, 100, 128, 160, 200, 243, 256, 400, 512,
+                                625, 1000, 1024, 1600, 2000, 2048, 3200, 4000, 4096, 6400, 8000, 77, 1001])
+def test_fft_sizes_directions_shift(B, orc, N):
+    rng = np.random.default_rng(N)
+    nvec = 3 if N > 256 else 37
+    x = crandn(rng, N * nvec)
+    w = rng.uniform(0.1, 1, N).astype(np.float32)
+    for fwd in (True, False):
+        for shift in (False, True):
+            for win in (None, w):
+                y = B.fft_vcc(N, fwd, win if win is not None else [], shift).work(nvec, x)
+                assert relerr(y, orc.fft_vcc(N, fwd, win, shift, x)) < 5e-6, (N, fwd, shift, win is not None)
+
+
+def test_fft_vcc_contract(B):
+    with pytest.raises(IndexError):
+        B.fft_vcc(0, True, [], False)              # std::out_of_range (gri_fft.cc:104-105)
+    f = B.fft_vcc(64, True, [], False)
+    assert f.set_window(np.ones(64)) is True
+    assert f.set_window(np.ones(63)) is False      # gr_fft_vcc.cc:55-64
+    assert f.set_window([]) is True
+
+
+# ---- a7 / a8 quadrature demod ----------------------------------------------------------------------------------
+def test_quad_demod_bit_exact(B, golden):
+    fx = golden[1]
+    blk = B.quadrature_demod_cf(float(fx["quad_gain"]))
+    assert np.array_equal(B.run(blk, fx["quad_x"], chunk=1234), fx["quad_y"])
+    y = B.run(B.quadrature_demod_cf(1.0), np.array([1, 1j, -1, -1j], np.complex64))
+    np.testing.assert_allclose(y, [0, np.pi / 2, np.pi / 2, np.pi / 2], atol=1e-6)
+    blk.set_gain(2.5)
+    assert blk.gain() == 2.5
+
+
+def test_fast_atan2f_device_bit_exact(B, golden):
+    import ctypes as C
+    import torch
+    from grb200 import lib
+    fx = golden[1]
+    y = torch.from_numpy(fx["atan_y"]).cuda()
+    x = torch.from_numpy(fx["atan_x"]).cuda()
+    o = torch.empty_like(y)
+    lib.check(lib.load().grcuda_fast_atan2f_device(C.c_void_p(y.data_ptr()), C.c_void_p(x.data_ptr()),
+                                                   C.c_void_p(o.data_ptr()), C.c_long(len(fx["atan_y"])), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy(), fx["atan_out"])
+
+
+# ---- a9 / a10 M&M clock recovery -------------------------------------------------------------------------------------
+def test_mm_known_answers(B, golden):
+    k = golden[0]["clock_recovery_mm_ff"]
+    blk = B.clock_recovery_mm_ff(*k["test02"]["args"])
+    assert blk.forecast(10) == 28
+    y, consumed = blk.general_work(100, np.ones(100, np.float32))
+    assert len(y) == 46 and consumed == 92
+    np.testing.assert_allclose(y[-30:], k["test02"]["expected_last30"], atol=0.5e-5)
+    blk = B.clock_recovery_mm_ff(*k["test04"]["args"])
+    y, _ = blk.general_work(4000, np.tile([1, 1, -1, -1], 1000).astype(np.float32))
+    np.testing.assert_allclose(np.abs(y[-30:]), k["test04"]["expected_pm"], atol=0.05)
+    with pytest.raises(IndexError):
+        B.clock_recovery_mm_ff(0.5, 0.01, 0.5, 0.01)
+    with pytest.raises(IndexError):
+        B.clock_recovery_mm_ff(2, 0.01, 0.5, -0.01)
+
+
+def test_mm_fixture_bit_exact_and_chunked(B, golden, orc):
+    fx = golden[1]
+    a = [float(v) for v in fx["mm_args"]]
+    x = fx["mm_x"]
+    for order, nm in ((B.ORDER_SSE, "sse"), (B.ORDER_GENERIC, "generic")):
+        blk = B.clock_recovery_mm_ff(*a, order=order)
+        y, c = blk.general_work(len(x), x)
+        assert c == int(fx["mm_consumed_" + nm]) and np.array_equal(y, fx["mm_y_" + nm])
+        # scheduler-style chunking: unconsumed items are re-presented, state persists in the block
+        blk = B.clock_recovery_mm_ff(*a, order=order)
+        pos, outs = 0, []
+        while pos < len(x) - 8:
+            seg = x[pos: pos + 500]
+            y2, c2 = blk.general_work(64, seg, abs_index0=pos)
+            if c2 == 0 and len(y2) == 0:
+                break
+            outs.append(y2)
+            pos += c2
+        got = np.concatenate(outs)
+        assert np.array_equal(got, fx["mm_y_" + nm][: len(got)]) and len(got) >= len(fx["mm_y_" + nm]) - 4
+        mu, om, _ = blk._state()
+        assert 0.0 <= mu <= 1.0 and abs(om - a[0]) <= a[4] + 1e-6
+
+
+def test_mm_batched_channels_bit_exact(B, orc):
+    import torch
+    from grb200 import synth
+    rng = np.random.default_rng(11)
+    nchan, n = 70, 3000
+    sps = 12500.0 / 4800.0
+    x = np.zeros((n, nchan), np.float32)
+    for c in range(nchan):
+        sym = rng.integers(0, 4, int(n / sps) + 2) * 2 - 3
+        x[:, c] = (synth.shape_symbols(sym, sps, nsamples=n) + 0.1 * rng.standard_normal(n)) * (1.0 if c % 7 else 1.5)
+    args = (sps, 0.25 * 0.175 ** 2, 0.5, 0.175, 0.005)
+    for order in (B.ORDER_SSE, B.ORDER_GENERIC):
+        blk = B.clock_recovery_mm_ff(*args, nchan=nchan, order=order)
+        blk.set_slicer(4, 0.0)
+        d_in = torch.from_numpy(x).cuda()
+        max_out = n
+        d_out = torch.zeros((max_out, nchan), dtype=torch.float32, device="cuda")
+        d_sl = torch.zeros((max_out, nchan), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(nchan, dtype=torch.int32, device="cuda")
+        blk.work_device(n, 0, d_in, d_out, d_sl, max_out, d_cnt)
+        torch.cuda.synchronize()
+        out, sl, cnt = d_out.cpu().numpy(), d_sl.cpu().numpy(), d_cnt.cpu().numpy()
+        for c in range(nchan):
+            want, _ = orc.mm_work(orc.mm_new(*args), x[:, c], order=order)
+            assert cnt[c] == len(want), c
+            assert np.array_equal(out[:cnt[c], c], want), c
+            assert np.array_equal(sl[:cnt[c], c], orc.slicer4(want, 0.0)), c
+
+
+# ---- a11 slicers, a12/a13 correlator -------------------------------------------------------------------------------
+def test_slicers_bit_exact(B, golden):
+    fx, k = golden[1], golden[0]
+    assert np.array_equal(B.run(B.pager_slicer_fb(0.0), fx["slicer_x"]), fx["slicer_y_a0"])
+    s = B.pager_slicer_fb(0.01)
+    assert np.array_equal(B.run(s, fx["slicer_x"], chunk=333), fx["slicer_y_a01"])
+    assert s.dc_offset() != 0.0
+    assert list(B.run(B.binary_slicer_fb(), np.array(k["binary_slicer"]["x"], np.float32))) == k["binary_slicer"]["z"]
+
+
+def test_correlator_known_answers_and_fixture(B, golden):
+    k, fx = golden[0]["correlate_access_code"], golden[1]
+    assert list(B.run(B.correlate_access_code_bb(k["t1_code"], 0), np.array(k["t1_src"], np.uint8))) == k["t1_expected"]
+    code = [(b >> i) & 1 for b in k["default_access_code_bytes"] for i in range(8)]
+    src = code + [1, 0, 1, 1] + [0] * 64
+    exp = [0] * 64 + code + [3, 0, 1, 1]
+    blk = B.correlate_access_code_bb("".join(str(b) for b in code), 0)
+    assert list(B.run(blk, np.array(src, np.uint8), chunk=13)) == exp     # registers persist across work calls
+    with pytest.raises(IndexError):
+        B.correlate_access_code_bb("1" * 65, 0)
+    from grb200 import synth
+    blk = B.correlate_access_code_bb(synth.access_code_string(synth.DMR_BS_DATA_SYNC_BITS), 2)
+    assert np.array_equal(B.run(blk, fx["corr_bits"], chunk=1000), fx["corr_out_t2"])
