@@ -304,3 +304,37 @@ def firdes_root_raised_cosine(gain, fs, sym, alpha, ntaps):
 
 def firdes_window(win, ntaps, beta=6.76):
     return _firdes(lib().grref_firdes_window, int(win), int(ntaps), C.c_double(beta))
+
+
+# ---- flagship chain on the CPU, multi-threaded (bench.py --impl reference / cpu_baseline) --------
+class _ChainParams(C.Structure):
+    _fields_ = [("M", C.c_uint), ("pfb_taps", C.POINTER(C.c_float)), ("pfb_ntaps", C.c_int), ("quad_gain", C.c_float),
+                ("rrc_taps", C.POINTER(C.c_float)), ("rrc_ntaps", C.c_int), ("omega", C.c_float),
+                ("gain_omega", C.c_float), ("mu", C.c_float), ("gain_mu", C.c_float), ("limit", C.c_float),
+                ("slicer_alpha", C.c_float), ("symbol_map", C.POINTER(C.c_int)), ("symbol_map_len", C.c_int),
+                ("access_code", C.c_char_p), ("threshold", C.c_int)]
+
+
+def bench_chain(M, pfb_taps, quad_gain, rrc_taps, omega, gain_omega, mu, gain_mu, limit, slicer_alpha, symbol_map,
+                access_code, threshold, x, nthreads, fft_fast=True, keep_y=False):
+    """Runs the reference's own blocks over x (rows*M interleaved complex64) with nthreads host threads.
+    Returns (seconds_channelizer, seconds_demod, nhits, Y or None)."""
+    L = lib()
+    pt = np.ascontiguousarray(pfb_taps, np.float32)
+    rt = np.ascontiguousarray(rrc_taps, np.float32)
+    x = np.ascontiguousarray(x, np.complex64)
+    rows = len(x) // M
+    mp = (C.c_int * len(symbol_map))(*[int(v) for v in symbol_map])
+    p = _ChainParams(M, _fp(pt), len(pt), quad_gain, _fp(rt), len(rt), omega, gain_omega, mu, gain_mu, limit,
+                     slicer_alpha, C.cast(mp, C.POINTER(C.c_int)), len(symbol_map), access_code.encode(), threshold)
+    secs = (C.c_double * 2)()
+    nh = C.c_long(0)
+    y = np.zeros(rows * M, np.complex64) if keep_y else None
+    L.grref_set_fft_fast(int(bool(fft_fast)))
+    try:
+        rc = L.grref_bench_chain(C.byref(p), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_long(rows), int(nthreads), secs,
+                                 C.byref(nh), y.ctypes.data_as(C.POINTER(C.c_float)) if keep_y else None)
+    finally:
+        L.grref_set_fft_fast(0)
+    assert rc == 0
+    return secs[0], secs[1], nh.value, (y.reshape(rows, M) if keep_y else None)

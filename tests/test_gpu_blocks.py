@@ -79,7 +79,7 @@ def test_fir_ccf_cfg1_full_size_properties(B, orc):
     rng = np.random.default_rng(1)
     n = 10_000_000
     x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
-    taps = firdes.low_pass(1.0, 1.0, 0.125, 0.11)[:64]
+    taps = firdes.low_pass(1.0, 1.0, 0.125, 0.05)[:64]
     assert len(taps) == 64
     blk = B.fir_filter_ccf(4, taps)
     y = B.run(blk, x)
