@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""bench.py -- input MS/s of the wideband PFB channelizer + batched DMR demod on 1/2/4/8 B200.
+
+Workload (BASELINE.json configs[4], named in `config.workload`): 100 MS/s complex stream -> 8000 x
+12.5 kHz channels (gr_pfb_channelizer_ccf, 16 taps/branch) -> per channel quadrature_demod_cf ->
+RRC fir_filter_fff -> clock_recovery_mm_ff -> 4-level slicer -> map/unpack -> correlate_access_code_bb.
+One "step" = one pass of the whole path over one time block of `--rows` channel-rate rows
+(default 12500 rows = 1 s of signal = 100 M input samples = 800 MB, i.e. larger than L2) per GPU.
+N > 1: one process per GPU (torchrun), the stream is time sharded (block = step*N + rank), halos and
+the per-channel loop state travel by NCCL send/recv (grb200/sharding.py).  Weak scaling.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU implementation of
+the same path (oracle/_ref: the reference sources compiled in place) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200"))
+
+M = 8000
+T = 16
+FS_CHANNEL = 12500.0
+WORKLOAD = "cfg5: 100 MS/s -> 8000 x 12.5 kHz PFB channelizer (16 taps/branch) + batched DMR 4FSK demod + sync search"
+STAGE_BYTES = {  # algorithmic HBM bytes per input sample, per stage
+    "pfb_fir": 16.0, "pfb_fft": 16.0, "quad_demod": 12.0, "rrc_fir": 8.0,
+    "mm_slicer": 4.0 + (4.0 + 1.0) / (FS_CHANNEL / 4800.0), "map_unpack_corr": (1.0 + 2.0) / (FS_CHANNEL / 4800.0),
+}
+
+
+def chain_config(max_rows, keep_bytes=False):
+    import numpy as np
+    from grb200 import chain, firdes
+    fs = M * FS_CHANNEL
+    # ~128 000-tap prototype (T = 16 taps per branch): low_pass_2, Blackman-harris, 60 dB
+    taps = firdes.low_pass_2(float(M), fs, 5400.0, 2131.0, 60.0, firdes.WIN_BLACKMAN_hARRIS)
+    assert (len(taps) + M - 1) // M == T, len(taps)
+    return chain.DmrChainConfig(M, np.asarray(taps, np.float32), fs_channel=FS_CHANNEL, max_rows_per_block=max_rows,
+                                keep_bytes=keep_bytes)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            r = [c.strip() for c in r]
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def run_reference(args):
+    """The reference arm: the reference's own blocks (oracle/_ref/libgrref.so) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import refharness as R
+    from grb200 import synth
+    kind = "reference"
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgrref.so was not built (needs /root/reference at build time)"}))
+        return 0
+    cfg = chain_config(args.cpu_rows)
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(6)
+    rows = args.cpu_rows
+    x, _ = synth.wideband_compose(rng, M, min(rows, 64), [], noise_sigma=1.0)  # white noise rows (cost is data independent)
+    x = np.tile(x, rows // min(rows, 64) + 1)[: rows * M]
+    kw = dict(M=M, pfb_taps=cfg.pfb_taps, quad_gain=cfg.quad_gain, rrc_taps=cfg.rrc_taps, omega=cfg.omega,
+              gain_omega=cfg.gain_omega, mu=cfg.mu, gain_mu=cfg.gain_mu, limit=cfg.omega_relative_limit,
+              slicer_alpha=cfg.slicer_alpha, symbol_map=cfg.symbol_map, access_code=cfg.access_code, threshold=cfg.threshold,
+              x=x, nthreads=cores, fft_fast=True)
+    for _ in range(args.warmup_ref):
+        R.bench_chain(**kw)
+    tot = 0.0
+    for _ in range(args.steps_ref):
+        s0, s1, _, _ = R.bench_chain(**kw)
+        tot += s0 + s1
+    ms_step = tot / args.steps_ref * 1e3
+    value = rows * M / (tot / args.steps_ref) / 1e6
+    sample = ("%d rows x %d channels = %.1f M input samples per step; reference blocks driven in one large chunk per "
+              "thread, channelizer time-sharded and demod tail channel-sharded over %d host threads; FFTW absent -> scalar "
+              "float32 mixed-radix FFT stand-in; block construction untimed" % (rows, M, rows * M / 1e6, cores))
+    line = {
+        "impl": "reference", "metric": "input MS/s, PFB channelizer+DMR demod", "value": value, "unit": "MS/s", "n_gpus": args.gpus,
+        "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from grb200 import chain, lib, sharding, synth_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    R = args.rows
+    cfg0 = chain_config(R)
+    probe = chain.DmrChain(chain_config(512))
+    halo = probe.warmup_rows() if world > 1 else 0   # extra input rows re-processed by each shard
+    del probe
+    cfg = chain_config(R + halo)
+    ch = chain.DmrChain(cfg)
+    Th = ch.history_rows()
+    x, active = synth_torch.wideband_block(M, R, Th + halo, args.active, 1234 + rank, dev)   # [(Th+halo) + R][M]
+    plan = sharding.TimeShardPlan(world, rank, R, halo)
+    ring = sharding.RingExchanger(plan)
+    state = torch.zeros(ch.state_bytes(), dtype=torch.uint8, device=dev)
+    halo_in = x[: Th + halo] if world > 1 else None
+    tail_rows = x[x.shape[0] - (Th + halo):] if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(s, last):
+        if world == 1:
+            ch.process_device(x, R)
+            return
+        works = ring.exchange_halo(tail_rows, halo_in, s)          # NCCL send/recv of the input halo
+        ring.wait_all(works)
+        ch.seek_async(plan.abs_start(s) - halo, stream)
+        ch.process_front_device(x, halo + R)                        # all ranks concurrently
+        if ring.recv_state(state, s):                               # loop state of block b-1 (ring)
+            ch.import_state(state, stream)
+        ch.process_tail_device()
+        ch.export_state(state, stream)
+        ring.send_state(state, s, last)
+
+    total_steps = args.warmup + args.steps
+    for s in range(args.warmup):
+        step(s, total_steps - 1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ch.set_profiling(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for s in range(args.warmup, total_steps):
+        step(s, total_steps - 1)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.launches() - n0
+    clocks = sampler.stop() if sampler else None
+    prof = ch.profile_read()
+    ch.set_profiling(False)
+    hits, nhits = ch.read_hits(16)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    hit_counts = sharding.gather_counts(nhits, world, dev)            # final result gather
+    samples_per_step = R * M
+    value = world * args.steps * samples_per_step / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-pointer C ABI (pinned host input, H2D + D2H inside the timed region)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host = torch.empty((Th + R, M), dtype=torch.complex64, pin_memory=True)
+    host.copy_(x[halo: halo + Th + R])
+    ch2 = chain.DmrChain(cfg0)
+    ch2.process_host(host.data_ptr(), R)
+    ch2.read_hits(16)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        ch2.process_host(host.data_ptr(), R)
+        _, nh = ch2.read_hits(1 << 16)
+        d2h += 4 + min(nh, 1 << 16) * 16
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * samples_per_step / float(t.item()) / 1e6
+    del ch2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (device time share inside the timed region) --------------
+    hbm_peak, peak_kind = peaks()
+    stage_ms = {k: v[0] for k, v in prof.items()}
+    stage_ln = {k: v[1] for k, v in prof.items()}
+    busy = sum(stage_ms.values()) or 1.0
+    stages = {}
+    rows_done = (halo + R) * args.steps
+    for k in STAGE_BYTES:
+        if stage_ms[k] <= 0:
+            continue
+        bytes_total = STAGE_BYTES[k] * rows_done * M
+        gbs = bytes_total / (stage_ms[k] * 1e-3) / 1e9
+        stages[k] = {"ms_per_step": stage_ms[k] / args.steps, "launches_per_step": stage_ln[k] / args.steps,
+                     "share": stage_ms[k] / busy, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    d = stages[dom]
+    per_launch_bytes = STAGE_BYTES[dom] * rows_done * M / max(stage_ln[dom], 1)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": None,
+                "algorithmic_bytes_per_launch": per_launch_bytes,
+                "avg_launch_ms": stage_ms[dom] / max(stage_ln[dom], 1), "stages": stages}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get(dom)
+        except Exception:
+            pass
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) --------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import refharness as Rh
+            if Rh.available():
+                rows_cpu = args.cpu_rows
+                xs = x[halo + Th: halo + Th + rows_cpu].cpu().numpy().reshape(-1)
+                cores = os.cpu_count() or 1
+                s0, s1, nh, _ = Rh.bench_chain(M=M, pfb_taps=cfg.pfb_taps, quad_gain=cfg.quad_gain, rrc_taps=cfg.rrc_taps,
+                                               omega=cfg.omega, gain_omega=cfg.gain_omega, mu=cfg.mu, gain_mu=cfg.gain_mu,
+                                               limit=cfg.omega_relative_limit, slicer_alpha=cfg.slicer_alpha,
+                                               symbol_map=cfg.symbol_map, access_code=cfg.access_code, threshold=cfg.threshold,
+                                               x=xs, nthreads=cores, fft_fast=True)
+                cpu = {"value": rows_cpu * M / (s0 + s1) / 1e6, "unit": "MS/s", "cores": cores, "kind": "reference",
+                       "sample": "first %d rows (%.1f M samples) of the GPU workload; reference blocks (oracle/_ref) on %d host "
+                                 "threads, channelizer %.2f s + demod %.2f s; FFTW stand-in = scalar float32 FFT"
+                                 % (rows_cpu, rows_cpu * M / 1e6, cores, s0, s1), "sync_hits": nh}
+        except Exception as e:  # the baseline must never take the bench down
+            cpu = {"value": None, "unit": "MS/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": "input MS/s, PFB channelizer+DMR demod", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_step_per_gpu": R, "samples_per_step_per_gpu": samples_per_step,
+                   "active_channels": int(args.active), "halo_rows": halo, "sharding": "time blocks, block = step*N + rank",
+                   "l2": "input block (%.0f MB) and every intermediate are larger than the 126 MB L2" % (samples_per_step * 8 / 1e6)},
+        "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": (Th + R) * M * 8, "d2h_bytes_per_step": d2h // e2e_steps,
+                "steps": e2e_steps, "api": "grcuda_dmr_chain_process_host + grcuda_dmr_chain_read_hits (pinned host input)"},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "sync_hits_last_step": hit_counts,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=12500, help="channel-rate rows per step per GPU (12500 = 1 s of signal)")
+    ap.add_argument("--active", type=int, default=800, help="channels carrying DMR bursts (10 % occupancy)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # the reference arm's steps are bounded samples (--cpu-rows) so that K steps finish within minutes
+    args.steps_ref = max(1, args.steps)
+    args.warmup_ref = max(0, args.warmup)
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

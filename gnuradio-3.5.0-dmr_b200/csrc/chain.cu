@@ -34,7 +34,12 @@ struct grcuda_dmr_chain {
   cudaStream_t stream = nullptr;
   Stager stager;
   long long abs_row = 0;  // absolute channel-rate row index of the next new row
-  int last_rows = 0;
+  EventProfiler prof;     // stages: 2 quad, 3 rrc, 4 mm, 5 corr, 6 carries (0/1 live in the pfb plan)
+  int last_rows = 0, front_rows = 0;
+  bool accumulate_hits = false;
+  cudaStream_t last_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  DevBuf d_stage[2];
   ~grcuda_dmr_chain() {
     if (pfb) grcuda_pfb_channelizer_ccf_destroy(pfb);
     if (quad) grcuda_quadrature_demod_cf_destroy(quad);
@@ -42,6 +47,11 @@ struct grcuda_dmr_chain {
     if (mm) grcuda_clock_recovery_mm_ff_destroy(mm);
     if (corr) grcuda_correlate_access_code_bb_destroy(corr);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int i = 0; i < 2; i++) {
+      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    }
   }
 };
 
@@ -114,6 +124,16 @@ int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
   h->abs_row = abs_row;
   return GRCUDA_OK;
 }
+// stream-ordered variant for the steady state of a time shard (no device-wide synchronisation)
+int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* stream_) {
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  const size_t M = h->M;
+  GRB_CUDA(cudaMemsetAsync(h->Y.p, 0, M * sizeof(float2), s));
+  GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
+  GRB_CUDA(cudaMemsetAsync(h->F.p, 0, (size_t)KEEP * M * sizeof(float), s));
+  h->abs_row = abs_row;
+  return GRCUDA_OK;
+}
 long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h) { return h->abs_row; }
 
 size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h) { return mm_state_bytes(h->mm) + corr_state_bytes(h->corr); }
@@ -132,10 +152,13 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
   return GRCUDA_OK;
 }
 
-int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
+// front stage: channelizer -> discriminator -> matched filter (finite-memory stages: a time shard
+// can run this on its block + halo without waiting for anybody)
+int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
     return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  h->last_stream = s;
   const size_t M = h->M;
   const long R = nrows;
   int rc;
@@ -145,39 +168,117 @@ int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d
   // 1. channelizer: [T + R][M] -> Y rows 1..R
   if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + M), s))) return rc;
   // 2. discriminator: Y rows 0..R -> D rows (nrrc-1)..
+  h->prof.begin(2, s);
   if ((rc = grcuda_quadrature_demod_cf_work_device(h->quad, R, (int)M, (const grcuda_complex*)Y, D + (size_t)(h->nrrc - 1) * M, s))) return rc;
+  h->prof.end(s);
   // 3. matched filter: D (history-prefixed; row 0 is absolute row abs_row-(nrrc-1)) -> F rows KEEP..
+  h->prof.begin(3, s);
   if ((rc = grcuda_fir_filter_fff_work_device(h->rrc, R, (int)M, D, F + (size_t)KEEP * M, (long)(h->abs_row - (h->nrrc - 1)), s))) return rc;
+  h->prof.end(s);
+  h->front_rows = nrows;
+  return GRCUDA_OK;
+}
+
+// tail stage: the loops with infinite memory (M&M + DC-tracking slicer + correlator registers); a
+// time shard runs it after importing its left neighbour's loop state
+int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
+  if (h->front_rows <= 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_tail without a pending process_front");
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  h->last_stream = s;
+  const size_t M = h->M;
+  const long R = h->front_rows;
+  int rc;
+  float2* Y = h->Y.as<float2>();
+  float* D = h->D.as<float>();
+  float* F = h->F.as<float>();
   // 4. clock recovery + slicer over F rows [abs_row-KEEP, abs_row+R)
+  h->prof.begin(4, s);
   if ((rc = grcuda_clock_recovery_mm_ff_work_device(h->mm, KEEP + R, (long)(h->abs_row - KEEP), F, h->soft.as<float>(),
                                                     h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), s)))
     return rc;
+  h->prof.end(s);
   // 5. dibits -> bits -> sync correlation
-  GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  h->prof.begin(5, s);
   if ((rc = grcuda_correlate_access_code_bb_work_symbols_device(
            h->corr, h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), h->symbol_map.data(),
            (int)h->symbol_map.size(), 2, h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr, 2 * h->max_sym,
            (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
     return rc;
-  // 6. carries for the next block (small device-to-device copies, stream ordered)
-  // (nrows >= min_rows guarantees that source and destination never overlap)
+  h->prof.end(s);
+  // 6. carries for the next block (small device-to-device copies, stream ordered;
+  //    nrows >= min_rows guarantees that source and destination never overlap)
+  h->prof.begin(6, s);
   GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   if (h->nrrc > 1)
     GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync(F, F + (size_t)R * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  h->prof.end(s, 0);
   h->abs_row += R;
-  h->last_rows = nrows;
+  h->last_rows = (int)R;
+  h->front_rows = 0;
   return GRCUDA_OK;
 }
 
+int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
+  int rc = grcuda_dmr_chain_process_front_device(h, d_in, nrows, stream_);
+  return rc ? rc : grcuda_dmr_chain_process_tail_device(h, stream_);
+}
+
+int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on) {
+  h->prof.on = on != 0;
+  return grcuda_pfb_channelizer_ccf_set_profiling(h->pfb, on);
+}
+int grcuda_dmr_chain_profile_read(grcuda_dmr_chain* h, float* ms, int* launches) {
+  float m[EventProfiler::kStages];
+  int l[EventProfiler::kStages];
+  h->prof.read(m, l);
+  grcuda_pfb_channelizer_ccf_profile_read(h->pfb, m, l);  // fills stages 0 and 1
+  for (int i = 0; i < GRCUDA_NSTAGES; i++) { if (ms) ms[i] = m[i]; if (launches) launches[i] = l[i]; }
+  return GRCUDA_OK;
+}
+
+// Host entry point: pinned, double-buffered staging.  The block is cut into sub-blocks; while
+// sub-block i runs on the compute stream, sub-block i+1 is DMA'd (and, for pageable callers,
+// memcpy'd into pinned chunks) on the copy stream.  Hits of all sub-blocks accumulate.
 int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in, int nrows) {
-  if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
-    return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
-  const size_t bytes = (size_t)(h->T + nrows) * h->M * sizeof(float2);
+  const int minr = grcuda_dmr_chain_min_rows(h);
+  if (nrows < minr || nrows > h->max_rows)
+    return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, minr, h->max_rows);
+  const size_t M = h->M;
+  int nsub = h->keep_bytes ? 1 : std::max(1, std::min(8, nrows / std::max(minr, 256)));
+  const int sub = (nrows + nsub - 1) / nsub;
   int rc;
-  if ((rc = h->d_in_host.reserve((size_t)(h->T + h->max_rows) * h->M * sizeof(float2)))) return rc;
-  if ((rc = h->stager.h2d(h->d_in_host.p, in, bytes, h->stream))) return rc;
-  if ((rc = grcuda_dmr_chain_process_device(h, (const grcuda_complex*)h->d_in_host.p, nrows, h->stream))) return rc;
+  if (!h->copy_stream) {
+    GRB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      GRB_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      GRB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t buf_bytes = (size_t)(h->T + sub) * M * sizeof(float2);
+  for (int i = 0; i < 2; i++)
+    if ((rc = h->d_stage[i].reserve(buf_bytes))) return rc;
+  GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), h->stream));
+  h->accumulate_hits = true;
+  int done = 0, i = 0;
+  while (done < nrows) {
+    int n = std::min(sub, nrows - done);
+    if (nrows - (done + n) > 0 && nrows - (done + n) < minr) n = nrows - done;  // fold a short tail
+    const int b = i & 1;
+    if (n > sub && (rc = h->d_stage[b].reserve((size_t)(h->T + n) * M * sizeof(float2)))) { h->accumulate_hits = false; return rc; }
+    if (i >= 2) GRB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));  // buffer b free again
+    // host rows [done, done + T + n) : T history rows + n new rows of this sub-block
+    if ((rc = h->stager.h2d(h->d_stage[b].p, (const char*)in + (size_t)done * M * sizeof(float2),
+                            (size_t)(h->T + n) * M * sizeof(float2), h->copy_stream))) { h->accumulate_hits = false; return rc; }
+    GRB_CUDA(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+    GRB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
+    if ((rc = grcuda_dmr_chain_process_device(h, (const grcuda_complex*)h->d_stage[b].p, n, h->stream))) { h->accumulate_hits = false; return rc; }
+    GRB_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+    done += n;
+    i++;
+  }
+  h->accumulate_hits = false;
   GRB_CUDA(cudaStreamSynchronize(h->stream));
   return GRCUDA_OK;
 }
@@ -197,13 +298,14 @@ int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r)
 
 int grcuda_dmr_chain_read_hits(grcuda_dmr_chain* h, grcuda_hit* hits, int max_hits) {
   int n = 0;
-  GRB_CUDA(cudaMemcpyAsync(&n, h->nhits.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  GRB_CUDA(cudaStreamSynchronize(h->stream));
+  cudaStream_t s = h->last_stream ? h->last_stream : h->stream;  // ordered after the last process call
+  GRB_CUDA(cudaMemcpyAsync(&n, h->nhits.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(cudaStreamSynchronize(s));
   n = std::min(n, h->max_hits);
   const int m = std::min(n, max_hits);
   if (m > 0) {
-    GRB_CUDA(cudaMemcpyAsync(hits, h->hits.p, (size_t)m * sizeof(grcuda_hit), cudaMemcpyDeviceToHost, h->stream));
-    GRB_CUDA(cudaStreamSynchronize(h->stream));
+    GRB_CUDA(cudaMemcpyAsync(hits, h->hits.p, (size_t)m * sizeof(grcuda_hit), cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(cudaStreamSynchronize(s));
   }
   return n;
 }

@@ -76,6 +76,60 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// Per-stage device timing with CUDA events recorded on the launch stream (bench.py's roofline
+// numbers come from here: the events bracket exactly the kernels of one stage).
+struct EventProfiler {
+  static const int kStages = 8;
+  bool on = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  float ms[kStages] = {0};
+  int launches[kStages] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(int stage, cudaStream_t s) {
+    if (!on) return;
+    Span sp; sp.stage = stage; sp.a = get(); sp.b = nullptr;
+    cudaEventRecord(sp.a, s);
+    spans.push_back(sp);
+  }
+  void end(cudaStream_t s, int nlaunch = 1) {
+    if (!on || spans.empty()) return;
+    Span& sp = spans.back();
+    sp.b = get();
+    cudaEventRecord(sp.b, s);
+    launches[sp.stage] += nlaunch;
+  }
+  // synchronises the recorded events, accumulates, returns totals and resets
+  void read(float* out_ms, int* out_launches) {
+    for (Span& sp : spans) {
+      if (sp.b) {
+        cudaEventSynchronize(sp.b);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.stage] += t;
+        pool.push_back(sp.b);
+      }
+      pool.push_back(sp.a);
+    }
+    spans.clear();
+    for (int i = 0; i < kStages; i++) {
+      if (out_ms) out_ms[i] = ms[i];
+      if (out_launches) out_launches[i] = launches[i];
+      ms[i] = 0.f;
+      launches[i] = 0;
+    }
+  }
+  ~EventProfiler() {
+    for (Span& sp : spans) { cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+};
+
 // Pinned, double-buffered staging between pageable host memory and the device.  Pointers that
 // are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are
 // DMA'd directly.

@@ -450,6 +450,7 @@ struct grcuda_pfb : PlanBase {
   PinBuf pin_in;
   FftPlan* fft = nullptr;
   long chunk_rows = 0;
+  EventProfiler prof;  // stage 0 = branch FIR kernel, stage 1 = FFT kernel
 
   ~grcuda_pfb() { fft_plan_destroy(fft); }
 
@@ -506,6 +507,7 @@ struct grcuda_pfb : PlanBase {
     if (rc) return rc;
     for (long r0 = 0; r0 < nout; r0 += crow) {
       const long n = std::min(crow, nout - r0);
+      prof.begin(0, s);
       if (fast) {
         PfbFirArgs a;
         a.x = d_rows_in + r0 * (long)M; a.u = d_u.as<float2>(); a.taps_t = d_taps_t.as<float>();
@@ -529,7 +531,10 @@ struct grcuda_pfb : PlanBase {
         pfb_fir_generic_kernel<<<grid_for(n * (long)M, 256), 256, 0, s>>>(a);
       }
       GRB_LAUNCH_CHECK();
+      prof.end(s);
+      prof.begin(1, s);
       if ((rc = fft_plan_exec(fft, d_u.as<float2>(), d_out + r0 * (long)M, n, nullptr, 0, 0, s))) return rc;
+      prof.end(s);
     }
     return GRCUDA_OK;
   }
@@ -571,6 +576,15 @@ unsigned grcuda_pfb_channelizer_ccf_history(grcuda_pfb* h) { return h->history; 
 int grcuda_pfb_channelizer_ccf_output_multiple(grcuda_pfb* h) { return h->output_multiple; }
 double grcuda_pfb_channelizer_ccf_relative_rate(grcuda_pfb* h) { return h->relative_rate; }
 int grcuda_pfb_channelizer_ccf_taps_per_filter(grcuda_pfb* h) { return h->T; }
+
+int grcuda_pfb_channelizer_ccf_set_profiling(grcuda_pfb* h, int on) { h->prof.on = on != 0; return GRCUDA_OK; }
+int grcuda_pfb_channelizer_ccf_profile_read(grcuda_pfb* h, float* ms2, int* launches2) {
+  float ms[EventProfiler::kStages];
+  int ln[EventProfiler::kStages];
+  h->prof.read(ms, ln);
+  for (int i = 0; i < 2; i++) { if (ms2) ms2[i] = ms[i]; if (launches2) launches2[i] = ln[i]; }
+  return GRCUDA_OK;
+}
 
 int grcuda_pfb_channelizer_ccf_work_device(grcuda_pfb* h, long nout, const grcuda_complex* d_in_rows,
                                            grcuda_complex* d_out, void* stream) {

@@ -81,6 +81,9 @@ class DmrChain:
     def seek(self, abs_row):
         _l.check(self.L.grcuda_dmr_chain_seek(self.h, C.c_longlong(abs_row)))
 
+    def seek_async(self, abs_row, stream=None):
+        _l.check(self.L.grcuda_dmr_chain_seek_async(self.h, C.c_longlong(abs_row), C.c_void_p(stream) if stream else None))
+
     def tell(self):
         return int(self.L.grcuda_dmr_chain_tell(self.h))
 
@@ -88,16 +91,38 @@ class DmrChain:
         return int(self.L.grcuda_dmr_chain_state_bytes(self.h))
 
     def export_state(self, d_state, stream=None):
-        _l.check(self.L.grcuda_dmr_chain_export_state(self.h, C.c_void_p(d_state.data_ptr()), stream))
+        _l.check(self.L.grcuda_dmr_chain_export_state(self.h, C.c_void_p(d_state.data_ptr()),
+                                                      C.c_void_p(stream) if stream else None))
 
     def import_state(self, d_state, stream=None):
-        _l.check(self.L.grcuda_dmr_chain_import_state(self.h, C.c_void_p(d_state.data_ptr()), stream))
+        _l.check(self.L.grcuda_dmr_chain_import_state(self.h, C.c_void_p(d_state.data_ptr()),
+                                                      C.c_void_p(stream) if stream else None))
 
     def process_device(self, d_in, nrows, stream=None):
         """d_in: torch CUDA tensor (or raw pointer int) addressing history_rows() rows + nrows new rows."""
         ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
         _l.check(self.L.grcuda_dmr_chain_process_device(self.h, C.c_void_p(ptr), int(nrows),
                                                         C.c_void_p(stream) if stream else None))
+
+    def process_front_device(self, d_in, nrows, stream=None):
+        ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
+        _l.check(self.L.grcuda_dmr_chain_process_front_device(self.h, C.c_void_p(ptr), int(nrows),
+                                                              C.c_void_p(stream) if stream else None))
+
+    def process_tail_device(self, stream=None):
+        _l.check(self.L.grcuda_dmr_chain_process_tail_device(self.h, C.c_void_p(stream) if stream else None))
+
+    STAGES = ("pfb_fir", "pfb_fft", "quad_demod", "rrc_fir", "mm_slicer", "map_unpack_corr", "carry_copies")
+
+    def set_profiling(self, on):
+        _l.check(self.L.grcuda_dmr_chain_set_profiling(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """{stage: (milliseconds, launches)} accumulated since the last read (CUDA events on the launch stream)."""
+        ms = (C.c_float * 7)()
+        ln = (C.c_int * 7)()
+        _l.check(self.L.grcuda_dmr_chain_profile_read(self.h, ms, ln))
+        return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(self.STAGES)}
 
     def process_host(self, rows, nrows):
         """rows: host array/pointer with history_rows() + nrows rows of M complex64 (pinned or pageable)."""

@@ -1,0 +1,98 @@
+"""Time sharding of the wideband stream across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).  The stream is cut
+into contiguous time blocks of `rows_per_block` channel-rate rows; block b = step*world + rank goes to
+`rank`.  Two things cross rank boundaries, both as point-to-point send/recv on their own process
+group so that their message orders cannot interleave:
+
+  halo   the last `halo_rows` INPUT rows of the left neighbour's block (tap history of the
+         channelizer + enough extra rows to rebuild the discriminator / matched-filter histories and
+         the M&M look-back locally).  Finite-memory stages need nothing else.
+  state  the per-channel LOOP state {mu, omega, last_sample, next input index, slicer avg,
+         correlator registers}: the M&M / slicer / correlator recurrences have infinite memory, so
+         block b's tail stage starts from block b-1's final state.  This is a ring: rank r receives
+         from r-1 and sends to r+1; rank 0 receives what rank world-1 sent in the previous step.
+
+The front stage of every rank runs concurrently; only the (cheap, latency-bound) tail stages are
+chained.  Nothing here computes: the data path is libgr_cuda.
+"""
+import torch
+import torch.distributed as dist
+
+
+class TimeShardPlan:
+    def __init__(self, world, rank, rows_per_block, halo_rows):
+        self.world, self.rank = int(world), int(rank)
+        self.rows_per_block, self.halo_rows = int(rows_per_block), int(halo_rows)
+
+    def block_index(self, step):
+        return step * self.world + self.rank
+
+    def abs_start(self, step):
+        """Absolute channel-rate row index of the first new row of this rank's block at `step`."""
+        return self.block_index(step) * self.rows_per_block
+
+    @property
+    def left(self):
+        return (self.rank - 1) % self.world
+
+    @property
+    def right(self):
+        return (self.rank + 1) % self.world
+
+    def has_left_state(self, step):
+        """False only for the very first block of the stream (it starts from the constructor state)."""
+        return self.block_index(step) > 0
+
+
+class RingExchanger:
+    """Halo + loop-state exchange between neighbouring time shards."""
+
+    def __init__(self, plan, halo_group=None, state_group=None):
+        self.plan = plan
+        if plan.world > 1:
+            self.halo_group = halo_group if halo_group is not None else dist.new_group()
+            self.state_group = state_group if state_group is not None else dist.new_group()
+        else:
+            self.halo_group = self.state_group = None
+
+    def exchange_halo(self, my_tail_rows, halo_out, step):
+        """Sends the last halo rows of my block to the right neighbour and receives my left neighbour's
+        into `halo_out`.  Returns the list of pending works (call wait_all before the front stage)."""
+        p = self.plan
+        if p.world == 1:
+            return []
+        ops = [dist.P2POp(dist.isend, my_tail_rows, p.right, group=self.halo_group),
+               dist.P2POp(dist.irecv, halo_out, p.left, group=self.halo_group)]
+        return dist.batch_isend_irecv(ops)
+
+    def recv_state(self, state_buf, step):
+        p = self.plan
+        if p.world == 1 or not p.has_left_state(step):
+            return False
+        dist.recv(state_buf, src=p.left, group=self.state_group)
+        return True
+
+    def send_state(self, state_buf, step, last_step):
+        p = self.plan
+        if p.world == 1:
+            return
+        # the last block of the whole run has nobody waiting for its state
+        if step == last_step and p.rank == p.world - 1:
+            return
+        dist.send(state_buf, dst=p.right, group=self.state_group)
+
+    @staticmethod
+    def wait_all(works):
+        for w in works:
+            w.wait()
+
+
+def gather_counts(value, world, device):
+    """Final result gather: per-rank scalar (e.g. sync hits of the step) -> list on rank 0."""
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    if world == 1:
+        return [int(value)]
+    out = [torch.zeros_like(t) for _ in range(world)] if dist.get_rank() == 0 else None
+    dist.gather(t, out, dst=0)
+    return [int(o.item()) for o in out] if out is not None else None

@@ -258,7 +258,13 @@ int grcuda_dmr_chain_history_rows(grcuda_dmr_chain* h);
  * history_rows() rows that precede them (zeros at stream start, or the neighbour shard's halo).
  * Per-channel demod state is carried inside the handle from block to block. */
 int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream);
-/* same through host memory: pinned double-buffered staging, H2D of the block, D2H of results */
+/* the two halves of process_device, for time shards: front = channelizer + discriminator + matched
+ * filter (finite memory), tail = M&M + slicer + correlator (loop state); a shard runs front on its
+ * block, import_state()s its left neighbour's state, then runs tail. */
+int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream);
+int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream);
+/* same through host memory: pinned double-buffered staging (sub-blocks: H2D of i+1 overlaps compute
+ * of i); sync hits of all sub-blocks accumulate for read_hits */
 int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in, int nrows);
 /* results of the last processed block (device pointers valid until the next process call) */
 typedef struct {
@@ -283,6 +289,7 @@ int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h);
  * loop state its left neighbour exported and continues bit-identically to a single-GPU run. */
 int grcuda_dmr_chain_warmup_rows(grcuda_dmr_chain* h);
 int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row);
+int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* stream); /* stream ordered, no sync */
 long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h);
 /* shard hand-off: export / import the per-channel loop state
  * {mu, omega, last_sample, next input index, slicer avg, correlator registers} so that the next
@@ -290,6 +297,22 @@ long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h);
 size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h);
 int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream);
 int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void* stream);
+
+/* ---- per-stage device timing (bench.py) -------------------------------------------------------
+ * CUDA events recorded on the launch stream around each stage's kernels.  profile_read
+ * synchronises, returns the accumulated milliseconds / launch counts since the last read. */
+#define GRCUDA_STAGE_PFB_FIR 0
+#define GRCUDA_STAGE_PFB_FFT 1
+#define GRCUDA_STAGE_QUAD 2
+#define GRCUDA_STAGE_RRC 3
+#define GRCUDA_STAGE_MM 4
+#define GRCUDA_STAGE_CORR 5
+#define GRCUDA_STAGE_CARRY 6
+#define GRCUDA_NSTAGES 7
+int grcuda_pfb_channelizer_ccf_set_profiling(grcuda_pfb* h, int on);
+int grcuda_pfb_channelizer_ccf_profile_read(grcuda_pfb* h, float ms[2], int launches[2]);
+int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on);
+int grcuda_dmr_chain_profile_read(grcuda_dmr_chain* h, float ms[GRCUDA_NSTAGES], int launches[GRCUDA_NSTAGES]);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
