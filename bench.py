@@ -180,15 +180,15 @@ def run_ours(args):
 
     def step(s, last):
         if world == 1:
-            ch.process_device(x, R)
+            ch.process_device(x, R, stream)     # on torch's current stream: the timing events live there
             return
         works = ring.exchange_halo(tail_rows, halo_in, s)          # NCCL send/recv of the input halo
         ring.wait_all(works)
         ch.seek_async(plan.abs_start(s) - halo, stream)
-        ch.process_front_device(x, halo + R)                        # all ranks concurrently
+        ch.process_front_device(x, halo + R, stream)                # all ranks concurrently
         if ring.recv_state(state, s):                               # loop state of block b-1 (ring)
             ch.import_state(state, stream)
-        ch.process_tail_device()
+        ch.process_tail_device(stream)
         ch.export_state(state, stream)
         ring.send_state(state, s, last)
 

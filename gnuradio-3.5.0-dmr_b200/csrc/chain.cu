@@ -5,8 +5,11 @@
 // state carried from block to block.
 //
 // Data layout in HBM (row = one channel-rate time step, M channels wide):
-//   Y  [1 + R][M] complex   channelizer output; row 0 = last row of the previous block (quad history)
-//   D  [nrrc-1 + R][M] f32  discriminator output; first nrrc-1 rows = carried history of the RRC FIR
+//   Y  [YH + R][M] complex  channelizer output; first YH rows = carried tail of the previous block
+//                           (fused front: YH = nrrc + 4 rows of discriminator + matched-filter history;
+//                           unfused: YH = 1, the discriminator's x[i-1])
+//   D  [nrrc-1 + R][M] f32  discriminator output (UNFUSED path only: generic summation order or very
+//                           long matched filters); first nrrc-1 rows = carried history of the RRC FIR
 //   F  [KEEP + R][M] f32    matched-filter output; first KEEP rows = carry for the M&M interpolator
 //   soft/sym [max_sym][M], bytes [2*max_sym][M], hits[], per-channel state arrays
 #include <algorithm>
@@ -24,6 +27,8 @@ const int KEEP = 64;  // rows of F kept in front of each block (M&M look-back, s
 struct grcuda_dmr_chain {
   unsigned M = 0;
   int T = 0, nrrc = 0, max_rows = 0, max_sym = 0, max_hits = 0, keep_bytes = 0;
+  int YH = 1;          // history rows in front of Y
+  bool fused = false;  // discriminator + matched filter in one kernel (kernel_demod_front.cuh)
   grcuda_pfb* pfb = nullptr;
   grcuda_quad* quad = nullptr;
   grcuda_fir_fff* rrc = nullptr;
@@ -78,12 +83,15 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   grcuda_clock_recovery_mm_ff_set_slicer(h->mm, 4, p->slicer_alpha);
   h->symbol_map.assign(p->symbol_map, p->symbol_map + p->symbol_map_len);
   h->T = grcuda_pfb_channelizer_ccf_taps_per_filter(h->pfb);
+  // The fused discriminator + matched-filter kernel restates the SSE summation order only
+  h->fused = p->order == GRCUDA_ORDER_SSE && h->nrrc <= demod_front_max_taps() && !getenv("GRCUDA_CHAIN_UNFUSED");
+  h->YH = h->fused ? demod_front_history(h->nrrc) : 1;
   const size_t M = h->M, R = h->max_rows;
   h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)p->omega * 1.25) + 64;
   h->max_hits = std::max<int>(4096, (int)(M * (size_t)h->max_sym / 32));
   int rc = 0;
-  rc = rc ? rc : h->Y.reserve((1 + R) * M * sizeof(float2));
-  rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
+  rc = rc ? rc : h->Y.reserve((h->YH + R) * M * sizeof(float2));
+  if (!h->fused) rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
   rc = rc ? rc : h->F.reserve((KEEP + R) * M * sizeof(float));
   rc = rc ? rc : h->soft.reserve((size_t)h->max_sym * M * sizeof(float));
   rc = rc ? rc : h->sym.reserve((size_t)h->max_sym * M);
@@ -93,8 +101,8 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   if (!rc && h->keep_bytes) rc = h->bytes.reserve((size_t)2 * h->max_sym * M);
   if (rc) { delete h; return nullptr; }
   // stream start: all histories are the zeros the reference runtime pre-loads (gr_buffer.cc:201-214)
-  if (cudaMemset(h->Y.p, 0, M * sizeof(float2)) != cudaSuccess ||
-      cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4) != cudaSuccess ||
+  if (cudaMemset(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2)) != cudaSuccess ||
+      (!h->fused && cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4) != cudaSuccess) ||
       cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
       cudaMemset(h->nhits.p, 0, sizeof(int)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -108,18 +116,18 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
 void grcuda_dmr_chain_destroy(grcuda_dmr_chain* h) { delete h; }
 int grcuda_dmr_chain_history_rows(grcuda_dmr_chain* h) { return h->T; }
 
-int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h) { return std::max(KEEP, h->nrrc - 1); }
+int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h) { return std::max(std::max(KEEP, h->nrrc - 1), h->YH); }
 int grcuda_dmr_chain_warmup_rows(grcuda_dmr_chain* h) {
   // rows a fresh chain must process before its F rows are those of the continuous stream:
-  // PFB transient (T) + quad history (1) + RRC history (nrrc-1) + M&M look-back (KEEP) + look-ahead (8)
-  const int w = h->T + h->nrrc + KEEP + 8;
+  // PFB transient (T) + discriminator / RRC history (YH + nrrc) + M&M look-back (KEEP) + look-ahead (8)
+  const int w = h->T + h->YH + h->nrrc + KEEP + 8;
   return std::max(w, grcuda_dmr_chain_min_rows(h));
 }
 int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
   const size_t M = h->M;
   GRB_CUDA(cudaDeviceSynchronize());
-  GRB_CUDA(cudaMemset(h->Y.p, 0, M * sizeof(float2)));
-  GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
+  GRB_CUDA(cudaMemset(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2)));
+  if (!h->fused) GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
   GRB_CUDA(cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)));
   h->abs_row = abs_row;
   return GRCUDA_OK;
@@ -128,8 +136,8 @@ int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
 int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
   const size_t M = h->M;
-  GRB_CUDA(cudaMemsetAsync(h->Y.p, 0, M * sizeof(float2), s));
-  GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
+  GRB_CUDA(cudaMemsetAsync(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2), s));
+  if (!h->fused) GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
   GRB_CUDA(cudaMemsetAsync(h->F.p, 0, (size_t)KEEP * M * sizeof(float), s));
   h->abs_row = abs_row;
   return GRCUDA_OK;
@@ -165,8 +173,21 @@ int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_comp
   float2* Y = h->Y.as<float2>();
   float* D = h->D.as<float>();
   float* F = h->F.as<float>();
-  // 1. channelizer: [T + R][M] -> Y rows 1..R
-  if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + M), s))) return rc;
+  const size_t YH = h->YH;
+  // 1. channelizer: [T + R][M] -> Y rows YH..YH+R
+  if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + YH * M), s))) return rc;
+  if (h->fused) {
+    // 2+3. discriminator + matched filter in one pass: Y (8 B/sample) -> F (4 B/sample); the
+    //      discriminator output only ever lives in shared memory
+    int nt = 0;
+    const float* rt = fir_fff_reversed_taps(h->rrc, &nt, nullptr);
+    h->prof.begin(3, s);
+    if ((rc = demod_front_launch(Y, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad), rt, nt, s)))
+      return rc;
+    h->prof.end(s);
+    h->front_rows = nrows;
+    return GRCUDA_OK;
+  }
   // 2. discriminator: Y rows 0..R -> D rows (nrrc-1)..
   h->prof.begin(2, s);
   if ((rc = grcuda_quadrature_demod_cf_work_device(h->quad, R, (int)M, (const grcuda_complex*)Y, D + (size_t)(h->nrrc - 1) * M, s))) return rc;
@@ -191,26 +212,21 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
   float2* Y = h->Y.as<float2>();
   float* D = h->D.as<float>();
   float* F = h->F.as<float>();
-  // 4. clock recovery + slicer over F rows [abs_row-KEEP, abs_row+R)
-  h->prof.begin(4, s);
-  if ((rc = grcuda_clock_recovery_mm_ff_work_device(h->mm, KEEP + R, (long)(h->abs_row - KEEP), F, h->soft.as<float>(),
-                                                    h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), s)))
-    return rc;
-  h->prof.end(s);
-  // 5. dibits -> bits -> sync correlation
+  // 4+5. clock recovery + slicer + (dibit map -> bits -> sync correlation fused in the same kernel)
+  //      over F rows [abs_row-KEEP, abs_row+R)
   if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
-  h->prof.begin(5, s);
-  if ((rc = grcuda_correlate_access_code_bb_work_symbols_device(
-           h->corr, h->sym.as<unsigned char>(), h->max_sym, h->counts.as<int>(), h->symbol_map.data(),
-           (int)h->symbol_map.size(), 2, h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr, 2 * h->max_sym,
-           (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
+  h->prof.begin(4, s);
+  if ((rc = mm_corr_launch(h->mm, h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, F, KEEP + R,
+                           (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(), h->max_sym,
+                           h->counts.as<int>(), h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr,
+                           (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
     return rc;
   h->prof.end(s);
   // 6. carries for the next block (small device-to-device copies, stream ordered;
   //    nrows >= min_rows guarantees that source and destination never overlap)
   h->prof.begin(6, s);
-  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-  if (h->nrrc > 1)
+  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, (size_t)h->YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  if (!h->fused && h->nrrc > 1)
     GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync(F, F + (size_t)R * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
   h->prof.end(s, 0);
@@ -284,7 +300,7 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
 }
 
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r) {
-  r->d_channels = (const grcuda_complex*)(h->Y.as<float2>() + h->M);
+  r->d_channels = (const grcuda_complex*)(h->Y.as<float2>() + (size_t)h->YH * h->M);
   r->d_soft = h->soft.as<float>();
   r->d_symbols = h->sym.as<unsigned char>();
   r->d_sym_counts = h->counts.as<int>();

@@ -350,12 +350,13 @@ __global__ void fir_fff_stream_kernel(const float* __restrict__ in, float* __res
 struct grcuda_fir_fff : PlanBase {
   int decim = 1, ntaps = 0, order = GRCUDA_ORDER_SSE;
   DevBuf d_rt;
-  std::vector<float> new_taps;
+  std::vector<float> new_taps, rt_host;
   bool updated = false;
   unsigned history = 1;
   int set_now(const std::vector<float>& taps) {
     cudaDeviceSynchronize();
     std::vector<float> rt(taps.rbegin(), taps.rend());
+    rt_host = rt;
     ntaps = (int)rt.size();
     history = (unsigned)ntaps;
     if ((size_t)ntaps * sizeof(float) > 96 * 1024)
@@ -497,7 +498,7 @@ struct grcuda_pfb : PlanBase {
     // to stay resident in the 126 MB L2 between the FIR kernel and the FFT kernel.
     long crow = chunk_rows;
     if (crow <= 0) {
-      size_t mb = 24;
+      size_t mb = 1u << 20;  // default: no chunking (measured faster than L2-resident chunks, profiles/r1_pfb_chunking.txt)
       if (const char* e = getenv("GRCUDA_PFB_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e));
       crow = std::max<long>(1, (long)(mb << 20) / (long)(M * sizeof(float2)));
     }
@@ -791,8 +792,10 @@ struct grcuda_mm : PlanBase {
     return GRCUDA_OK;
   }
   int launch(const float* d_in, long ninput, long abs_row0, float* d_out, unsigned char* d_sl, int max_out, int* d_cnt,
-             cudaStream_t s) {
+             cudaStream_t s, const MMCorrFuse* fuse = nullptr) {
     MMArgs a;
+    memset(&a.corr, 0, sizeof a.corr);
+    if (fuse) a.corr = *fuse;
     a.in = d_in; a.ninput = ninput; a.abs_row0 = abs_row0; a.nchan = nchan; a.out = d_out; a.sliced = d_sl;
     a.max_out = max_out; a.counts = d_cnt; a.state = d_state.as<MMChanState>();
     {
@@ -801,8 +804,24 @@ struct grcuda_mm : PlanBase {
       a.slicer_levels = slicer_levels; a.slicer_alpha = slicer_alpha; a.slicer_beta = slicer_beta;
     }
     a.order = order; a.mmse_eff = tabs.mmse_eff;
+    // prefetch ~12 symbols ahead of the interpolator window, enough rows to cover one symbol advance
+    a.pf_n = std::min(16, (int)std::ceil(max_omega) + 1);
+    a.pf_dist = 8 + (int)(12.0f * omega0);
+    if (const char* e = getenv("GRCUDA_MM_PREFETCH_SYMBOLS")) a.pf_dist = 8 + (int)(atof(e) * omega0);
+    if (a.pf_dist <= 8) a.pf_n = 0;
     const int threads = 64;
-    mm_kernel<<<(nchan + threads - 1) / threads, threads, 0, s>>>(a);
+    // ring depth: ~50 rows of look-ahead is >= 10 symbols up to 5 samples/symbol; slower symbol rates
+    // (e.g. the 10 samples/symbol single-channel config) get the deep ring
+    if (max_omega <= 5.0f) {
+      mm_kernel<64><<<(nchan + threads - 1) / threads, threads, 64 * threads * sizeof(float), s>>>(a);
+    } else {
+      static bool attr_done = false;
+      if (!attr_done) {
+        GRB_CUDA(cudaFuncSetAttribute((const void*)mm_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 64 * 4));
+        attr_done = true;
+      }
+      mm_kernel<512><<<(nchan + threads - 1) / threads, threads, 512 * threads * sizeof(float), s>>>(a);
+    }
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
   }
@@ -1016,6 +1035,31 @@ int grcuda_correlate_access_code_bb_work_symbols_device(grcuda_corr* h, const un
 // ---- internal accessors (chain.cu) -------------------------------------------------------------
 #include "internal.h"
 namespace grb {
+// M&M + slicer with the map/unpack/correlator fused into the same kernel (chain.cu's tail stage)
+int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const float* d_in,
+                   long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out, int* d_counts,
+                   unsigned char* d_bytes, grcuda_hit* d_hits, int max_hits, int* d_nhits, cudaStream_t s) {
+  if (mm->nchan != corr->nchan) return set_error(GRCUDA_EINVAL, "mm/corr channel counts differ");
+  MMCorrFuse f;
+  memset(&f, 0, sizeof f);
+  f.on = 1;
+  f.bits_per_symbol = bits_per_symbol;
+  for (int i = 0; i < 256; i++) f.map[i] = (unsigned char)i;
+  for (int i = 0; i < std::min(nmap, 256); i++) f.map[i] = (unsigned char)map[i];
+  f.out = d_bytes;
+  f.state = corr->d_state.as<CorrChanState>();
+  { std::lock_guard<std::mutex> lk(corr->mu); f.p = corr->p; }
+  f.hits = (CorrHit*)d_hits;
+  f.max_hits = max_hits;
+  f.nhits = d_nhits;
+  return mm->launch(d_in, ninput, abs_row0, d_soft, d_sym, max_out, d_counts, s, &f);
+}
+const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
+  if (ntaps) *ntaps = h->ntaps;
+  if (order) *order = h->order;
+  return h->rt_host.data();
+}
+float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }
 void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }
 size_t mm_state_bytes(grcuda_mm* h) { return (size_t)h->nchan * sizeof(MMChanState); }
 void* corr_state_ptr(grcuda_corr* h) { return h->d_state.p; }

@@ -133,35 +133,17 @@ GR_HD int mod4(long a) { return (int)(a & 3); }  // two's complement: correct fo
 
 // ---- 8-tap MMSE interpolator (gri_mmse_fir_interpolator.cc:61-71) ---------------------------
 // c[0..7] = coefficients applied to v[0..7] (= reference taps[imu][7-i]); v[i] = in[ii+i].
-GR_HD float mmse8(const float c[8], const float v[8], int order, int al) {
-  float p[8];
+// generic (gr_fir_XXX_generic.cc.t:28-55): a_l = p[l] + p[l+4], result ((a0+a1)+a2)+a3.
+// SSE (float_dotprod_sse64.S): lane (i+al)&3 sums p[i] then p[i+4] (always < 4 blocks, so one
+// accumulator), result (d0+d2)+(d1+d3) over LANES.  With q_i = p[i]+p[i+4] the lane of q_i is
+// (i+al)&3, so the result is (q0+q2)+(q1+q3) for al = 0, 2 and (q3+q1)+(q0+q2) for al = 1, 3:
+// the same value for every alignment because IEEE addition commutes.  Hence no `al` here.
+GR_HD float mmse8(const float c[8], const float v[8], int order) {
+  float q[4];
 #pragma unroll
-  for (int i = 0; i < 8; i++) p[i] = GR_FMUL(c[i], v[i]);
-  if (order == GR_ORDER_GENERIC) {
-    const float a0 = GR_FADD(p[0], p[4]), a1 = GR_FADD(p[1], p[5]);
-    const float a2 = GR_FADD(p[2], p[6]), a3 = GR_FADD(p[3], p[7]);
-    return GR_FADD(GR_FADD(GR_FADD(a0, a1), a2), a3);
-  }
-  // SSE order.  Element i sits in lane (i+al)&3 of block (i+al)>>2; nblocks = 2 (al=0) or 3,
-  // always < 4, so every block accumulates into xmm4 in order and the result is (d0+d2)+(d1+d3).
-  float d[4];
-  if (al == 0) {
-#pragma unroll
-    for (int l = 0; l < 4; l++) d[l] = GR_FADD(p[l], p[l + 4]);
-  } else {
-    // lanes: block0 has lanes al..3 (elements 0..3-al), block1 elements 4-al..7-al, block2 the rest
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-      const int i0 = l - al, i1 = l + 4 - al, i2 = l + 8 - al;
-      float s = 0.f;
-      bool first = true;
-      if (i0 >= 0) { s = p[i0]; first = false; }
-      if (i1 >= 0 && i1 < 8) { s = first ? p[i1] : GR_FADD(s, p[i1]); first = false; }
-      if (i2 < 8) { s = first ? p[i2] : GR_FADD(s, p[i2]); }
-      d[l] = s;
-    }
-  }
-  return GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3]));
+  for (int i = 0; i < 4; i++) q[i] = GR_FADD(GR_FMUL(c[i], v[i]), GR_FMUL(c[i + 4], v[i + 4]));
+  if (order == GR_ORDER_GENERIC) return GR_FADD(GR_FADD(GR_FADD(q[0], q[1]), q[2]), q[3]);
+  return GR_FADD(GR_FADD(q[0], q[2]), GR_FADD(q[1], q[3]));
 }
 
 // ---- Mueller & Mueller loop state (digital_clock_recovery_mm_ff.cc:102-139) ------------------

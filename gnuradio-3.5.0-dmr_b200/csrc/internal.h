@@ -1,6 +1,7 @@
 // Non-ABI accessors between the translation units of libgr_cuda (hidden visibility).
 #pragma once
 #include <cstddef>
+#include <cuda_runtime.h>
 #include "../../include/gr_cuda.h"
 
 namespace grb {
@@ -8,4 +9,15 @@ void* mm_state_ptr(grcuda_mm* h);
 size_t mm_state_bytes(grcuda_mm* h);
 void* corr_state_ptr(grcuda_corr* h);
 size_t corr_state_bytes(grcuda_corr* h);
+int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const float* d_in,
+                   long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out, int* d_counts,
+                   unsigned char* d_bytes, grcuda_hit* d_hits, int max_hits, int* d_nhits, cudaStream_t s);
+// fused quadrature_demod_cf + fir_filter_fff (SSE order) on [time][channel] data (demod_front.cu)
+int demod_front_max_taps();
+int demod_front_history(int ntaps);
+int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* rt, int ntaps,
+                       cudaStream_t s);
+// reversed taps / order / gain of the stand-alone plans (host copies)
+const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order);
+float quad_gain(grcuda_quad* h);
 }  // namespace grb

@@ -37,7 +37,8 @@ def _dp(t):
 
 def _torch_stream():
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    s = torch.cuda.current_stream().cuda_stream
+    return C.c_void_p(s if s else 1)   # torch's default stream (0) is cudaStreamLegacy (0x1); NULL = plan's own stream
 
 
 class _Block:
@@ -262,6 +263,18 @@ class quadrature_demod_cf(_Block):
     def work_device(self, nrows, nchan, d_in, d_out):
         _l.check(self.L.grcuda_quadrature_demod_cf_work_device(self.h, C.c_long(nrows), int(nchan), _dp(d_in), _dp(d_out),
                                                                _torch_stream()))
+
+
+def quad_demod_fir_fff_history(fir):
+    """Rows of channelizer output the fused discriminator + matched filter wants in front of a block."""
+    return int(_l.load().grcuda_quad_demod_fir_fff_history(fir.h))
+
+
+def quad_demod_fir_fff_work_device(quad, fir, nrows, nchan, d_in, d_out, abs_row0):
+    """quadrature_demod_cf -> fir_filter_fff fused into one kernel on [time][channel] data (SSE order):
+    d_in = [history + nrows][nchan] complex64 CUDA tensor, d_out = [nrows][nchan] float32."""
+    _l.check(_l.load().grcuda_quad_demod_fir_fff_work_device(quad.h, fir.h, C.c_long(nrows), int(nchan), _dp(d_in),
+                                                            _dp(d_out), C.c_long(abs_row0), _torch_stream()))
 
 
 class clock_recovery_mm_ff(_Block):

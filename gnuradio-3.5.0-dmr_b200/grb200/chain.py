@@ -8,6 +8,13 @@ from . import lib as _l
 from . import synth
 
 
+def _sp(stream):
+    """None -> the plan's own stream; 0 (torch's default stream) -> cudaStreamLegacy; else the handle."""
+    if stream is None:
+        return None
+    return C.c_void_p(stream if stream else 1)
+
+
 class DmrChainConfig:
     """Parameters of the reference flowgraph this object stands for."""
 
@@ -82,7 +89,7 @@ class DmrChain:
         _l.check(self.L.grcuda_dmr_chain_seek(self.h, C.c_longlong(abs_row)))
 
     def seek_async(self, abs_row, stream=None):
-        _l.check(self.L.grcuda_dmr_chain_seek_async(self.h, C.c_longlong(abs_row), C.c_void_p(stream) if stream else None))
+        _l.check(self.L.grcuda_dmr_chain_seek_async(self.h, C.c_longlong(abs_row), _sp(stream)))
 
     def tell(self):
         return int(self.L.grcuda_dmr_chain_tell(self.h))
@@ -92,25 +99,25 @@ class DmrChain:
 
     def export_state(self, d_state, stream=None):
         _l.check(self.L.grcuda_dmr_chain_export_state(self.h, C.c_void_p(d_state.data_ptr()),
-                                                      C.c_void_p(stream) if stream else None))
+                                                      _sp(stream)))
 
     def import_state(self, d_state, stream=None):
         _l.check(self.L.grcuda_dmr_chain_import_state(self.h, C.c_void_p(d_state.data_ptr()),
-                                                      C.c_void_p(stream) if stream else None))
+                                                      _sp(stream)))
 
     def process_device(self, d_in, nrows, stream=None):
         """d_in: torch CUDA tensor (or raw pointer int) addressing history_rows() rows + nrows new rows."""
         ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
         _l.check(self.L.grcuda_dmr_chain_process_device(self.h, C.c_void_p(ptr), int(nrows),
-                                                        C.c_void_p(stream) if stream else None))
+                                                        _sp(stream)))
 
     def process_front_device(self, d_in, nrows, stream=None):
         ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
         _l.check(self.L.grcuda_dmr_chain_process_front_device(self.h, C.c_void_p(ptr), int(nrows),
-                                                              C.c_void_p(stream) if stream else None))
+                                                              _sp(stream)))
 
     def process_tail_device(self, stream=None):
-        _l.check(self.L.grcuda_dmr_chain_process_tail_device(self.h, C.c_void_p(stream) if stream else None))
+        _l.check(self.L.grcuda_dmr_chain_process_tail_device(self.h, _sp(stream)))
 
     STAGES = ("pfb_fir", "pfb_fft", "quad_demod", "rrc_fir", "mm_slicer", "map_unpack_corr", "carry_copies")
 

@@ -164,6 +164,17 @@ int grcuda_quadrature_demod_cf_work_device(grcuda_quad* h, long noutput_items, i
                                            float* d_out, void* stream);
 int grcuda_fast_atan2f_device(const float* d_y, const float* d_x, float* d_out, long n, void* stream);
 
+/* ---- a7+a8+a2 fused: gr_quadrature_demod_cf -> gr_fir_filter_fff, batched [time][channel] ------
+ * One pass over the channelizer output (gr_quadrature_demod_cf.cc:46-62 feeding
+ * gr_fir_filter_XXX.cc.t:66-88 / float_dotprod_sse64.S): 8 B read + 4 B written per channel sample,
+ * the discriminator output stays in shared memory.  Bit identical to running the two blocks one
+ * after the other in the SSE summation order (GRCUDA_EUNSUPPORTED for GRCUDA_ORDER_GENERIC or more
+ * than 129 taps).  d_in addresses the first of history() rows that precede the nrows new rows
+ * (zeros at stream start); abs_row0 = absolute stream index of the first NEW row. */
+int grcuda_quad_demod_fir_fff_history(grcuda_fir_fff* f);
+int grcuda_quad_demod_fir_fff_work_device(grcuda_quad* q, grcuda_fir_fff* f, long nrows, int nchan,
+                                          const grcuda_complex* d_in, float* d_out, long abs_row0, void* stream);
+
 /* ---- a9/a10/a11  digital_clock_recovery_mm_ff (+ gri_mmse_fir_interpolator, slicers) --------
  * replaces digital_clock_recovery_mm_ff::general_work (digital_clock_recovery_mm_ff.cc:102-139)
  * and gri_mmse_fir_interpolator::interpolate (gri_mmse_fir_interpolator.cc:61-71), batched over

@@ -102,7 +102,7 @@ int emul_mm(float omega, float gain_omega, float mu, float gain_mu, float lim, c
   while (oo < noutput && ii < ni) {
     float v[8];
     for (int i = 0; i < 8; i++) v[i] = in[ii + i];
-    const float o = mmse8(g_mmse_eff + 8 * mm_imu(s.mu), v, order, mod4(abs0 + ii));
+    const float o = mmse8(g_mmse_eff + 8 * mm_imu(s.mu), v, order);
     out[oo++] = o;
     ii += mm_update(s, p, o);
   }

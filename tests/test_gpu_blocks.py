@@ -139,6 +139,51 @@ def test_fir_fff_batched_device_layout(B, orc):
             assert np.array_equal(got[:, c], orc.fir_fff(taps, 1, x[:, c], order=order)), c
 
 
+@pytest.mark.parametrize("ntaps", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 29, 30, 31, 32, 61, 111, 129])
+def test_quad_demod_fir_fff_fused_bit_exact(B, orc, ntaps):
+    """The fused discriminator + matched-filter kernel == quadrature_demod_cf followed by fir_filter_fff (SSE
+    order), bit for bit, for every (ntaps-1) mod 4 / ((ntaps-1)/4) mod 4 instantiation, ragged channel counts,
+    row counts that are not multiples of the tile, and a stream cut into blocks at odd absolute rows."""
+    import torch
+    rng = np.random.default_rng(100 + ntaps)
+    nchan, n = 45, 700 + ntaps
+    taps = rng.standard_normal(ntaps).astype(np.float32)
+    y = (rng.standard_normal((n, nchan)) + 1j * rng.standard_normal((n, nchan))).astype(np.complex64)
+    y[5:9, 3] = 0                       # atan2(0, 0) corner
+    gain = 3.0699801
+    quad, fir = B.quadrature_demod_cf(gain), B.fir_filter_fff(1, taps, B.ORDER_SSE)
+    H = B.quad_demod_fir_fff_history(fir)
+    assert H >= ntaps
+    want = np.stack([orc.fir_fff(taps, 1, orc.quadrature_demod_cf(gain, y[:, c]), order=orc.ORDER_SSE)
+                     for c in range(nchan)], axis=1)
+    ybuf = np.concatenate([np.zeros((H, nchan), np.complex64), y])
+    got = np.empty((n, nchan), np.float32)
+    r0 = 0
+    for blk in (1, 130, 3, 257, n):     # blocks starting at absolute rows 0, 1, 131, 134, 391
+        r1 = min(n, r0 + blk)
+        d_in = torch.from_numpy(np.ascontiguousarray(ybuf[r0:r1 + H])).cuda()
+        d_out = torch.full((r1 - r0, nchan), np.nan, dtype=torch.float32, device="cuda")
+        B.quad_demod_fir_fff_work_device(quad, fir, r1 - r0, nchan, d_in, d_out, r0)
+        torch.cuda.synchronize()
+        got[r0:r1] = d_out.cpu().numpy()
+        r0 = r1
+        if r0 >= n:
+            break
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_quad_demod_fir_fff_fused_contract(B):
+    fir = B.fir_filter_fff(1, np.ones(130, np.float32), B.ORDER_SSE)
+    import torch
+    d = torch.zeros((400, 4), dtype=torch.complex64, device="cuda")
+    o = torch.zeros((100, 4), dtype=torch.float32, device="cuda")
+    with pytest.raises(NotImplementedError):
+        B.quad_demod_fir_fff_work_device(B.quadrature_demod_cf(1.0), fir, 100, 4, d, o, 0)
+    with pytest.raises(NotImplementedError):
+        B.quad_demod_fir_fff_work_device(B.quadrature_demod_cf(1.0), B.fir_filter_fff(1, np.ones(5, np.float32), B.ORDER_GENERIC),
+                                         100, 4, d, o, 0)
+
+
 # ---- a3 freq_xlating_fir_filter_ccf -------------------------------------------------------------------
 def test_freq_xlating_fixture(B, golden, orc):
     fx = golden[1]
