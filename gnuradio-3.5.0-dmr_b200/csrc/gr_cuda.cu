@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "fft_plan.h"
 #include "kernels_demod.cuh"
+#include "kernel_mm.cuh"
 #include "kernels_fir.cuh"
 
 using namespace grb;
@@ -804,23 +805,17 @@ struct grcuda_mm : PlanBase {
       a.slicer_levels = slicer_levels; a.slicer_alpha = slicer_alpha; a.slicer_beta = slicer_beta;
     }
     a.order = order; a.mmse_eff = tabs.mmse_eff;
-    // prefetch ~12 symbols ahead of the interpolator window, enough rows to cover one symbol advance
-    a.pf_n = std::min(16, (int)std::ceil(max_omega) + 1);
-    a.pf_dist = 8 + (int)(12.0f * omega0);
-    if (const char* e = getenv("GRCUDA_MM_PREFETCH_SYMBOLS")) a.pf_dist = 8 + (int)(atof(e) * omega0);
-    if (a.pf_dist <= 8) a.pf_n = 0;
-    const int threads = 64;
-    // ring depth: ~50 rows of look-ahead is >= 10 symbols up to 5 samples/symbol; slower symbol rates
-    // (e.g. the 10 samples/symbol single-channel config) get the deep ring
+    a.debug = 0;
+    if (const char* e = getenv("GRCUDA_MM_DEBUG")) a.debug = atoi(e);
+    // look-ahead ring depth in rows: ~120 rows is >= 24 symbols up to 5 samples/symbol (several HBM round
+    // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
+    const int grid = (nchan + MMW_CH - 1) / MMW_CH;
     if (max_omega <= 5.0f) {
-      mm_kernel<64><<<(nchan + threads - 1) / threads, threads, 64 * threads * sizeof(float), s>>>(a);
+      mm_ws_kernel<128><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);
     } else {
-      static bool attr_done = false;
-      if (!attr_done) {
-        GRB_CUDA(cudaFuncSetAttribute((const void*)mm_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 64 * 4));
-        attr_done = true;
-      }
-      mm_kernel<512><<<(nchan + threads - 1) / threads, threads, 512 * threads * sizeof(float), s>>>(a);
+      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)mm_ws_smem_bytes(512)));
+      mm_ws_kernel<512><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
     }
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(128) fir_fff_kernel(const float* __restrict__ 
 // ---- digital_clock_recovery_mm_ff::general_work, batched (digital_clock_recovery_mm_ff.cc:102-139)
 // One thread per channel: the loop is sequential in time (mu/omega/last_sample feed back), but
 // the channels are independent and, in [time][channel] layout, the lanes of a warp walk the
-// same rows at (nearly) the same pace, so their loads share 128 B lines.
+// same rows at (nearly) the same pace, so their loads share 128 B lines.  The kernel itself is in
+// kernel_mm.cuh (warp specialised: loader / recursion / slicer+correlator).
 struct MMChanState {  // persists across work calls (the block's members d_mu, d_omega, ...)
   float mu, omega, last_sample, slicer_avg;
   long long next_abs;  // absolute input index of the next in[ii] for this channel
@@ -90,7 +91,7 @@ struct MMCorrFuse {
 
 struct MMArgs {
   MMCorrFuse corr;
-  int pf_dist, pf_n;     // L1 prefetch: rows [ii+pf_dist, ii+pf_dist+pf_n) are requested every iteration
+  int debug;             // experiments only (GRCUDA_MM_DEBUG): 1 = post warp discards, 2 = core skips the queue
   const float* in;       // [ninput][nchan], row 0 has absolute index abs_row0
   long ninput;
   long abs_row0;
@@ -106,125 +107,6 @@ struct MMArgs {
   float slicer_alpha, slicer_beta;
   const float* mmse_eff; // [129][8] coefficients applied to in[ii+0..7]
 };
-
-#define MM_PEND 8   // cp.async groups allowed in flight while the interpolator reads the ring
-#define MM_BACK 8   // rows kept behind ii for (rare) backward steps of the loop
-// Latency is everything here: 8000 channels are only 250 warps, one per scheduler, so the loop
-// runs at single-warp instruction latency.  The body is kept to 32-bit index arithmetic,
-// incrementally updated pointers and two LDS.128 for the taps.
-template <int MM_RING>
-__global__ void __launch_bounds__(64) mm_kernel(const MMArgs a) {
-  extern __shared__ float mm_ring[];  // [MM_RING][blockDim.x]
-  __shared__ __align__(16) float tab[129 * 8];
-  __shared__ unsigned char smap[256];
-  for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) tab[i] = a.mmse_eff[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) smap[i] = a.corr.map[i];
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.nchan) return;
-  MMChanState st = a.state[c];
-  MMState s;
-  s.mu = st.mu; s.omega = st.omega; s.last_sample = st.last_sample;
-  float avg = st.slicer_avg;
-  const int ninput = (int)a.ninput;
-  int ii = (int)(st.next_abs - a.abs_row0);  // may be > 0: samples already consumed
-  const int ni = ninput - 8;                  // :112
-  int oo = 0;
-  const size_t nchan = (size_t)a.nchan;
-  const float* __restrict__ col = a.in + c;
-  CorrChanState cs;
-  cs.data_reg = 0; cs.flag_reg = 0; cs.nbits = 0;
-  const bool corr_on = a.corr.on != 0;
-  if (corr_on) cs = a.corr.state[c];
-  int ob = 0;
-  // floor(mu) can be negative when gain_mu*mm_val < -omega (unnormalised input): the reference then
-  // re-reads older items of its circular buffer.  We keep a carry of older rows in front of each
-  // block for that; stepping even further back is clamped (and counted) instead of reading out
-  // of bounds, which is where the reference's behaviour is undefined anyway.
-  if (ii < 0) { ii = 0; st.clamped++; }
-  // The next iteration's addresses depend on this iteration's result (ii += floor(mu)), so a plain
-  // load would expose one full HBM round trip per symbol.  Instead every thread owns a ring of
-  // MM_RING rows of its column in shared memory (ring[row % MM_RING][thread]: conflict free) that
-  // is kept filled ahead of ii with cp.async (LDGSTS: no register staging, no stall until the
-  // data is consumed ~10 symbols later).
-  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(mm_ring + threadIdx.x);
-  const unsigned RS4 = blockDim.x * 4u;        // ring row pitch in bytes
-  int filled = ii, lo = ii;                    // rows [max(lo, filled - MM_RING), filled) are requested / landed
-  const float* gp = col + (size_t)ii * nchan;  // global address of row `filled`
-  int gend[MM_PEND + 1];                       // gend[k]: `filled` after the group committed k iterations ago
-#pragma unroll
-  for (int k = 0; k <= MM_PEND; k++) gend[k] = ii;
-  float* op = a.out + c;
-  unsigned char* sp = a.sliced ? a.sliced + c : nullptr;
-  unsigned char* bp = (corr_on && a.corr.out) ? a.corr.out + c : nullptr;
-  const int order = a.order, slv = a.slicer_levels, kbits = a.corr.bits_per_symbol;
-  const float s_alpha = a.slicer_alpha, s_beta = a.slicer_beta;
-  const MMParams mp = a.p;
-  const CorrParams cp = a.corr.p;
-  while (oo < a.max_out && ii < ni) {
-    {  // top up the ring: rows [filled, min(ii + MM_RING - MM_BACK, ninput))
-      const int want = min(ii + (MM_RING - MM_BACK), ninput);
-      while (filled < want) {
-        const unsigned dst = ring_s + (unsigned)(filled & (MM_RING - 1)) * RS4;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gp) : "memory");
-        gp += nchan;
-        filled++;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-      for (int k = MM_PEND; k > 0; k--) gend[k] = gend[k - 1];
-      gend[0] = filled;
-      // rows < gend[MM_PEND] belong to groups older than the MM_PEND most recent ones
-      if (ii + 8 <= gend[MM_PEND]) asm volatile("cp.async.wait_group %0;" ::"n"(MM_PEND) : "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const unsigned src = ring_s + (unsigned)((ii + i) & (MM_RING - 1)) * RS4;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(src));
-    }
-    const float4* tp = reinterpret_cast<const float4*>(tab + 8 * mm_imu(s.mu));
-    const float4 t0 = tp[0], t1 = tp[1];
-    const float cf[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-    const float o = mmse8(cf, v, order);
-    *op = o;
-    op += nchan;
-    unsigned char d = 0;
-    if (slv == 4) d = slice4(o, avg, s_alpha, s_beta);
-    else if (slv == 2) d = slice2(o);
-    if (sp) { *sp = d; sp += nchan; }
-    if (corr_on) {
-      const unsigned dib = smap[d];
-      for (int b = kbits - 1; b >= 0; b--) {  // gr_unpack_k_bits_bb: MSB first
-        const unsigned char t = corr_step(cs.data_reg, cs.flag_reg, cp, (dib >> b) & 1u);
-        if (bp) { *bp = t; bp += nchan; }
-        if (t & 2) {
-          const int h = atomicAdd(a.corr.nhits, 1);
-          if (h < a.corr.max_hits) { a.corr.hits[h].channel = c; a.corr.hits[h].pad = 0; a.corr.hits[h].bit_index = cs.nbits + ob; }
-        }
-        ob++;
-      }
-    }
-    oo++;
-    ii += mm_update(s, mp, o);
-    if (ii < lo || ii < filled - MM_RING) {  // stepped back past what the ring still holds: restart it
-      if (ii < 0) { ii = 0; st.clamped++; }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      filled = lo = ii;
-      gp = col + (size_t)ii * nchan;
-#pragma unroll
-      for (int k = 0; k <= MM_PEND; k++) gend[k] = ii;
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (ii < ni) st.overflow++;
-  st.mu = s.mu; st.omega = s.omega; st.last_sample = s.last_sample; st.slicer_avg = avg;
-  st.next_abs = a.abs_row0 + ii;
-  a.state[c] = st;
-  a.counts[c] = oo;
-  if (corr_on) { cs.nbits += ob; a.corr.state[c] = cs; }
-}
 
 // stand-alone slicer (single stream; the recurrence on d_avg is sequential when alpha != 0)
 __global__ void slicer_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long n, int levels,
