@@ -9,18 +9,24 @@
 // therefore moved out of the warp that carries it.  A CTA owns 64 neighbouring channels (two
 // groups of 32, lane = channel) and six warps:
 //
-//   warps 0,1  CORE    the Mueller & Mueller recursion only.  Branch free: the 8 input samples
-//                      and the interpolator taps are fetched from shared memory speculatively,
-//                      the step is computed, and a predicate (input landed, queue slot free)
-//                      decides whether the new state is committed.  floor()/rint() are done with
-//                      the 1.5*2^23 trick (one FADD/FFMA instead of a conversion-unit round trip);
-//                      the timing-error term picks one of the four exactly equivalent sums.
+//   warps 4,5  CORE    the Mueller & Mueller recursion only, four symbols per trip.  The 8 input
+//                      samples and the interpolator taps are fetched from shared memory
+//                      speculatively, the step is computed, and a predicate (input landed, queue
+//                      slots free, ordinary forward step) decides whether the new state is
+//                      committed.  floor()/rint() are done with the 1.5*2^23 trick (one FADD/FFMA
+//                      instead of a conversion-unit round trip); the timing-error term picks one of
+//                      the four exactly equivalent sums.  Anything unusual (a backward step, the
+//                      last few symbols of a call, |mu| >= 2^22) takes a plain one-symbol path that
+//                      reads the input straight from global memory.
 //   warps 2,3  POST    takes soft symbols from a shared-memory queue, eight at a time: soft symbol
 //                      -> HBM, 4-level (or binary) slicer, dibit map, bit unpack, access-code
-//                      correlation (__popcll over the 64-bit shift register), sync-hit list.
-//   warps 4,5  LOADER  keeps a per-lane ring of the lane's input column in shared memory filled
+//                      correlation over a 16-bit window (__popc over the 64-bit shift register at
+//                      all 16 positions at once; only the registers are carried), sync-hit list.
+//   warps 0,1  LOADER  keeps a per-lane ring of the lane's input column in shared memory filled
 //                      RING-8 rows ahead of the loop with cp.async (LDGSTS: no register staging) and
 //                      publishes how far the data has landed.  HBM latency never meets the loop.
+//                      (A core warp shares its scheduler (warp id % 4) with a loader warp and wins
+//                      the arbitration: the higher warp id goes first.)
 //
 // Warps talk through shared memory only (all six are co-resident by construction, so spinning is
 // safe).  Queue slots carry their own full/empty state (a reserved NaN pattern = empty), so no
@@ -64,32 +70,6 @@ static inline size_t mm_ws_smem_bytes(int ring) {
   return (size_t)(ring + 8) * MMW_CH * 4 + 129 * 8 * 4 + MMW_Q * MMW_CH * 4 + 3 * MMW_CH * 4 + 256;
 }
 
-// The loop update (mm_update in gr_math.cuh) restated for the shortest dependent chain.  Identical
-// results: fmul(+-1, x) is exact, so mm_val = slice(last)*out - slice(out)*last is one of the four
-// sums below, each rounded once exactly like the reference's subtraction; floor() by adding
-// 1.5*2^23 with round-towards-minus-infinity (exact for |mu| < 2^22, else the slow way).
-__device__ __forceinline__ int mmw_update(float& mu, float& omega, float& last, const MMParams& p, float out) {
-  const bool ln = last < 0.f, on = out < 0.f;
-  const float mm_val = ln ? (on ? __fadd_rn(-out, last) : __fsub_rn(-out, last))
-                          : (on ? __fadd_rn(out, last) : __fsub_rn(out, last));
-  last = out;
-  float om = __fadd_rn(omega, __fmul_rn(p.gain_omega, mm_val));
-  om = __fadd_rn(p.omega_mid, branchless_clip(__fsub_rn(om, p.omega_mid), p.omega_relative_limit));
-  omega = om;
-  const float m2 = __fadd_rn(__fadd_rn(mu, om), __fmul_rn(p.gain_mu, mm_val));
-  int adv;
-  if (fabsf(m2) < 4194304.0f) {
-    const float t = __fadd_rd(m2, MMW_MAGIC);
-    adv = __float_as_int(t) - MMW_MAGIC_BITS;
-    mu = __fsub_rn(m2, __fsub_rn(t, MMW_MAGIC));
-  } else {  // also NaN
-    const float fl = floorf(m2);
-    mu = __fsub_rn(m2, fl);
-    adv = (int)fl;
-  }
-  return adv;
-}
-
 template <int RING>
 __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
@@ -102,7 +82,7 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
   unsigned char* smap = reinterpret_cast<unsigned char*>(pub_done + MMW_CH);  // [256] gr_map_bb table
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int role = warp >> 1;                        // 0 core, 1 post, 2 loader
+  const int role = warp >> 1;                        // 0 loader, 1 post, 2 core
   const int cl = (warp & 1) * 32 + lane;             // channel within the CTA
   const int c = blockIdx.x * MMW_CH + cl;
   const bool valid = c < a.nchan;
@@ -122,7 +102,7 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
   int ii0 = (int)(st.next_abs - a.abs_row0);  // may be > 0: samples already consumed
   const bool clamp0 = ii0 < 0;
   if (clamp0) ii0 = 0;
-  if (role == 0) {
+  if (role == 2) {
     pub_ii[cl] = ii0;
     pub_filled[cl] = ii0;
     pub_done[cl] = valid ? 0 : 1;
@@ -135,15 +115,16 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
   const unsigned q_lane = (unsigned)__cvta_generic_to_shared(q + cl);
   constexpr unsigned RP = MMW_CH * 4;  // ring / queue row pitch in bytes
 
-  if (role == 2) {
+  if (role == 0) {
     // ---------------------------------------------------------------------------- LOADER
-    int filled = ii0, g1 = ii0, g2 = ii0;  // fill level after the last / the second to last committed group
+    // Rows [filled - RING, filled) of the lane's column sit in ring slot (row % RING); the loader
+    // runs ahead to pub_ii + RING - BACK, so it only ever overwrites rows < pub_ii - BACK.
+    int filled = ii0, g1 = ii0;  // g1: fill level after the previous trip's group
     const float* gp = col + (size_t)ii0 * nchan;
     while (true) {
       const int cur = mmw_ldv(pub_ii + cl);
       const int fin = mmw_ldv(pub_done + cl);
       const int want = (valid && !fin) ? min(cur + (RING - MMW_BACK), ninput) : filled;
-      const bool any = filled < want;
       while (filled < want) {
         const unsigned slot = (unsigned)filled & (RING - 1);
         const unsigned dst = ring_lane + slot * RP;
@@ -153,34 +134,39 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         filled++;
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      // everything but the two most recent groups has landed: rows < g2
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      // everything but the group just committed has landed: rows < g1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
       __threadfence_block();
-      mmw_stv(pub_filled + cl, g2);
-      g2 = g1;
+      mmw_stv(pub_filled + cl, g1);
       g1 = filled;
       if (__all_sync(0xffffffffu, fin != 0)) break;
-      if (!__any_sync(0xffffffffu, any)) __nanosleep(64);
+      __nanosleep(200);  // ~4 symbols of the loop; the ring holds > 40
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     return;
   }
 
-  if (role == 0) {
+  if (role == 2) {
     // ---------------------------------------------------------------------------- CORE
     float mu = st.mu, omega = st.omega, last = st.last_sample;
-    int ii = ii0, oo = 0, hi = ii0, filled_seen = ii0;
+    int ii = ii0, oo = 0, hi = ii0;
     int clamped = clamp0 ? 1 : 0;
+    bool careful = false;  // the lane's next step goes through the one-symbol path below
     const MMParams mp = a.p;
-    const int order = a.order, max_out = a.max_out;
+    const int order = a.order;
+    const int max_out = valid ? a.max_out : 0;
     const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
     while (true) {
-      bool need_slow = false;
+      // ---- four symbols, committed only while nothing unusual happens ---------------------------
+      // rows < pub_filled have landed; (ii <= fs8) == (ii + 8 <= pub_filled && ii < ni)
+      const int fs8 = min(mmw_ldv(pub_filled + cl), ninput - 1) - 8;
+      // the post warp empties slots in order, so a free slot oo+3 means oo..oo+3 are free
+      const bool qfree4 = mmw_ldq(q_lane + (unsigned)((oo + 3) & (MMW_Q - 1)) * RP) == MMW_EMPTY;
+      const bool fast = !careful && oo + 4 <= max_out && qfree4;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const bool act = valid && oo < max_out && ii < ni;
-        // speculative fetch: any address inside the ring is readable; `ready` below says whether
-        // rows ii..ii+7 of this lane's column are really the ones in these slots
+        // speculative fetch: any address inside the ring is readable; the predicate below says
+        // whether rows ii..ii+7 of this lane's column are really the ones in these slots
         const unsigned src = ring_lane + ((unsigned)ii & (RING - 1)) * RP;
         float v[8], cf[8];
 #pragma unroll
@@ -190,37 +176,44 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         const unsigned ta = tab_s + imu * 32u;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cf[0]), "=f"(cf[1]), "=f"(cf[2]), "=f"(cf[3]) : "r"(ta));
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(cf[4]), "=f"(cf[5]), "=f"(cf[6]), "=f"(cf[7]) : "r"(ta));
-        const unsigned qslot = q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP;
-        const unsigned qw = mmw_ldq(qslot);
-        // rows [max(hi - BACK, ii0), pub_filled) of this lane's column are in the ring and cannot be
-        // recycled by the loader (it never overwrites rows >= pub_ii - BACK, and pub_ii <= hi)
-        const bool behind = ii < max(hi - MMW_BACK, ii0);
-        if (ii + 8 > filled_seen) filled_seen = mmw_ldv(pub_filled + cl);
-        const bool ready = act && !behind && ii + 8 <= filled_seen && qw == MMW_EMPTY;
-        need_slow = need_slow || (act && behind);
-
         const float o = mmse8(cf, v, order);
-        float mu2 = mu, om2 = omega, la2 = last;
-        int ii2 = ii + mmw_update(mu2, om2, la2, mp, o);
+        // mm_update (gr_math.cuh) restated for the shortest dependent chain.  fmul(+-1, x) is exact,
+        // so mm_val = slice(last)*o - slice(o)*last is one of four sums, each rounded once exactly
+        // like the reference's subtraction
+        const bool ln = last < 0.f, on = o < 0.f;
+        const float mm_val = ln ? (on ? __fadd_rn(-o, last) : __fsub_rn(-o, last))
+                                : (on ? __fadd_rn(o, last) : __fsub_rn(o, last));
+        float om = __fadd_rn(omega, __fmul_rn(mp.gain_omega, mm_val));
+        om = __fadd_rn(mp.omega_mid, branchless_clip(__fsub_rn(om, mp.omega_mid), mp.omega_relative_limit));
+        const float m2 = __fadd_rn(__fadd_rn(mu, om), __fmul_rn(mp.gain_mu, mm_val));
+        // floor(m2) by adding 1.5*2^23 rounding towards minus infinity: exact for 0 <= m2 < 2^22
+        const float t = __fadd_rd(m2, MMW_MAGIC);
+        const int adv = __float_as_int(t) - MMW_MAGIC_BITS;
+        const float mu2 = __fsub_rn(m2, __fsub_rn(t, MMW_MAGIC));
         unsigned ob = __float_as_uint(o);
         if (ob == MMW_EMPTY) ob = 0x7fc00000u;
-        if (ready) {
-          mmw_stq(qslot, ob);
-          if (ii2 < 0) { ii2 = 0; clamped++; }
-          mu = mu2; omega = om2; last = la2; ii = ii2;
-          oo++;
-          hi = max(hi, ii);
-          mmw_stv(pub_ii + cl, ii);
+        const bool plain = m2 >= 0.f && m2 < 4194304.0f;  // forward step, floor trick valid (false for NaN)
+        if (fast && ii <= fs8) {
+          if (plain) {
+            mmw_stq(q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP, ob);
+            mu = mu2; omega = om; last = o;
+            ii += adv;
+            oo++;
+          } else {
+            careful = true;  // nothing committed: the step is redone below
+          }
         }
       }
-      const bool act = valid && oo < max_out && ii < ni;
+      mmw_stv(pub_ii + cl, ii);
+      // ---- one symbol the plain way: backward steps, the tail of a call, out-of-range mu --------
+      // (the whole input is in global memory before the kernel starts; the ring is only a latency
+      // optimisation, so this path depends on nobody)
+      const bool act = oo < max_out && ii < ni;
       if (!__any_sync(0xffffffffu, act)) break;
-      if (__any_sync(0xffffffffu, need_slow)) {
-        // a lane stepped back past what its ring still holds (unnormalised input): one step straight
-        // from global memory; the ring catches up with it as ii grows again
-        const bool behind = ii < max(hi - MMW_BACK, ii0);
+      const bool tail = oo + 4 > max_out;  // fewer than four output slots left in this call
+      if (__any_sync(0xffffffffu, act && (careful || tail))) {
         const unsigned qslot = q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP;
-        if (act && behind && mmw_ldq(qslot) == MMW_EMPTY) {
+        if (act && (careful || tail) && mmw_ldq(qslot) == MMW_EMPTY) {
           float v[8], cf[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) v[i] = __ldg(col + (size_t)(ii + i) * nchan);
@@ -232,10 +225,16 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
           if (ob == MMW_EMPTY) ob = 0x7fc00000u;
           mmw_stq(qslot, ob);
           oo++;
-          ii += mmw_update(mu, omega, last, mp, o);
-          if (ii < 0) { ii = 0; clamped++; }
+          MMState s;
+          s.mu = mu; s.omega = omega; s.last_sample = last;
           hi = max(hi, ii);
-          mmw_stv(pub_ii + cl, ii);
+          ii += mm_update(s, mp, o);
+          mu = s.mu; omega = s.omega; last = s.last_sample;
+          if (ii < 0) { ii = 0; clamped++; }
+          // the ring still holds rows >= hi - BACK (the loader never overwrites rows >= pub_ii - BACK
+          // and every published position is <= hi); older rows keep coming from global memory
+          careful = ii < max(hi - MMW_BACK, ii0);
+          mmw_stv(pub_ii + cl, min(ii, hi));
         }
       }
     }
@@ -265,10 +264,20 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
     const float s_alpha = a.slicer_alpha, s_beta = a.slicer_beta;
     const CorrParams cp = a.corr.p;
     const bool discard = a.debug == 1;
+    // window form of the correlator: valid when a match cannot raise its flag inside the same 16 bits
+    const int code_len = cp.flag_bit ? 64 - (__ffsll((long long)cp.flag_bit) - 1) : 0;
+    const bool windowed = corr_on && kbits == 2 && bp == nullptr && code_len >= 16 && a.debug != 3;
+    const int flag_shift = 64 - code_len;
+    const unsigned code_hi = (unsigned)(cp.access_code >> 32), code_lo = (unsigned)cp.access_code;
+    const unsigned mask_hi = (unsigned)(cp.mask >> 32), mask_lo = (unsigned)cp.mask;
     int consumed = 0, ob = 0;
     bool finished = !valid;
 
-    // one soft symbol: HBM store, slicer, symbol store, dibit -> bits -> correlator
+    auto hit = [&](int bit) {
+      const int h = atomicAdd(a.corr.nhits, 1);
+      if (h < a.corr.max_hits) { a.corr.hits[h].channel = c; a.corr.hits[h].pad = 0; a.corr.hits[h].bit_index = cs.nbits + bit; }
+    };
+    // one soft symbol the plain way: HBM store, slicer, symbol store, dibit -> bits -> correlator
     auto emit = [&](float o) {
       *op = o;
       op += nchan;
@@ -281,10 +290,7 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         for (int b = kbits - 1; b >= 0; b--) {  // gr_unpack_k_bits_bb: MSB first
           const unsigned char t = corr_step(cs.data_reg, cs.flag_reg, cp, (dib >> b) & 1u);
           if (bp) { *bp = t; bp += nchan; }
-          if (t & 2) {
-            const int h = atomicAdd(a.corr.nhits, 1);
-            if (h < a.corr.max_hits) { a.corr.hits[h].channel = c; a.corr.hits[h].pad = 0; a.corr.hits[h].bit_index = cs.nbits + ob; }
-          }
+          if (t & 2) hit(ob);
           ob++;
         }
       }
@@ -303,44 +309,46 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         if (full) {
 #pragma unroll
           for (int i = 0; i < MMW_PB; i++) mmw_stq(slot[i], MMW_EMPTY);
-          if (!discard) {
-            if (kbits == 2 && corr_on) {
-              // the common DMR case, fully unrolled so that the eight symbols' independent work
-              // (stores, slicer, table lookups, popcounts) overlaps; only the two shift registers
-              // are carried from bit to bit
-              unsigned dib[MMW_PB];
+          if (discard) {
+          } else if (windowed) {
+            // Eight dibits = 16 bits at once.  Before bit j the data register is (data << j) | (the
+            // first j new bits), so all 16 mismatch counts are independent funnel shifts + popcounts;
+            // a match at bit j lands in the flag register at bit (64 - len) + (15 - j) after the 16
+            // shifts, and the flags that reach bit 63 during these 16 bits are the register's top 16
+            // bits as they are now (len >= 16: no match of this window can get there yet).
+            unsigned bits16 = 0;
 #pragma unroll
-              for (int i = 0; i < MMW_PB; i++) {
-                const float o = __uint_as_float(w[i]);
-                op[(size_t)i * nchan] = o;
-                unsigned char d = 0;
-                if (slv == 4) d = slice4(o, avg, s_alpha, s_beta);
-                else if (slv == 2) d = slice2(o);
-                if (sp) sp[(size_t)i * nchan] = d;
-                dib[i] = smap[d];
-              }
-              op += MMW_PB * nchan;
-              if (sp) sp += MMW_PB * nchan;
-#pragma unroll
-              for (int i = 0; i < MMW_PB; i++) {
-#pragma unroll
-                for (int b = 1; b >= 0; b--) {
-                  const unsigned char t = corr_step(cs.data_reg, cs.flag_reg, cp, (dib[i] >> b) & 1u);
-                  if (bp) bp[(size_t)(2 * i + 1 - b) * nchan] = t;
-                  if (t & 2) {
-                    const int h = atomicAdd(a.corr.nhits, 1);
-                    if (h < a.corr.max_hits) {
-                      a.corr.hits[h].channel = c; a.corr.hits[h].pad = 0; a.corr.hits[h].bit_index = cs.nbits + ob + 2 * i + 1 - b;
-                    }
-                  }
-                }
-              }
-              if (bp) bp += 2 * MMW_PB * nchan;
-              ob += 2 * MMW_PB;
-            } else {
-#pragma unroll 1
-              for (int i = 0; i < MMW_PB; i++) emit(__uint_as_float(w[i]));
+            for (int i = 0; i < MMW_PB; i++) {
+              const float o = __uint_as_float(w[i]);
+              op[(size_t)i * nchan] = o;
+              unsigned char d = 0;
+              if (slv == 4) d = slice4(o, avg, s_alpha, s_beta);
+              else if (slv == 2) d = slice2(o);
+              if (sp) sp[(size_t)i * nchan] = d;
+              bits16 |= ((unsigned)smap[d] & 3u) << (14 - 2 * i);
             }
+            op += MMW_PB * nchan;
+            if (sp) sp += MMW_PB * nchan;
+            const unsigned dhi = (unsigned)(cs.data_reg >> 32), dlo = (unsigned)cs.data_reg;
+            const unsigned inb = bits16 << 16;
+            unsigned mm = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const unsigned shi = __funnelshift_l(dlo, dhi, j), slo = __funnelshift_l(inb, dlo, j);
+              const unsigned nwrong = __popc((shi ^ code_hi) & mask_hi) + __popc((slo ^ code_lo) & mask_lo);
+              mm |= (nwrong <= cp.threshold ? 1u : 0u) << (15 - j);
+            }
+            const unsigned hits16 = (unsigned)(cs.flag_reg >> 48);
+            if (hits16) {
+              for (int j = 0; j < 16; j++)
+                if (hits16 & (0x8000u >> j)) hit(ob + j);
+            }
+            cs.data_reg = (cs.data_reg << 16) | bits16;
+            cs.flag_reg = (cs.flag_reg << 16) | ((unsigned long long)mm << flag_shift);
+            ob += 16;
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < MMW_PB; i++) emit(__uint_as_float(w[i]));
           }
           consumed += MMW_PB;
         } else {
@@ -355,6 +363,8 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
             } else if (consumed == dn - 1) {
               finished = true;
             }
+          } else {
+            __nanosleep(100);
           }
         }
       }

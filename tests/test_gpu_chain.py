@@ -195,3 +195,36 @@ def test_chain_8000_channels_small(orc):
     xr = x.reshape(rows, M)
     ch2.process_host(np.concatenate([np.zeros((T, M), np.complex64), xr[:400]]), 400)
     assert np.array_equal(ch2.fetch()["channels"], y[:400])
+
+
+@pytest.mark.parametrize("code_bits,threshold", [(48, 2), (48, 0), (24, 1), (16, 0), (12, 1), (64, 3)])
+def test_chain_hits_without_byte_stream(orc, code_bits, threshold):
+    """keep_bytes=False runs the correlator 16 bits at a time (window form) instead of bit by bit: the sync-hit
+    list must equal the one derived from the reference-format byte stream (keep_bytes=True) and the oracle's,
+    for access codes on both sides of the 16-bit window limit, across uneven block boundaries."""
+    from grb200 import chain, synth
+    M, T, rows = 40, 8, 3000
+    rng = np.random.default_rng(40 + code_bits)
+    active = [1, 5, 22, 38]
+    x, _ = synth.wideband_compose(rng, M, rows, active, noise_sigma=5e-3)
+    xr = x.reshape(rows, M)
+    sync = synth.access_code_string(synth.DMR_BS_DATA_SYNC_BITS)
+    code = (sync + sync)[:code_bits] if code_bits > 48 else sync[48 - code_bits:]
+    hits = {}
+    for kb in (True, False):
+        cfg = make_cfg(M, T, max_rows=rows, keep_bytes=kb)
+        cfg.access_code, cfg.threshold = code, threshold
+        res = run_chain_blocks(chain.DmrChain(cfg), xr, 700 if kb else 431)
+        hits[kb] = sorted(res[4])
+        if kb:
+            y, byts = res[0], res[3]
+    assert hits[True] == hits[False]
+    # and against the oracle's correlator on the GPU's own channelizer output
+    nh = 0
+    for c in active + [0, 39]:
+        _, _, cb = oracle_tail(orc, cfg, y[:, c], orc.ORDER_SSE)
+        n = len(byts[c])
+        want = [int(i) for i in np.nonzero(cb[:n] & 2)[0]]
+        assert [b for (cc, b) in hits[False] if cc == c] == want, c
+        nh += len(want)
+    assert nh > 0 or code_bits == 64
