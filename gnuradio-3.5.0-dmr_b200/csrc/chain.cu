@@ -180,9 +180,10 @@ int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_comp
     // 2+3. discriminator + matched filter in one pass: Y (8 B/sample) -> F (4 B/sample); the
     //      discriminator output only ever lives in shared memory
     int nt = 0;
-    const float* rt = fir_fff_reversed_taps(h->rrc, &nt, nullptr);
+    fir_fff_reversed_taps(h->rrc, &nt, nullptr);
     h->prof.begin(3, s);
-    if ((rc = demod_front_launch(Y, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad), rt, nt, s)))
+    if ((rc = demod_front_launch(Y, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad),
+                                 fir_fff_front_taps(h->rrc), nt, s)))
       return rc;
     h->prof.end(s);
     h->front_rows = nrows;

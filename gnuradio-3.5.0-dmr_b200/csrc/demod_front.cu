@@ -22,24 +22,31 @@ template <int RHO> static df_kernel_t pick_qm(int qm) {
 int demod_front_max_taps() { return 4 * DF_MAXB - 7; }
 int demod_front_history(int ntaps) { return ntaps + 4; }  // rows of Y that must precede the block
 
-// y: [hist + nrows][M] complex with hist = demod_front_history(ntaps); rt = REVERSED taps.
-int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* rt, int ntaps,
+// host image of the kernel's tap store: tp[al][p] = rt[p - al] (rt = REVERSED taps), zero padded
+std::vector<float> demod_front_tap_table(const float* rt, int ntaps) {
+  std::vector<float> tp((size_t)4 * DF_MAXB * 4, 0.f);
+  for (int al = 0; al < 4; al++)
+    for (int p = 0; p < DF_MAXB * 4; p++) {
+      const int i = p - al;
+      if (i >= 0 && i < ntaps) tp[(size_t)al * DF_MAXB * 4 + p] = rt[i];
+    }
+  return tp;
+}
+
+// y: [hist + nrows][M] complex with hist = demod_front_history(ntaps); d_tp = device copy of
+// demod_front_tap_table().
+int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
                        cudaStream_t s) {
-  if (ntaps < 1 || ntaps > demod_front_max_taps()) return set_error(GRCUDA_EUNSUPPORTED, "demod_front: %d taps", ntaps);
+  if (ntaps < 1 || ntaps > demod_front_max_taps() || !d_tp) return set_error(GRCUDA_EUNSUPPORTED, "demod_front: %d taps", ntaps);
   if (nrows <= 0) return GRCUDA_OK;
   DeviceTables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
   DemodFrontArgs a;
   a.y = y; a.f = f; a.abs_row0 = abs_row0; a.nrows = nrows; a.M = M; a.hist = demod_front_history(ntaps);
-  a.gain = gain; a.atan_table = tabs.atan; a.ntaps = ntaps;
+  a.gain = gain; a.atan_table = tabs.atan; a.ntaps = ntaps; a.tp = d_tp;
   const int n1 = ntaps - 1, rho = n1 & 3;
   a.q = n1 >> 2;
-  for (int al = 0; al < 4; al++)
-    for (int p = 0; p < DF_MAXB * 4; p++) {
-      const int i = p - al;
-      a.tp[al][p] = (i >= 0 && i < ntaps) ? rt[i] : 0.f;
-    }
   df_kernel_t k;
   switch (rho) {
     case 0: k = pick_qm<0>(a.q & 3); break;
@@ -48,7 +55,7 @@ int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int 
     default: k = pick_qm<3>(a.q & 3); break;
   }
   const int J = a.q + 1 + (rho > 0 ? 1 : 0);
-  const size_t smem = ((size_t)(DF_RT + 4 * (J - 1)) * 32 + 257) * sizeof(float);
+  const size_t smem = ((size_t)4 * DF_MAXB * 4 + 260 + (size_t)(DF_RT + 4 * (J - 1)) * 32) * sizeof(float);
   if (smem > 48 * 1024) GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long A0 = (abs_row0 >> 2) << 2;
   const long ntiles = (abs_row0 + nrows - A0 + DF_RT - 1) / DF_RT;
@@ -72,12 +79,12 @@ int grcuda_quad_demod_fir_fff_history(grcuda_fir_fff* f) {
 int grcuda_quad_demod_fir_fff_work_device(grcuda_quad* q, grcuda_fir_fff* f, long nrows, int nchan,
                                           const grcuda_complex* d_in, float* d_out, long abs_row0, void* stream) {
   int nt = 0, order = 0;
-  const float* rt = grb::fir_fff_reversed_taps(f, &nt, &order);
+  grb::fir_fff_reversed_taps(f, &nt, &order);
   if (order != GRCUDA_ORDER_SSE)
     return grb::set_error(GRCUDA_EUNSUPPORTED, "quad_demod_fir_fff: only the SSE summation order is fused");
   if (nrows > 0x7fffffffL || nchan < 1) return grb::set_error(GRCUDA_EINVAL, "quad_demod_fir_fff: bad shape");
-  return grb::demod_front_launch((const float2*)d_in, d_out, abs_row0, (int)nrows, nchan, grb::quad_gain(q), rt, nt,
-                                 (cudaStream_t)stream);
+  return grb::demod_front_launch((const float2*)d_in, d_out, abs_row0, (int)nrows, nchan, grb::quad_gain(q),
+                                 grb::fir_fff_front_taps(f), nt, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "fft_plan.h"
+#include "internal.h"
 #include "kernels_demod.cuh"
 #include "kernel_mm.cuh"
 #include "kernels_fir.cuh"
@@ -350,7 +351,8 @@ __global__ void fir_fff_stream_kernel(const float* __restrict__ in, float* __res
 
 struct grcuda_fir_fff : PlanBase {
   int decim = 1, ntaps = 0, order = GRCUDA_ORDER_SSE;
-  DevBuf d_rt;
+  DevBuf d_rt, d_front_tp;
+  bool has_front_tp = false;
   std::vector<float> new_taps, rt_host;
   bool updated = false;
   unsigned history = 1;
@@ -365,6 +367,13 @@ struct grcuda_fir_fff : PlanBase {
     int rc = d_rt.reserve(std::max<size_t>(4, rt.size() * sizeof(float)));
     if (rc) return rc;
     if (ntaps) GRB_CUDA(cudaMemcpy(d_rt.p, rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    has_front_tp = false;
+    if (ntaps >= 1 && ntaps <= demod_front_max_taps()) {  // tap store of the fused discriminator + FIR kernel
+      const std::vector<float> tp = demod_front_tap_table(rt.data(), ntaps);
+      if ((rc = d_front_tp.reserve(tp.size() * sizeof(float)))) return rc;
+      GRB_CUDA(cudaMemcpy(d_front_tp.p, tp.data(), tp.size() * sizeof(float), cudaMemcpyHostToDevice));
+      has_front_tp = true;
+    }
     if ((size_t)ntaps * sizeof(float) > 48 * 1024) {
       GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1056,6 +1065,7 @@ const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
   if (order) *order = h->order;
   return h->rt_host.data();
 }
+const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }
 float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }
 void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }
 size_t mm_state_bytes(grcuda_mm* h) { return (size_t)h->nchan * sizeof(MMChanState); }

@@ -36,7 +36,10 @@ GR_HD float fast_atan2f(float y, float x, const float* __restrict__ table) {
   const float y_abs = fabsf(y), x_abs = fabsf(x);
   const float z = (y_abs < x_abs) ? GR_FDIV(y_abs, x_abs) : GR_FDIV(x_abs, y_abs);  // :138-141
   float base_angle;
-  if ((double)z < 0.003921569) {  // TAN_MAP_RES is a double literal (:32,147)
+  // `z < TAN_MAP_RES` compares the float with a DOUBLE literal 0.003921569 (:32,147).  The literal lies
+  // strictly between the floats 0x3b808081 and 0x3b808082, so for a float z the test is exactly
+  // z < 0x3b808082 (no FP64 instruction on the device).
+  if (z < 0.00392156932502985f) {
     base_angle = z;
   } else {
     // alpha = z*256 - .5 is evaluated in double and stored to float (:151); z*256 is exact and

@@ -1,6 +1,7 @@
 // Non-ABI accessors between the translation units of libgr_cuda (hidden visibility).
 #pragma once
 #include <cstddef>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/gr_cuda.h"
 
@@ -15,8 +16,10 @@ int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, i
 // fused quadrature_demod_cf + fir_filter_fff (SSE order) on [time][channel] data (demod_front.cu)
 int demod_front_max_taps();
 int demod_front_history(int ntaps);
-int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* rt, int ntaps,
+std::vector<float> demod_front_tap_table(const float* rt, int ntaps);  // host image of the kernel's tap store
+int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
                        cudaStream_t s);
+const float* fir_fff_front_taps(grcuda_fir_fff* h);  // device copy of demod_front_tap_table (nullptr: too many taps)
 // reversed taps / order / gain of the stand-alone plans (host copies)
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order);
 float quad_gain(grcuda_quad* h);

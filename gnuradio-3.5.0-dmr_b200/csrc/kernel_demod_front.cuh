@@ -5,9 +5,17 @@
 //   writes F [nrows][M] float           (4 B/sample)         touches HBM (it lives in a smem tile)
 //
 // A CTA owns 32 neighbouring channels x DF_RT consecutive rows.  Phase 1 computes the discriminator
-// for the tile (+ the FIR history rows above it) into shared memory; phase 2 runs the FIR with a
-// lane = a channel and each thread producing groups of four consecutive outputs a0..a0+3
-// (a0 = 0 mod 4 in ABSOLUTE stream index), so that the four outputs share every loaded sample.
+// for the tile (+ the FIR history rows above it) into shared memory: a warp walks CONSECUTIVE rows
+// of its 32 channels, so the previous sample is the register it loaded one row earlier and the
+// loads of several rows are in flight together.  Phase 2 runs the FIR with a lane = a channel and
+// each thread producing groups of four consecutive outputs a0..a0+3 (a0 = 0 mod 4 in ABSOLUTE
+// stream index), so that the four outputs share every loaded sample; the taps come from shared
+// memory as broadcast LDS.128 (one instruction per output and block of four taps).
+//
+// This kernel is FP32-issue bound, not HBM bound: the reference order forbids FMA contraction
+// (separate IEEE multiply and add per tap: 2 x 36 instructions per output for 29 taps, + the 16-way
+// accumulator tree, + ~50 for the table arctangent with a correctly rounded division), i.e.
+// ~170 instructions per 12 bytes of HBM traffic against a machine balance of ~11 FP32 lanes-ops/B.
 //
 // SSE order restated per output a (see gr_math.cuh dot_sse): the window starts at s = a-(ntaps-1);
 // samples are grouped in ABSOLUTE aligned blocks of four (lane = absolute index mod 4); the output's
@@ -22,7 +30,7 @@
 
 namespace grb {
 
-#define DF_RT 128        // output rows per CTA tile (multiple of 4)
+#define DF_RT 256        // output rows per CTA tile (multiple of 4)
 #define DF_THREADS 256
 #define DF_MAXB 34       // max aligned blocks per output window -> ntaps <= 4*DF_MAXB - 7
 
@@ -34,19 +42,21 @@ struct DemodFrontArgs {
   float gain;
   const float* atan_table;
   int ntaps, q;          // ntaps - 1 = 4*q + rho
-  float tp[4][DF_MAXB * 4];  // tp[al][p] = rt[p - al] (reversed taps shifted by al, zero padded):
-                             // the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
+  const float* tp;       // [4][DF_MAXB * 4] device: tp[al][p] = rt[p - al] (reversed taps shifted by al, zero
+                         // padded): the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
 };
 
 template <int RHO, int QM>
 __global__ void __launch_bounds__(DF_THREADS, 2) demod_front_kernel(const DemodFrontArgs a) {
-  extern __shared__ float df_smem[];  // d tile [drows][32] then atan table [257]
+  extern __shared__ __align__(16) float df_smem[];  // taps [4][DF_MAXB*4], atan table [260], d tile [drows][32]
   constexpr int DELTA_B = RHO > 0 ? 1 : 0;                 // class B (r >= RHO) starts one union block later
   const int q = a.q;
   const int J = q + 1 + DELTA_B;                            // union blocks per group of four outputs
   const int drows = DF_RT + 4 * (J - 1);                    // d rows the tile touches
-  float* dtile = df_smem;
-  float* tab = df_smem + (size_t)drows * 32;
+  float* taps_s = df_smem;
+  float* tab = taps_s + 4 * DF_MAXB * 4;
+  float* dtile = tab + 260;
+  for (int i = threadIdx.x; i < 4 * DF_MAXB * 4; i += DF_THREADS) taps_s[i] = a.tp[i];
   for (int i = threadIdx.x; i < 257; i += DF_THREADS) tab[i] = a.atan_table[i];
 
   const int c0 = blockIdx.x * 32;
@@ -55,32 +65,52 @@ __global__ void __launch_bounds__(DF_THREADS, 2) demod_front_kernel(const DemodF
   const long d_row0 = tile_start - 4L * (J - 1);            // absolute row of dtile row 0
   const long ybase = a.abs_row0 - a.hist;                   // absolute row of y row 0
   const long yrows = (long)a.hist + a.nrows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
   __syncthreads();
 
   // ---- phase 1: discriminator into shared memory (gr_quadrature_demod_cf.cc:56-59) -----------
   {
-    const int ch = threadIdx.x & 31;
-    const int c = c0 + ch;
-    for (int r = threadIdx.x >> 5; r < drows; r += DF_THREADS / 32) {
-      const long p = d_row0 + r;              // absolute row
-      const long yi = p - ybase;              // buffer row of Y[p]
-      float d = 0.f;
-      if (c < a.M && yi >= 0 && yi < yrows) {
-        const float2 cur = __ldg(a.y + yi * a.M + c);
-        float2 prev = make_float2(0.f, 0.f);  // before the buffer = before the stream: zeros
-        if (yi >= 1) prev = __ldg(a.y + (yi - 1) * a.M + c);
-        d = quad_demod(cur, prev, a.gain, tab);
+    constexpr int NW = DF_THREADS / 32;
+    const int per = (drows + NW - 1) / NW;                  // consecutive rows per warp
+    const int r0 = warp * per, r1 = min(drows, r0 + per);
+    const bool cok = c < a.M;
+    const float2* __restrict__ ycol = a.y + (cok ? c : 0);
+    auto ld = [&](long yi) -> float2 {                      // rows outside the buffer: before the stream / not there yet
+      if (cok && yi >= 0 && yi < yrows) return __ldg(ycol + yi * a.M);
+      return make_float2(0.f, 0.f);
+    };
+    const long yi0 = d_row0 + r0 - ybase;                   // buffer row of the first d row of this warp
+    float2 prev = ld(yi0 - 1);
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = ld(yi0 + (r - r0) + u);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long yi = yi0 + (r - r0) + u;
+        // d = 0 where the reference has not produced a sample (before the stream start the history is
+        // zeros, gr_buffer.cc:201-214; rows past the end of the buffer only ever meet zero taps)
+        const float d = (cok && yi >= 0 && yi < yrows) ? quad_demod(v[u], prev, a.gain, tab) : 0.f;
+        dtile[(r + u) * 32 + lane] = d;
+        prev = v[u];
       }
-      dtile[r * 32 + ch] = d;
+    }
+    for (; r < r1; r++) {
+      const long yi = yi0 + (r - r0);
+      const float2 cur = ld(yi);
+      dtile[r * 32 + lane] = (cok && yi >= 0 && yi < yrows) ? quad_demod(cur, prev, a.gain, tab) : 0.f;
+      prev = cur;
     }
   }
   __syncthreads();
 
   // ---- phase 2: RRC FIR, four outputs per thread per step --------------------------------------
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = c0 + lane;
+  const float4* tp4 = reinterpret_cast<const float4*>(taps_s);  // tp4[al * DF_MAXB + b] = taps of block b for alignment al
   for (int g = warp; g < DF_RT / 4; g += DF_THREADS / 32) {
     const long a0 = tile_start + 4L * g;
+    if (a0 + 3 < a.abs_row0 || a0 >= a.abs_row0 + a.nrows) continue;  // warp uniform
     float acc[4][4][4];  // [output r][slot][lane]
 #pragma unroll
     for (int r = 0; r < 4; r++)
@@ -90,7 +120,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) demod_front_kernel(const DemodF
         for (int l = 0; l < 4; l++) acc[r][s][l] = 0.f;
     const float* dcol = dtile + (size_t)(4 * g) * 32 + lane;  // union block j lane l -> dcol[(4j+l)*32]
 
-    // one union block for all four outputs; SLOTJ = j for the first four blocks (prologue rules), -1 after
+    // one union block for all four outputs; SLOT_OF = accumulator slot of this block (see below)
 #define DF_BLOCK(j_, SLOT_OF)                                                              \
     {                                                                                      \
       float x[4];                                                                          \
@@ -102,8 +132,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) demod_front_kernel(const DemodF
         const int P = delta + nbm;                                                         \
         const int al = ((r - RHO) % 4 + 4) % 4;                                            \
         const int slot = SLOT_OF;                                                          \
+        (void)P;                                                                           \
         if ((j_) >= delta) {                                                               \
-          const float* t = a.tp[al] + 4 * ((j_) - delta);                                  \
+          const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                            \
+          const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                     \
           _Pragma("unroll") for (int l = 0; l < 4; l++)                                    \
             acc[r][slot][l] = GR_FADD(acc[r][slot][l], GR_FMUL(t[l], x[l]));               \
         }                                                                                  \
