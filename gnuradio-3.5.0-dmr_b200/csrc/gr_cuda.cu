@@ -504,6 +504,13 @@ struct grcuda_pfb : PlanBase {
     if (rc0) return rc0;
     if (nout <= 0) return GRCUDA_OK;
     const bool fast = (rr == (int)M) && TT;
+    // bulk copies need 16-byte aligned row segments: even M (8-byte samples), 16-byte aligned base
+    const bool tma_ok = fast && TT <= 16 && (M % 2 == 0) && (((uintptr_t)d_rows_in & 15) == 0) && !getenv("GRCUDA_PFB_NO_TMA");
+    if (tma_ok) {
+      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
+      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
+      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
+    }
     // The branch-filter output u is only an intermediate: process in row chunks small enough
     // to stay resident in the 126 MB L2 between the FIR kernel and the FFT kernel.
     long crow = chunk_rows;
@@ -519,7 +526,24 @@ struct grcuda_pfb : PlanBase {
     for (long r0 = 0; r0 < nout; r0 += crow) {
       const long n = std::min(crow, nout - r0);
       prof.begin(0, s);
-      if (fast) {
+      if (fast && tma_ok) {
+        // TMA-staged branch filter: 256-column tiles, grid sized to whole waves of one CTA per SM
+        PfbFirArgs a;
+        a.x = d_rows_in + r0 * (long)M; a.u = d_u.as<float2>(); a.taps_t = d_taps_t.as<float>();
+        a.M = (int)M; a.T = T; a.nrows = n;
+        const int gx = ((int)M + PFT_COLS - 1) / PFT_COLS;
+        long gy = std::max<long>(1, (n + 383) / 384);
+        const long waves = (gx * gy + sm_count() - 1) / sm_count();
+        gy = std::max<long>(1, std::min<long>(n, waves * sm_count() / gx));
+        a.rows_per_thread = (int)((n + gy - 1) / gy);
+        dim3 grid(gx, (unsigned)((n + a.rows_per_thread - 1) / a.rows_per_thread));
+        const size_t smem = pfb_fir_tma_smem();
+        switch (TT) {
+          case 4: pfb_fir_tma_kernel<4><<<grid, PFT_COLS, smem, s>>>(a); break;
+          case 8: pfb_fir_tma_kernel<8><<<grid, PFT_COLS, smem, s>>>(a); break;
+          default: pfb_fir_tma_kernel<16><<<grid, PFT_COLS, smem, s>>>(a); break;
+        }
+      } else if (fast) {
         PfbFirArgs a;
         a.x = d_rows_in + r0 * (long)M; a.u = d_u.as<float2>(); a.taps_t = d_taps_t.as<float>();
         a.M = (int)M; a.T = T; a.nrows = n;

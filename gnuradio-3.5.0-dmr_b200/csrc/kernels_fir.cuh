@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "fft_radix.cuh"
+#include "tma.cuh"
 
 namespace grb {
 
@@ -171,15 +172,23 @@ __global__ void __launch_bounds__(128) pfb_fir_kernel(const PfbFirArgs a) {
     }
   }
   float2* __restrict__ uc = a.u + (M - 1 - j);
-  // process rows in groups of TT so that window indices are compile-time
+  // rows in groups of TT so that window indices are compile-time; the loads of NB rows are issued
+  // back to back BEFORE their arithmetic (NB x 256 B per warp in flight): the kernel is a pure
+  // stream and only memory-level parallelism keeps HBM busy
+  constexpr int NB = TT < 8 ? TT : 8;
   for (long mb = m0; mb < m1; mb += TT) {
 #pragma unroll
-    for (int s = 0; s < TT; s++) {
-      const long m = mb + s;
-      if (m < m1) {
+    for (int sb = 0; sb < TT; sb += NB) {
+      float2 nx[NB];
+      const float2* __restrict__ xr = xc + (mb + sb + H) * (long)M;
+#pragma unroll
+      for (int s = 0; s < NB; s++) nx[s] = (mb + sb + s < m1) ? __ldg(xr + (long)s * M) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int s2 = 0; s2 < NB; s2++) {
         // slot for this row: relative index s in the group; the preload put row (m0+H-d) at
         // slot (TT-d)%TT, i.e. row (mb+H+s) belongs to slot s.
-        w[s] = __ldg(xc + (m + H) * (long)M);
+        const int s = sb + s2;
+        w[s] = nx[s2];
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < TT; t++) {
@@ -187,9 +196,95 @@ __global__ void __launch_bounds__(128) pfb_fir_kernel(const PfbFirArgs a) {
           acc.x += h[t] * x.x;
           acc.y += h[t] * x.y;
         }
-        uc[m * (long)M] = acc;
+        if (mb + s < m1) uc[(mb + s) * (long)M] = acc;
       }
     }
+  }
+}
+
+// Same filter, sample windows staged through shared memory by the bulk copy engine (TMA).
+// A CTA owns 256 neighbouring columns x rows_per_cta output rows.  The 2 KB row segments of its
+// column tile arrive in stages of 32 rows (64 KB) through cp.async.bulk; three stages (192 KB) are
+// in flight per SM whatever the register allocation, which is what a 16 B/sample stream with
+// ~1 us of HBM latency needs (the register-window kernel above has 16 warps x 8 loads x 256 B =
+// 32 KB in flight per SM and stops at a third of the HBM rate).  Thread = column: one LDS.64 per row
+// (conflict free), TT FFMA pairs on the register window, one coalesced store.
+#define PFT_COLS 256
+#define PFT_SR 32
+#define PFT_NST 3
+static inline size_t pfb_fir_tma_smem() { return (size_t)PFT_NST * PFT_SR * PFT_COLS * sizeof(float2) + 64; }
+
+template <int TT>
+__global__ void __launch_bounds__(PFT_COLS) pfb_fir_tma_kernel(const PfbFirArgs a) {
+  extern __shared__ __align__(128) unsigned char pft_smem[];
+  float2* stage = reinterpret_cast<float2*>(pft_smem);  // [NST][SR][COLS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(pft_smem + (size_t)PFT_NST * PFT_SR * PFT_COLS * sizeof(float2));
+  const int tid = threadIdx.x;
+  const int M = a.M, T = a.T, H = a.T;
+  const int col0 = blockIdx.x * PFT_COLS;
+  const int ncols = min(PFT_COLS, M - col0);
+  const long m0 = (long)blockIdx.y * a.rows_per_thread;
+  const long m1 = min(a.nrows, m0 + a.rows_per_thread);
+  if (m0 >= m1) return;
+  // sequence of buffer rows this CTA walks: bs + i, i in [0, nseq); output row of step i is m0 + i - (T-1)
+  const long bs = m0 + H - (T - 1);
+  const int nseq = (int)(m1 - m0) + T - 1;
+  const int nstages = (nseq + PFT_SR - 1) / PFT_SR;
+  const unsigned row_bytes = (unsigned)ncols * sizeof(float2);
+
+  if (tid == 0) {
+    for (int s = 0; s < PFT_NST; s++) mbar_init(full + s, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // warp 0: the 32 row segments of stage k
+    const int i0 = k * PFT_SR;
+    const int nr = min(PFT_SR, nseq - i0);
+    uint64_t* bar = full + (k % PFT_NST);
+    if (tid == 0) mbar_expect_tx(bar, row_bytes * (unsigned)nr);
+    __syncwarp();
+    if (tid < nr) {
+      float2* dst = stage + ((size_t)(k % PFT_NST) * PFT_SR + tid) * PFT_COLS;
+      bulk_g2s(dst, a.x + (bs + i0 + tid) * (long)M + col0, row_bytes, bar);
+    }
+  };
+  if (tid < 32)
+    for (int k = 0; k < PFT_NST && k < nstages; k++) issue(k);
+
+  const bool cok = tid < ncols;
+  const int j = col0 + (cok ? tid : 0);
+  float h[TT];
+#pragma unroll
+  for (int t = 0; t < TT; t++) h[t] = __ldg(a.taps_t + (size_t)t * M + j);
+  float2 w[TT];  // slot s holds sequence row i with i % TT == s
+#pragma unroll
+  for (int s = 0; s < TT; s++) w[s] = make_float2(0.f, 0.f);
+  float2* __restrict__ uc = a.u + (M - 1 - j) + (m0 - (T - 1)) * (long)M;  // + i * M = output row of step i
+
+  for (int k = 0; k < nstages; k++) {
+    mbar_wait(full + (k % PFT_NST), (unsigned)(k / PFT_NST) & 1u);
+    const float2* __restrict__ sp = stage + (size_t)(k % PFT_NST) * PFT_SR * PFT_COLS + tid;
+#pragma unroll
+    for (int g = 0; g < PFT_SR / TT; g++) {
+      const int ig = k * PFT_SR + g * TT;
+      if (ig < nseq) {  // CTA uniform
+#pragma unroll
+        for (int s = 0; s < TT; s++) {
+          const int i = ig + s;
+          w[s] = sp[(g * TT + s) * PFT_COLS];
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < TT; t++) {
+            const float2 x = w[(s - t + TT) % TT];
+            acc.x += h[t] * x.x;
+            acc.y += h[t] * x.y;
+          }
+          if (cok && i >= T - 1 && i < nseq) uc[(long)i * M] = acc;
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with this stage's buffer
+    if (tid < 32 && k + PFT_NST < nstages) issue(k + PFT_NST);
   }
 }
 
