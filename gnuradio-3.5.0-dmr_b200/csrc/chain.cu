@@ -10,7 +10,14 @@
 //                           unfused: YH = 1, the discriminator's x[i-1])
 //   D  [nrrc-1 + R][M] f32  discriminator output (UNFUSED path only: generic summation order or very
 //                           long matched filters); first nrrc-1 rows = carried history of the RRC FIR
-//   F  [KEEP + R][M] f32    matched-filter output; first KEEP rows = carry for the M&M interpolator
+//   F  2 x [KEEP + R][M] f32  matched-filter output, double buffered; first KEEP rows = carry for the
+//                           M&M interpolator (copied from the other buffer's tail)
+//
+// Streams.  The front (channelizer, discriminator, matched filter: HBM / FP32 bound, fills the
+// machine) runs on the caller's stream; the tail (M&M recursion + slicer + correlator: 125 CTAs
+// running at instruction latency, see kernel_mm.cuh) runs on the chain's own tail stream and
+// therefore overlaps the front of the NEXT block.  Events order the two: tail(b) waits for
+// front(b); front(b+2) waits for tail(b) before it reuses that F buffer.
 //   soft/sym [max_sym][M], bytes [2*max_sym][M], hits[], per-channel state arrays
 #include <algorithm>
 #include <cmath>
@@ -35,7 +42,15 @@ struct grcuda_dmr_chain {
   grcuda_mm* mm = nullptr;
   grcuda_corr* corr = nullptr;
   std::vector<int> symbol_map;
-  DevBuf Y, D, F, soft, sym, counts, bytes, hits, nhits, d_in_host;
+  DevBuf Y, D, Fb[2], soft, sym, counts, bytes, hits, nhits, d_in_host;
+  int fcur = 0;           // F buffer of the block whose front ran last
+  bool pipeline = true;   // tail on its own stream (overlaps the next block's front)
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
+  bool tail_pending[2] = {false, false};
+  cudaEvent_t ev_state = nullptr;  // export/import_state copies (they touch what the tail kernel reads and writes)
+  bool state_pending = false;
+  int prev_rows = 0;      // rows of the previous block (where its F tail sits)
   cudaStream_t stream = nullptr;
   Stager stager;
   long long abs_row = 0;  // absolute channel-rate row index of the next new row
@@ -52,7 +67,13 @@ struct grcuda_dmr_chain {
     if (mm) grcuda_clock_recovery_mm_ff_destroy(mm);
     if (corr) grcuda_correlate_access_code_bb_destroy(corr);
     if (stream) cudaStreamDestroy(stream);
+    if (tail_stream) cudaStreamDestroy(tail_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int i = 0; i < 2; i++) {
+      if (ev_front[i]) cudaEventDestroy(ev_front[i]);
+      if (ev_tail[i]) cudaEventDestroy(ev_tail[i]);
+    }
+    if (ev_state) cudaEventDestroy(ev_state);
     for (int i = 0; i < 2; i++) {
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -92,7 +113,8 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   int rc = 0;
   rc = rc ? rc : h->Y.reserve((h->YH + R) * M * sizeof(float2));
   if (!h->fused) rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
-  rc = rc ? rc : h->F.reserve((KEEP + R) * M * sizeof(float));
+  rc = rc ? rc : h->Fb[0].reserve((KEEP + R) * M * sizeof(float));
+  rc = rc ? rc : h->Fb[1].reserve((KEEP + R) * M * sizeof(float));
   rc = rc ? rc : h->soft.reserve((size_t)h->max_sym * M * sizeof(float));
   rc = rc ? rc : h->sym.reserve((size_t)h->max_sym * M);
   rc = rc ? rc : h->counts.reserve(M * sizeof(int));
@@ -103,13 +125,21 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   // stream start: all histories are the zeros the reference runtime pre-loads (gr_buffer.cc:201-214)
   if (cudaMemset(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2)) != cudaSuccess ||
       (!h->fused && cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4) != cudaSuccess) ||
-      cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
+      cudaMemset(h->Fb[0].p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
+      cudaMemset(h->Fb[1].p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
       cudaMemset(h->nhits.p, 0, sizeof(int)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_front[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_front[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming) != cudaSuccess) {
     set_error(GRCUDA_ECUDA, "dmr_chain: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
     return nullptr;
   }
+  h->pipeline = getenv("GRCUDA_CHAIN_NO_OVERLAP") == nullptr;
   return h;
 }
 
@@ -128,7 +158,7 @@ int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
   GRB_CUDA(cudaDeviceSynchronize());
   GRB_CUDA(cudaMemset(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2)));
   if (!h->fused) GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
-  GRB_CUDA(cudaMemset(h->F.p, 0, (size_t)KEEP * M * sizeof(float)));
+  h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
   return GRCUDA_OK;
 }
@@ -138,26 +168,47 @@ int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* st
   const size_t M = h->M;
   GRB_CUDA(cudaMemsetAsync(h->Y.p, 0, (size_t)h->YH * M * sizeof(float2), s));
   if (!h->fused) GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
-  GRB_CUDA(cudaMemsetAsync(h->F.p, 0, (size_t)KEEP * M * sizeof(float), s));
+  h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
   return GRCUDA_OK;
 }
 long long grcuda_dmr_chain_tell(grcuda_dmr_chain* h) { return h->abs_row; }
 
 size_t grcuda_dmr_chain_state_bytes(grcuda_dmr_chain* h) { return mm_state_bytes(h->mm) + corr_state_bytes(h->corr); }
+// the loop state is read and written by the tail kernel, which may run on the chain's tail stream:
+// order the copy after the last tail, and the next tail after the copy
+static int state_copy_begin(grcuda_dmr_chain* h, cudaStream_t s) {
+  if (h->tail_pending[h->fcur]) GRB_CUDA(cudaStreamWaitEvent(s, h->ev_tail[h->fcur], 0));
+  return GRCUDA_OK;
+}
+static int state_copy_end(grcuda_dmr_chain* h, cudaStream_t s) {
+  GRB_CUDA(cudaEventRecord(h->ev_state, s));
+  h->state_pending = true;
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_join(grcuda_dmr_chain* h, void* stream_) {
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  for (int i = 0; i < 2; i++)
+    if (h->tail_pending[i]) GRB_CUDA(cudaStreamWaitEvent(s, h->ev_tail[i], 0));
+  return GRCUDA_OK;
+}
 int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  int rc0 = state_copy_begin(h, s);
+  if (rc0) return rc0;
   GRB_CUDA(cudaMemcpyAsync(d_state, mm_state_ptr(h->mm), mm_state_bytes(h->mm), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync((char*)d_state + mm_state_bytes(h->mm), corr_state_ptr(h->corr), corr_state_bytes(h->corr),
                            cudaMemcpyDeviceToDevice, s));
-  return GRCUDA_OK;
+  return state_copy_end(h, s);
 }
 int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  int rc0 = state_copy_begin(h, s);
+  if (rc0) return rc0;
   GRB_CUDA(cudaMemcpyAsync(mm_state_ptr(h->mm), d_state, mm_state_bytes(h->mm), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync(corr_state_ptr(h->corr), (const char*)d_state + mm_state_bytes(h->mm), corr_state_bytes(h->corr),
                            cudaMemcpyDeviceToDevice, s));
-  return GRCUDA_OK;
+  return state_copy_end(h, s);
 }
 
 // front stage: channelizer -> discriminator -> matched filter (finite-memory stages: a time shard
@@ -165,14 +216,29 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
 int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
     return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
+  if (h->front_rows > 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_front twice without process_tail");
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
-  h->last_stream = s;
   const size_t M = h->M;
   const long R = nrows;
   int rc;
+  const int cur = h->fcur ^ 1;  // this block's F buffer; the other one holds the previous block
   float2* Y = h->Y.as<float2>();
   float* D = h->D.as<float>();
-  float* F = h->F.as<float>();
+  float* F = h->Fb[cur].as<float>();
+  const float* Fprev = h->Fb[cur ^ 1].as<float>();
+  // F[cur] was last read by the tail of the block before the previous one
+  if (h->tail_pending[cur]) {
+    GRB_CUDA(cudaStreamWaitEvent(s, h->ev_tail[cur], 0));
+    h->tail_pending[cur] = false;
+  }
+  // M&M look-back carry: the last KEEP matched-filter rows of the previous block (written by its
+  // front on this same stream order; its tail only reads them)
+  h->prof.begin(6, s);
+  if (h->prev_rows > 0)
+    GRB_CUDA(cudaMemcpyAsync(F, Fprev + (size_t)h->prev_rows * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  else
+    GRB_CUDA(cudaMemsetAsync(F, 0, (size_t)KEEP * M * sizeof(float), s));
+  h->prof.end(s, 0);
   const size_t YH = h->YH;
   // 1. channelizer: [T + R][M] -> Y rows YH..YH+R
   if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + YH * M), s))) return rc;
@@ -186,17 +252,25 @@ int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_comp
                                  fir_fff_front_taps(h->rrc), nt, s)))
       return rc;
     h->prof.end(s);
-    h->front_rows = nrows;
-    return GRCUDA_OK;
+  } else {
+    // 2. discriminator: Y rows 0..R -> D rows (nrrc-1)..
+    h->prof.begin(2, s);
+    if ((rc = grcuda_quadrature_demod_cf_work_device(h->quad, R, (int)M, (const grcuda_complex*)Y, D + (size_t)(h->nrrc - 1) * M, s))) return rc;
+    h->prof.end(s);
+    // 3. matched filter: D (history-prefixed; row 0 is absolute row abs_row-(nrrc-1)) -> F rows KEEP..
+    h->prof.begin(3, s);
+    if ((rc = grcuda_fir_filter_fff_work_device(h->rrc, R, (int)M, D, F + (size_t)KEEP * M, (long)(h->abs_row - (h->nrrc - 1)), s))) return rc;
+    h->prof.end(s);
   }
-  // 2. discriminator: Y rows 0..R -> D rows (nrrc-1)..
-  h->prof.begin(2, s);
-  if ((rc = grcuda_quadrature_demod_cf_work_device(h->quad, R, (int)M, (const grcuda_complex*)Y, D + (size_t)(h->nrrc - 1) * M, s))) return rc;
-  h->prof.end(s);
-  // 3. matched filter: D (history-prefixed; row 0 is absolute row abs_row-(nrrc-1)) -> F rows KEEP..
-  h->prof.begin(3, s);
-  if ((rc = grcuda_fir_filter_fff_work_device(h->rrc, R, (int)M, D, F + (size_t)KEEP * M, (long)(h->abs_row - (h->nrrc - 1)), s))) return rc;
-  h->prof.end(s);
+  // carries of the front stages for the next block (small device-to-device copies, stream ordered;
+  // nrows >= min_rows guarantees that source and destination never overlap)
+  h->prof.begin(6, s);
+  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, (size_t)h->YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  if (!h->fused && h->nrrc > 1)
+    GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  h->prof.end(s, 0);
+  GRB_CUDA(cudaEventRecord(h->ev_front[cur], s));
+  h->fcur = cur;
   h->front_rows = nrows;
   return GRCUDA_OK;
 }
@@ -207,12 +281,15 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
   if (h->front_rows <= 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_tail without a pending process_front");
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
   h->last_stream = s;
-  const size_t M = h->M;
   const long R = h->front_rows;
+  const int cur = h->fcur;
   int rc;
-  float2* Y = h->Y.as<float2>();
-  float* D = h->D.as<float>();
-  float* F = h->F.as<float>();
+  float* F = h->Fb[cur].as<float>();
+  GRB_CUDA(cudaStreamWaitEvent(s, h->ev_front[cur], 0));
+  if (h->state_pending) {
+    GRB_CUDA(cudaStreamWaitEvent(s, h->ev_state, 0));
+    h->state_pending = false;
+  }
   // 4+5. clock recovery + slicer + (dibit map -> bits -> sync correlation fused in the same kernel)
   //      over F rows [abs_row-KEEP, abs_row+R)
   if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
@@ -223,23 +300,20 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
                            (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
     return rc;
   h->prof.end(s);
-  // 6. carries for the next block (small device-to-device copies, stream ordered;
-  //    nrows >= min_rows guarantees that source and destination never overlap)
-  h->prof.begin(6, s);
-  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, (size_t)h->YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-  if (!h->fused && h->nrrc > 1)
-    GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  GRB_CUDA(cudaMemcpyAsync(F, F + (size_t)R * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  h->prof.end(s, 0);
+  GRB_CUDA(cudaEventRecord(h->ev_tail[cur], s));
+  h->tail_pending[cur] = true;
   h->abs_row += R;
   h->last_rows = (int)R;
+  h->prev_rows = (int)R;
   h->front_rows = 0;
   return GRCUDA_OK;
 }
 
 int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   int rc = grcuda_dmr_chain_process_front_device(h, d_in, nrows, stream_);
-  return rc ? rc : grcuda_dmr_chain_process_tail_device(h, stream_);
+  if (rc) return rc;
+  // the tail goes to the chain's own stream: it overlaps the front of the next block
+  return grcuda_dmr_chain_process_tail_device(h, h->pipeline ? (void*)h->tail_stream : stream_);
 }
 
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on) {
@@ -276,7 +350,10 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
   const size_t buf_bytes = (size_t)(h->T + sub) * M * sizeof(float2);
   for (int i = 0; i < 2; i++)
     if ((rc = h->d_stage[i].reserve(buf_bytes))) return rc;
-  GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), h->stream));
+  {
+    cudaStream_t ts = h->pipeline ? h->tail_stream : h->stream;  // where the tails of the sub-blocks run
+    GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), ts));
+  }
   h->accumulate_hits = true;
   int done = 0, i = 0;
   while (done < nrows) {
@@ -297,6 +374,7 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
   }
   h->accumulate_hits = false;
   GRB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->last_stream) GRB_CUDA(cudaStreamSynchronize(h->last_stream));
   return GRCUDA_OK;
 }
 

@@ -15,6 +15,7 @@
 // HBM traffic = 8 B read + 8 B written per point: the algorithmic minimum (16 B/sample).
 #pragma once
 #include "fft_radix.cuh"
+#include "tma.cuh"
 
 namespace grb {
 
@@ -42,21 +43,23 @@ __device__ __forceinline__ int fft_phys(int i, int pad_div) { return pad_div ? i
 template <int PADDIV> __device__ __forceinline__ int fft_phys_c(int i) { return PADDIV ? i + i / (PADDIV ? PADDIV : 1) : i; }
 
 // ---- one pass, compile-time radix; N / Ns may be compile-time (fixed kernels) or runtime ------
-template <int R, int DIR, bool FROM_GLOBAL, bool TO_GLOBAL, int PADDIV>
+template <int R, int DIR, bool FROM_GLOBAL, bool TO_GLOBAL, int PADDIV, bool STAGED = false>
 __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j, bool row_ok, long row,
-                                         float2* __restrict__ srow, const float2* __restrict__ tw) {
+                                         float2* __restrict__ srow, const float2* __restrict__ tw,
+                                         const float2* __restrict__ staged_row = nullptr) {
   const int nb = N / R;
   const bool active = row_ok && j < nb;
   float2 v[R];
   if (active) {
     if (FROM_GLOBAL) {
-      const float2* __restrict__ g = a.in + row * (long)N;
+      // STAGED: the row was brought into shared memory by a bulk copy while the previous row was computed
+      const float2* __restrict__ g = STAGED ? staged_row : a.in + row * (long)N;
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const int i = j + r * nb;
         int gi = i + a.in_rot;
         if (gi >= N) gi -= N;
-        float2 x = __ldg(g + gi);
+        float2 x = STAGED ? g[gi] : __ldg(g + gi);
         if (a.window) {
           const float w = __ldg(a.window + i);
           x.x *= w;
@@ -104,24 +107,61 @@ template <int R0, int R1, int R2, int R3> struct FftFixedCfg {
 
 // MINB = resident CTAs per SM the register allocation must allow (occupancy vs. spills trade-off,
 // chosen per plan from measurements; see profiles/).
-template <int DIR, int R0, int R1, int R2, int R3, int MINB>
+// STAGED: persistent CTAs prefetch their input rows into shared memory with cp.async.bulk (TMA): the
+// load of group g + gridDim.x is issued as soon as the first pass has pulled group g out of the
+// stage buffer, and lands while the remaining passes and the HBM write of group g run, so the
+// HBM read, the butterflies and the HBM write of successive rows overlap even at one CTA per SM
+// (an 8000-point row needs 64 KB of work space and ~100 registers x 400 threads).  One stage
+// buffer only: work + stage = 131 KB, which leaves room for a CTA of the (long, latency bound)
+// clock-recovery kernel of the previous block on the same SM.
+template <int DIR, int R0, int R1, int R2, int R3, int MINB, bool STAGED>
 __global__ void __launch_bounds__(FftFixedCfg<R0, R1, R2, R3>::THREADS, MINB) fft_fixed_kernel(const FftArgs a) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int NP = FftFixedCfg<R0, R1, R2, R3>::NP;
   constexpr int PADDIV = (NP > 1 && (R0 % 2 == 0)) ? R0 : 0;
-  extern __shared__ float2 fft_smem[];
+  extern __shared__ __align__(128) float2 fft_smem[];
   const int tpr = a.threads_per_row;
   const int lrow = threadIdx.x / tpr;
   const int j = threadIdx.x - lrow * tpr;
   float2* srow = fft_smem + (size_t)lrow * a.row_stride;
   const long ngroups = (a.nrows + a.rows_per_cta - 1) / a.rows_per_cta;
-  for (long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+  // staged layout: [work rows][stage][mbarrier]; stage = rows_per_cta * N float2
+  const size_t work = (((size_t)a.rows_per_cta * a.row_stride * sizeof(float2)) + 127) / 128 * 128;
+  const size_t stage_bytes = (size_t)a.rows_per_cta * N * sizeof(float2);
+  unsigned char* base = reinterpret_cast<unsigned char*>(fft_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + work + stage_bytes);
+  auto issue = [&](long g) {  // one thread
+    const long r0 = g * a.rows_per_cta;
+    const unsigned bytes = (unsigned)(min((long)a.rows_per_cta, a.nrows - r0) * N * sizeof(float2));
+    mbar_expect_tx(full, bytes);
+    bulk_g2s(base + work, a.in + r0 * (long)N, bytes, full);
+  };
+  if (STAGED) {
+    if (threadIdx.x == 0) {
+      mbar_init(full, 1);
+      mbar_init_fence();
+      if ((long)blockIdx.x < ngroups) issue(blockIdx.x);
+    }
+    __syncthreads();
+  }
+  int it = 0;
+  for (long g = blockIdx.x; g < ngroups; g += gridDim.x, it++) {
     const long row = g * a.rows_per_cta + lrow;
     const bool row_ok = lrow < a.rows_per_cta && row < a.nrows;
+    const float2* st = nullptr;
+    if (STAGED) {
+      mbar_wait(full, (unsigned)it & 1u);
+      st = reinterpret_cast<const float2*>(base + work) + (size_t)lrow * N;
+    }
     if (NP == 1) {
-      fft_pass<R0, DIR, true, true, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
+      fft_pass<R0, DIR, true, true, PADDIV, STAGED>(a, N, 1, j, row_ok, row, srow, nullptr, st);
+      if (STAGED) {
+        __syncthreads();  // every thread has its inputs in registers: the stage can be refilled
+        if (threadIdx.x == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x);
+      }
     } else {
-      fft_pass<R0, DIR, true, false, PADDIV>(a, N, 1, j, row_ok, row, srow, nullptr);
+      fft_pass<R0, DIR, true, false, PADDIV, STAGED>(a, N, 1, j, row_ok, row, srow, nullptr, st);  // ends with a barrier
+      if (STAGED && threadIdx.x == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x);
       if (NP == 2) {
         fft_pass<R1, DIR, false, true, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
       } else {

@@ -18,6 +18,9 @@ struct FftPlan {
   int npass = 0;
   int radix[FFT_MAX_PASSES] = {0};
   fft_kernel_t kernel = nullptr;
+  fft_kernel_t kernel_staged = nullptr;  // same plan, input rows double-buffered in smem by bulk copies
+  size_t smem_staged = 0;
+  int max_ctas_staged = 0;
   float2* d_tw = nullptr;
   const float2* tw[FFT_MAX_PASSES] = {nullptr};
   int rows_per_cta = 1, threads_per_row = 1, row_stride = 0, pad_div = 0;
@@ -27,10 +30,11 @@ struct FftPlan {
   std::string desc;
 };
 
-struct FixedEntry { int n, r0, r1, r2, r3, minb; fft_kernel_t fwd, bwd; };
-#define FX(R0, R1, R2, R3, MB)                                                                \
-  { (R0) * (R1) * (R2) * (R3), R0, R1, R2, R3, MB, fft_fixed_kernel<-1, R0, R1, R2, R3, MB>, \
-    fft_fixed_kernel<1, R0, R1, R2, R3, MB> }
+struct FixedEntry { int n, r0, r1, r2, r3, minb; fft_kernel_t fwd, bwd, fwd_s, bwd_s; };
+#define FX(R0, R1, R2, R3, MB)                                                                       \
+  { (R0) * (R1) * (R2) * (R3), R0, R1, R2, R3, MB, fft_fixed_kernel<-1, R0, R1, R2, R3, MB, false>, \
+    fft_fixed_kernel<1, R0, R1, R2, R3, MB, false>, fft_fixed_kernel<-1, R0, R1, R2, R3, MB, true>, \
+    fft_fixed_kernel<1, R0, R1, R2, R3, MB, true> }
 // For a given n the FIRST entry is the default; GRCUDA_FFT_VARIANT=<k> selects the k-th.
 static const FixedEntry kFixed[] = {
     FX(20, 20, 20, 1, 1), FX(20, 20, 20, 1, 2), FX(10, 10, 10, 8, 1), FX(10, 10, 10, 8, 2),  // 8000
@@ -108,6 +112,11 @@ FftPlan* fft_plan_create(int n, int dir) {
     p->row_stride = n + (p->pad_div ? n / p->pad_div : 0) + 1;
     p->threads = p->rows_per_cta * tpr;
     p->smem = p->npass > 1 ? (size_t)p->rows_per_cta * p->row_stride * sizeof(float2) : 0;
+    // staged variant: work rows (128 B aligned) + one input stage + its mbarrier
+    p->kernel_staged = p->dir < 0 ? fe->fwd_s : fe->bwd_s;
+    p->smem_staged = (((size_t)p->rows_per_cta * p->row_stride * sizeof(float2)) + 127) / 128 * 128 +
+                     (size_t)p->rows_per_cta * n * sizeof(float2) + 16;
+    if (n % 2 != 0 || p->smem_staged > 220 * 1024 || n * p->rows_per_cta < 1024) p->kernel_staged = nullptr;
   } else {
     int rem = n, np = 0;
     const int cand[] = {8, 4, 2, 5, 3};
@@ -149,6 +158,16 @@ FftPlan* fft_plan_create(int n, int dir) {
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   }
   p->max_ctas = per_sm * sm_count();
+  if (p->kernel_staged) {
+    int ps = 0;
+    if (cudaFuncSetAttribute((const void*)p->kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_staged) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)p->kernel_staged, p->threads, p->smem_staged) != cudaSuccess || ps < 1) {
+      cudaGetLastError();
+      p->kernel_staged = nullptr;
+    } else {
+      p->max_ctas_staged = ps * sm_count();
+    }
+  }
   char buf[256];
   snprintf(buf, sizeof buf, "fft n=%d dir=%d kind=%s radices=%d,%d,%d,%d rows/cta=%d threads=%d smem=%zu ctas/sm=%d", n,
            p->dir, p->kind == 0 ? "fixed" : (p->kind == 1 ? "generic" : "naive"), p->radix[0], p->radix[1], p->radix[2],
@@ -181,8 +200,16 @@ int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, con
     p->kernel<<<grid, 128, 0, stream>>>(a);
   } else {
     const long ngroups = (nrows + p->rows_per_cta - 1) / p->rows_per_cta;
-    const int grid = (int)std::min<long>(ngroups, p->max_ctas);
-    p->kernel<<<grid, p->threads, p->smem, stream>>>(a);
+    // bulk copies need 16-byte aligned sources; a few groups per CTA to have something to overlap
+    const bool staged = p->kernel_staged && (((uintptr_t)d_in & 15) == 0) && ngroups >= 2L * p->max_ctas_staged &&
+                        !getenv("GRCUDA_FFT_NO_TMA");
+    if (staged) {
+      const int grid = (int)std::min<long>(ngroups, p->max_ctas_staged);
+      p->kernel_staged<<<grid, p->threads, p->smem_staged, stream>>>(a);
+    } else {
+      const int grid = (int)std::min<long>(ngroups, p->max_ctas);
+      p->kernel<<<grid, p->threads, p->smem, stream>>>(a);
+    }
   }
   GRB_LAUNCH_CHECK();
   return GRCUDA_OK;

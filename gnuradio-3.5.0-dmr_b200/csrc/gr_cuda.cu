@@ -840,13 +840,11 @@ struct grcuda_mm : PlanBase {
     a.order = order; a.mmse_eff = tabs.mmse_eff;
     a.debug = 0;
     if (const char* e = getenv("GRCUDA_MM_DEBUG")) a.debug = atoi(e);
-    // look-ahead ring depth in rows: ~250 rows is >= 50 symbols up to 5 samples/symbol (several HBM round
+    // look-ahead ring depth in rows: ~120 rows is >= 24 symbols up to 5 samples/symbol (several HBM round
     // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
     const int grid = (nchan + MMW_CH - 1) / MMW_CH;
     if (max_omega <= 5.0f) {
-      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)mm_ws_smem_bytes(256)));
-      mm_ws_kernel<256><<<grid, MMW_THREADS, mm_ws_smem_bytes(256), s>>>(a);
+      mm_ws_kernel<128><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);  // 47 KB: co-resides with the front kernels
     } else {
       GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)mm_ws_smem_bytes(512)));

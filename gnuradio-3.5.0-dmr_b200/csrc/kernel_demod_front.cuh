@@ -47,7 +47,7 @@ struct DemodFrontArgs {
 };
 
 template <int RHO, int QM>
-__global__ void __launch_bounds__(DF_THREADS, 2) demod_front_kernel(const DemodFrontArgs a) {
+__global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   extern __shared__ __align__(16) float df_smem[];  // taps [4][DF_MAXB*4], atan table [260], d tile [drows][32]
   constexpr int DELTA_B = RHO > 0 ? 1 : 0;                 // class B (r >= RHO) starts one union block later
   const int q = a.q;

@@ -204,14 +204,15 @@ __global__ void __launch_bounds__(128) pfb_fir_kernel(const PfbFirArgs a) {
 
 // Same filter, sample windows staged through shared memory by the bulk copy engine (TMA).
 // A CTA owns 256 neighbouring columns x rows_per_cta output rows.  The 2 KB row segments of its
-// column tile arrive in stages of 32 rows (64 KB) through cp.async.bulk; three stages (192 KB) are
+// column tile arrive in stages of 16 rows (32 KB) through cp.async.bulk; four stages (128 KB) are
 // in flight per SM whatever the register allocation, which is what a 16 B/sample stream with
 // ~1 us of HBM latency needs (the register-window kernel above has 16 warps x 8 loads x 256 B =
-// 32 KB in flight per SM and stops at a third of the HBM rate).  Thread = column: one LDS.64 per row
+// 32 KB in flight per SM and stops at a third of the HBM rate).  128 KB leaves room on the SM for a
+// CTA of the clock-recovery kernel of the previous block, which runs concurrently.  Thread = column: one LDS.64 per row
 // (conflict free), TT FFMA pairs on the register window, one coalesced store.
 #define PFT_COLS 256
-#define PFT_SR 32
-#define PFT_NST 3
+#define PFT_SR 16
+#define PFT_NST 4
 static inline size_t pfb_fir_tma_smem() { return (size_t)PFT_NST * PFT_SR * PFT_COLS * sizeof(float2) + 64; }
 
 template <int TT>
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(PFT_COLS) pfb_fir_tma_kernel(const PfbFirArgs 
     mbar_init_fence();
   }
   __syncthreads();
-  auto issue = [&](int k) {  // warp 0: the 32 row segments of stage k
+  auto issue = [&](int k) {  // warp 0: the PFT_SR row segments of stage k
     const int i0 = k * PFT_SR;
     const int nr = min(PFT_SR, nseq - i0);
     uint64_t* bar = full + (k % PFT_NST);

@@ -111,6 +111,10 @@ class DmrChain:
         _l.check(self.L.grcuda_dmr_chain_process_device(self.h, C.c_void_p(ptr), int(nrows),
                                                         _sp(stream)))
 
+    def join(self, stream=None):
+        """Makes `stream` wait for the tails (M&M + slicer + correlator) queued so far on the chain's own stream."""
+        _l.check(self.L.grcuda_dmr_chain_join(self.h, _sp(stream)))
+
     def process_front_device(self, d_in, nrows, stream=None):
         ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
         _l.check(self.L.grcuda_dmr_chain_process_front_device(self.h, C.c_void_p(ptr), int(nrows),

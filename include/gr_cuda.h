@@ -274,6 +274,11 @@ int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d
  * block, import_state()s its left neighbour's state, then runs tail. */
 int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream);
 int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream);
+/* process_device runs the front on `stream` and the tail on the chain's own stream, so that the tail
+ * of block b overlaps the front of block b+1 (GRCUDA_CHAIN_NO_OVERLAP=1 in the environment puts both
+ * on `stream`).  join() makes `stream` wait for every tail queued so far: call it before timing or
+ * before consuming result_get() pointers on that stream.  read_hits() synchronises by itself. */
+int grcuda_dmr_chain_join(grcuda_dmr_chain* h, void* stream);
 /* same through host memory: pinned double-buffered staging (sub-blocks: H2D of i+1 overlaps compute
  * of i); sync hits of all sub-blocks accumulate for read_hits */
 int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in, int nrows);

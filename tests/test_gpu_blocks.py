@@ -306,6 +306,35 @@ def test_fft_sizes_directions_shift(B, orc, N):
                 assert relerr(y, orc.fft_vcc(N, fwd, win, shift, x)) < 5e-6, (N, fwd, shift, win is not None)
 
 
+@pytest.mark.parametrize("N,nvec", [(8000, 700), (4096, 1500), (160, 40000), (400, 20000), (2000, 3000)])
+def test_fft_many_rows_staged_path(B, N, nvec):
+    """Enough rows for the persistent, bulk-copy (TMA) double-buffered variant of the FFT kernel (it is only
+    chosen when every CTA gets several row groups): unstaged and staged paths must agree with the float64 DFT,
+    with a ragged last group, a window and both shifts."""
+    import torch
+    rng = np.random.default_rng(N + 1)
+    x = crandn(rng, N * nvec).reshape(nvec, N)
+    w = rng.uniform(0.1, 1, N).astype(np.float32)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty_like(d_in)
+    for fwd, shift, win in ((True, False, None), (True, True, w), (False, True, None)):
+        blk = B.fft_vcc(N, fwd, win if win is not None else [], shift)
+        blk.work_device(nvec, d_in, d_out)
+        torch.cuda.synchronize()
+        y = d_out.cpu().numpy()
+        xs = x.astype(np.complex128)
+        if win is not None:
+            xs = xs * w
+        elif (not fwd) and shift:
+            xs = np.roll(xs, -(N // 2), axis=1)       # gr_fft_vcc_fftw.cc:74-79: dst[i] = in[(i + floor(N/2)) % N]
+        ref = np.fft.fft(xs, axis=1) if fwd else np.fft.ifft(xs, axis=1) * N
+        if fwd and shift:
+            ref = np.roll(ref, N - int(np.ceil(N / 2.0)), axis=1)   # :89-93
+        for r in (0, 1, nvec // 2, nvec - 2, nvec - 1):
+            assert relerr(y[r], ref[r]) < 5e-6, (N, fwd, shift, r)
+        assert relerr(y, ref) < 5e-6
+
+
 def test_fft_vcc_contract(B):
     with pytest.raises(IndexError):
         B.fft_vcc(0, True, [], False)              # std::out_of_range (gri_fft.cc:104-105)
