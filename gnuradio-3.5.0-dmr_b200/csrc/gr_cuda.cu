@@ -208,8 +208,8 @@ struct grcuda_fir_ccf : PlanBase {
 extern "C" {
 
 grcuda_fir_ccf* grcuda_fir_filter_ccf_create(int decimation, const float* taps, int ntaps) {
-  if (!device_ok()) return nullptr;
   if (decimation < 1 || ntaps < 0) { set_error(GRCUDA_EINVAL, "fir_filter_ccf: bad decimation/ntaps"); return nullptr; }
+  if (!device_ok()) return nullptr;
   grcuda_fir_ccf* h = new grcuda_fir_ccf;
   h->core.decim = decimation;
   if (h->base_init() || h->set_now(std::vector<float>(taps, taps + ntaps))) { delete h; return nullptr; }
@@ -280,8 +280,8 @@ extern "C" {
 
 grcuda_fxlat* grcuda_freq_xlating_fir_filter_ccf_create(int decimation, const float* taps, int ntaps,
                                                        double center_freq, double sampling_freq) {
-  if (!device_ok()) return nullptr;
   if (decimation < 1 || ntaps < 0) { set_error(GRCUDA_EINVAL, "freq_xlating_fir_filter_ccf: bad arguments"); return nullptr; }
+  if (!device_ok()) return nullptr;
   grcuda_fxlat* h = new grcuda_fxlat;
   h->core.decim = decimation;
   h->proto.assign(taps, taps + ntaps);
@@ -402,11 +402,11 @@ struct grcuda_fir_fff : PlanBase {
 extern "C" {
 
 grcuda_fir_fff* grcuda_fir_filter_fff_create(int decimation, const float* taps, int ntaps, int order) {
-  if (!device_ok()) return nullptr;
   if (decimation < 1 || ntaps < 0 || (order != GRCUDA_ORDER_GENERIC && order != GRCUDA_ORDER_SSE)) {
     set_error(GRCUDA_EINVAL, "fir_filter_fff: bad arguments");
     return nullptr;
   }
+  if (!device_ok()) return nullptr;
   grcuda_fir_fff* h = new grcuda_fir_fff;
   h->decim = decimation;
   h->order = order;
@@ -578,7 +578,7 @@ struct grcuda_pfb : PlanBase {
 extern "C" {
 
 grcuda_pfb* grcuda_pfb_channelizer_ccf_create(unsigned numchans, const float* taps, int ntaps, float oversample_rate) {
-  if (!device_ok()) return nullptr;
+  // argument errors first: they are reported identically with or without a device
   if (numchans < 1 || ntaps < 0 || !(oversample_rate > 0)) { set_error(GRCUDA_EINVAL, "pfb_channelizer_ccf: bad arguments"); return nullptr; }
   double intp = 0;
   const double fltp = modf(numchans / oversample_rate, &intp);  // :56-60
@@ -586,6 +586,7 @@ grcuda_pfb* grcuda_pfb_channelizer_ccf_create(unsigned numchans, const float* ta
     set_error(GRCUDA_EINVAL, "gr_pfb_channelizer: oversample rate must be N/i for i in [1, N]");
     return nullptr;
   }
+  if (!device_ok()) return nullptr;
   grcuda_pfb* h = new grcuda_pfb;
   h->M = numchans;
   h->os = oversample_rate;
@@ -711,8 +712,8 @@ struct grcuda_fft : PlanBase {
 extern "C" {
 
 grcuda_fft* grcuda_fft_vcc_create(int fft_size, int forward, const float* window, int nwindow, int shift) {
-  if (!device_ok()) return nullptr;
   if (fft_size <= 0) { set_error(GRCUDA_ERANGE, "gri_fftw: invalid fft_size"); return nullptr; }
+  if (!device_ok()) return nullptr;
   grcuda_fft* h = new grcuda_fft;
   h->n = fft_size;
   h->forward = forward != 0;

@@ -1,0 +1,163 @@
+"""The C++ host blocks (include/gr_b200_blocks.h: the reference's gr_block interface over libgr_cuda) driven
+like the reference's QA code drives its blocks -- vector_source -> block -> vector_sink under a small
+single-threaded scheduler (tests/cpp/block_harness.cc) -- and compared with the oracle.
+
+Not-GPU part: the header compiles with plain g++, links against libgr_cuda.so, and constructor argument
+errors surface as the reference's exception types without touching a device."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import has_cuda
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200")
+EXE = os.path.join(ROOT, "build", "block_harness")
+TOL = 1e-4   # BASELINE.json north_star: max relative error on FIR / channelizer / FFT outputs
+
+
+@pytest.fixture(scope="module")
+def harness():
+    src = os.path.join(ROOT, "tests", "cpp", "block_harness.cc")
+    deps = [src, os.path.join(ROOT, "include", "gr_b200_blocks.h"), os.path.join(ROOT, "include", "gr_b200_runtime.h"),
+            os.path.join(ROOT, "include", "gr_cuda.h")]
+    if not os.path.exists(os.path.join(PKG, "libgr_cuda.so")):
+        pytest.skip("libgr_cuda.so not built")
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), src,
+                               "-L" + PKG, "-lgr_cuda", "-Wl,-rpath," + PKG, "-o", EXE])
+    return EXE
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+def test_header_compiles_and_maps_argument_errors(harness):
+    out = subprocess.check_output([harness, "errors"], text=True)
+    got = dict(l.split() for l in out.strip().splitlines())
+    assert got == {
+        "pfb_bad_oversample": "invalid_argument",   # gr_pfb_channelizer_ccf.cc:57-60
+        "mm_omega_lt_1": "out_of_range",            # digital_clock_recovery_mm_ff.cc:58-59
+        "mm_negative_gain": "out_of_range",         # :60-61
+        "corr_code_too_long": "out_of_range",       # digital_correlate_access_code_bb.cc:54-57
+        "fft_size_zero": "out_of_range",            # gri_fft.cc:104-105
+        "io_signature": "invalid_argument",
+    }
+
+
+gpu = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+
+def run(harness, tmp_path, spec, x, out_dtype, max_noutput=1000, files=()):
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.ascontiguousarray(x).tofile(inp)
+    args = []
+    for s in spec:
+        if isinstance(s, np.ndarray):
+            f = tmp_path / ("arg%d.bin" % len(args))
+            np.ascontiguousarray(s, np.float32).tofile(f)
+            args.append(str(f))
+        else:
+            args.append(str(s))
+    subprocess.check_call([harness, "run"] + args + [str(inp), str(outp), str(max_noutput)])
+    return np.fromfile(outp, dtype=out_dtype)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_scheduler_visible_contracts(harness):
+    out = subprocess.run([harness, "contract"], text=True, capture_output=True)
+    assert out.returncode == 0 and "contract ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_fir_blocks_through_the_scheduler(harness, tmp_path, orc):
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal(20000) + 1j * rng.standard_normal(20000)).astype(np.complex64)
+    taps = rng.standard_normal(64).astype(np.float32)
+    y = run(harness, tmp_path, ["fir_ccf", 4, taps], x, np.complex64, max_noutput=777)
+    want = orc.fir_ccf(taps, 4, x)
+    assert len(y) >= len(want) - 1 and relerr(y, want[:len(y)]) < TOL
+    xf = rng.standard_normal(30000).astype(np.float32)
+    tf = rng.standard_normal(29).astype(np.float32)
+    for chunk in (1000, 333):    # the SSE summation order follows the ABSOLUTE index: chunking must not matter
+        yf = run(harness, tmp_path, ["fir_fff", 1, tf], xf, np.float32, max_noutput=chunk)
+        wf = orc.fir_fff(tf, 1, xf, order=orc.ORDER_SSE)
+        assert len(yf) == len(wf) and np.array_equal(yf, wf)
+    yx = run(harness, tmp_path, ["fxlat", 5, taps, 12500.0, 100000.0], x, np.complex64, max_noutput=512)
+    wx = orc.freq_xlating_fir_ccf(taps, 5, 12500.0, 100000.0, x)
+    wx = wx[0] if isinstance(wx, tuple) else wx
+    assert len(yx) >= len(wx) - 1 and relerr(yx, wx[:len(yx)]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+@pytest.mark.parametrize("M,T,os_rate", [(20, 6, 1.0), (160, 16, 1.0), (8, 4, 2.0)])
+def test_pfb_channelizer_block(harness, tmp_path, orc, M, T, os_rate):
+    rng = np.random.default_rng(M)
+    rows = 600
+    x = (rng.standard_normal(rows * M) + 1j * rng.standard_normal(rows * M)).astype(np.complex64)
+    taps = rng.standard_normal(M * T - 3).astype(np.float32)
+    y = run(harness, tmp_path, ["pfb", M, taps, os_rate], x, np.complex64, max_noutput=96)
+    want, _ = orc.pfb_channelizer_ccf(M, taps, x, os_rate)
+    want = want.reshape(-1)
+    n = min(len(y), len(want))
+    assert n >= len(want) - 96 * M and n > 0
+    assert relerr(y[:n], want[:n]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_fft_vcc_block(harness, tmp_path, orc):
+    rng = np.random.default_rng(5)
+    N, nvec = 4096, 40
+    x = (rng.standard_normal(N * nvec) + 1j * rng.standard_normal(N * nvec)).astype(np.complex64)
+    from grb200 import firdes
+    w = np.asarray(firdes.window(firdes.WIN_BLACKMAN_hARRIS, N), np.float32)
+    y = run(harness, tmp_path, ["fft", N, 1, w, 0], x, np.complex64, max_noutput=7)
+    assert relerr(y, orc.fft_vcc(N, True, w, False, x)) < TOL
+    y = run(harness, tmp_path, ["fft", N, 1, "-", 1], x, np.complex64, max_noutput=16)
+    assert relerr(y, orc.fft_vcc(N, True, None, True, x)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_demod_tail_blocks_bit_exact(harness, tmp_path, orc):
+    """BASELINE config 2 shape: quadrature_demod_cf -> RRC -> clock_recovery_mm_ff -> 4-level slicer ->
+    correlate_access_code_bb as separate C++ blocks, each bit exact against the oracle on the oracle's input."""
+    from grb200 import firdes, synth
+    rng = np.random.default_rng(3)
+    fs, sps = 48000.0, 10
+    sym = rng.choice([-3.0, -1.0, 1.0, 3.0], 3000)
+    up = np.repeat(sym, sps).astype(np.float32)
+    ph = np.cumsum(2 * np.pi * 648.0 * up / fs)
+    xc = np.exp(1j * ph).astype(np.complex64) + 0.01 * (rng.standard_normal(len(ph)) + 1j * rng.standard_normal(len(ph))).astype(np.complex64)
+    gain = fs / (2 * np.pi * 648.0)
+    d = run(harness, tmp_path, ["quad", repr(float(np.float32(gain)))], xc, np.float32, max_noutput=4096)
+    wd = orc.quadrature_demod_cf(np.float32(gain), xc)
+    assert np.array_equal(d, wd)
+    rrc = np.asarray(firdes.root_raised_cosine(1.0, fs, 4800.0, 0.2, 11 * sps + 1), np.float32)
+    f = run(harness, tmp_path, ["fir_fff", 1, rrc], wd, np.float32, max_noutput=3000)
+    wf = orc.fir_fff(rrc, 1, wd, order=orc.ORDER_SSE)
+    assert np.array_equal(f, wf)
+    omega, gmu = float(sps), 0.175
+    gom = 0.25 * gmu * gmu
+    m = run(harness, tmp_path, ["mm", omega, repr(gom), 0.5, gmu, 0.005], wf, np.float32, max_noutput=500)
+    wm, _ = orc.mm_work(orc.mm_new(omega, gom, 0.5, gmu, 0.005), wf, order=orc.ORDER_SSE)
+    assert len(m) > 2900 and np.array_equal(m, wm[:len(m)]) and len(m) >= len(wm) - 2
+    s = run(harness, tmp_path, ["slicer4", 0.0], wm, np.uint8, max_noutput=999)
+    ws = orc.slicer4(wm, 0.0)
+    assert np.array_equal(s, ws)
+    s2 = run(harness, tmp_path, ["slicer2"], wm, np.uint8, max_noutput=999)
+    assert np.array_equal(s2, orc.binary_slicer(wm))
+    bits = orc.unpack_k_bits_bb(2, orc.map_bb(synth.SLICER_TO_DIBIT_MAP, ws))
+    code = synth.access_code_string(synth.DMR_BS_DATA_SYNC_BITS)
+    bits[1000:1048] = np.frombuffer(code.encode(), np.uint8) & 1      # plant one sync word
+    c = run(harness, tmp_path, ["corr", code, 1], bits, np.uint8, max_noutput=640)
+    wc = orc.corr_work(orc.corr_new(code, 1), bits)
+    assert np.array_equal(c, wc) and np.any(c & 2)
