@@ -207,6 +207,7 @@ def run_ours(args):
     e0.record()
     for s in range(args.warmup, total_steps):
         step(s, total_steps - 1)
+    ring.finish()
     ch.join(stream)      # the tails run on the chain's own stream: the timed region ends when the last one has
     e1.record()
     torch.cuda.synchronize()

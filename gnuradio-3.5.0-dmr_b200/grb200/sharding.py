@@ -55,6 +55,8 @@ class RingExchanger:
             self.state_group = state_group if state_group is not None else dist.new_group()
         else:
             self.halo_group = self.state_group = None
+        self._pending = None     # the state send in flight (non-blocking: see send_state)
+        self._send_buf = None
 
     def exchange_halo(self, my_tail_rows, halo_out, step):
         """Sends the last halo rows of my block to the right neighbour and receives my left neighbour's
@@ -80,7 +82,21 @@ class RingExchanger:
         # the last block of the whole run has nobody waiting for its state
         if step == last_step and p.rank == p.world - 1:
             return
-        dist.send(state_buf, dst=p.right, group=self.state_group)
+        # Non-blocking, from a private copy: the right neighbour only posts its recv after ITS halo exchange
+        # of the next step, which in turn needs this rank to have reached the same exchange -- a blocking
+        # send here deadlocks on transports whose send waits for the matching recv (gloo; NCCL only avoids
+        # it because its sends are stream-ordered).
+        self.finish()
+        if self._send_buf is None or self._send_buf.shape != state_buf.shape or self._send_buf.device != state_buf.device:
+            self._send_buf = torch.empty_like(state_buf)
+        self._send_buf.copy_(state_buf)
+        self._pending = dist.isend(self._send_buf, dst=p.right, group=self.state_group)
+
+    def finish(self):
+        """Waits for the state send in flight (call once after the last step)."""
+        if self._pending is not None:
+            self._pending.wait()
+            self._pending = None
 
     @staticmethod
     def wait_all(works):
