@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #define GR_HD __host__ __device__ __forceinline__
 
@@ -31,39 +32,54 @@ namespace grb {
 
 // ---- gr_fast_atan2f (gnuradio-core/src/lib/general/gr_fast_atan2f.cc:125-198) ---------------
 // `table` = the reference's 257-entry arctangent table (build/generated/gr_tables.h).
+// Branch free (a warp's lanes sit in different octants: the reference's if/else tree would make the
+// warp walk every path).  Same operations on the same operands as the reference, hence the same
+// bits: every octant's result is ONE rounded addition (+-K) + (+-base) with K = pi or pi/2
+// (a - b == a + (-b) exactly), except the first octant pair, which returns +-base untouched.
+GR_HD unsigned gr_f2u(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+GR_HD float gr_u2f(unsigned u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
 GR_HD float fast_atan2f(float y, float x, const float* __restrict__ table) {
-  if (y == 0.0f && x == 0.0f) return 0.0f;  // :131-132
   const float y_abs = fabsf(y), x_abs = fabsf(x);
-  const float z = (y_abs < x_abs) ? GR_FDIV(y_abs, x_abs) : GR_FDIV(x_abs, y_abs);  // :138-141
-  float base_angle;
+  const bool ylt = y_abs < x_abs;                                                 // :138-141
+  const float z = GR_FDIV(ylt ? y_abs : x_abs, ylt ? x_abs : y_abs);
   // `z < TAN_MAP_RES` compares the float with a DOUBLE literal 0.003921569 (:32,147).  The literal lies
   // strictly between the floats 0x3b808081 and 0x3b808082, so for a float z the test is exactly
   // z < 0x3b808082 (no FP64 instruction on the device).
-  if (z < 0.00392156932502985f) {
-    base_angle = z;
-  } else {
-    // alpha = z*256 - .5 is evaluated in double and stored to float (:151); z*256 is exact and
-    // the float subtraction rounds the same exact value once, so this is bit identical.
-    float alpha = GR_FSUB(GR_FMUL(z, 256.0f), 0.5f);
-    const int index = (int)alpha;
-    alpha = GR_FSUB(alpha, (float)index);
-    const float t0 = table[index], t1 = table[index + 1];
-    base_angle = GR_FADD(t0, GR_FMUL(GR_FSUB(t1, t0), alpha));  // :155-157
-  }
-  float angle;
-  if (x_abs > y_abs) {  // :160-171
-    if (x >= 0.0f) {
-      angle = (y >= 0.0f) ? base_angle : -base_angle;
-    } else {
-      const float pi = 3.14159265358979323846f;
-      angle = (y >= 0.0f) ? GR_FSUB(pi, base_angle) : GR_FSUB(base_angle, pi);
-    }
-  } else {  // :172-186
-    const float hp = 1.57079632679489661923f;
-    if (y >= 0.0f) angle = (x >= 0.0f) ? GR_FSUB(hp, base_angle) : GR_FADD(hp, base_angle);
-    else angle = (x >= 0.0f) ? GR_FADD(-hp, base_angle) : GR_FSUB(-hp, base_angle);
-  }
-  return angle;
+  // alpha = z*256 - .5 is evaluated in double and stored to float (:151); z*256 is exact and
+  // the float subtraction rounds the same exact value once, so this is bit identical.
+  float alpha = GR_FSUB(GR_FMUL(z, 256.0f), 0.5f);
+  int index = (int)alpha;                       // z in [0, 1] -> alpha in [-0.5, 255.5] -> index in [0, 255]
+  index = index < 0 ? 0 : (index > 255 ? 255 : index);  // only NaN / garbage inputs get here out of range: stay in the table
+  alpha = GR_FSUB(alpha, (float)index);
+  const float t0 = table[index], t1 = table[index + 1];
+  const float lerp = GR_FADD(t0, GR_FMUL(GR_FSUB(t1, t0), alpha));                // :155-157
+  const float base = (z < 0.00392156932502985f) ? z : lerp;
+  // octant (:159-186):  x_abs > y_abs: x >= 0 ? (y >= 0 ? base : -base) : (y >= 0 ? pi - base : base - pi)
+  //                     else        : y >= 0 ? (x >= 0 ? hp - base : hp + base) : (x >= 0 ? -hp + base : -hp - base)
+  const bool xa = x_abs > y_abs, xp = x >= 0.0f, yp = y >= 0.0f;
+  const float K = xa ? 3.14159265358979323846f : 1.57079632679489661923f;
+  const unsigned sK = yp ? 0u : 0x80000000u;                      // sign of K: + for y >= 0
+  const bool neg_base = xa ? yp : (yp == xp);
+  const float sum = GR_FADD(gr_u2f(gr_f2u(K) ^ sK), gr_u2f(gr_f2u(base) ^ (neg_base ? 0x80000000u : 0u)));
+  const float first = gr_u2f(gr_f2u(base) ^ sK);                  // x_abs > y_abs && x >= 0: +-base itself
+  const float angle = (xa && xp) ? first : sum;
+  return (y == 0.0f && x == 0.0f) ? 0.0f : angle;                 // :131-132
 }
 
 // gr_quadrature_demod_cf::work (gr_quadrature_demod_cf.cc:56-59):

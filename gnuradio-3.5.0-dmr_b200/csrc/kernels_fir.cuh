@@ -268,21 +268,32 @@ __global__ void __launch_bounds__(PFT_COLS) pfb_fir_tma_kernel(const PfbFirArgs 
 #pragma unroll
     for (int g = 0; g < PFT_SR / TT; g++) {
       const int ig = k * PFT_SR + g * TT;
-      if (ig < nseq) {  // CTA uniform
-#pragma unroll
-        for (int s = 0; s < TT; s++) {
-          const int i = ig + s;
-          w[s] = sp[(g * TT + s) * PFT_COLS];
-          float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < TT; t++) {
-            const float2 x = w[(s - t + TT) % TT];
-            acc.x += h[t] * x.x;
-            acc.y += h[t] * x.y;
-          }
-          if (cok && i >= T - 1 && i < nseq) uc[(long)i * M] = acc;
-        }
+      float2* __restrict__ up = uc + (long)ig * M;
+      // two accumulation chains per component (even / odd taps): the 2 x TT FFMAs of a row are then
+      // 4 chains of TT/2 instead of 2 chains of TT dependent instructions
+#define PFT_ROW(s_, GUARD)                                                    \
+      {                                                                       \
+        w[s_] = sp[(g * TT + (s_)) * PFT_COLS];                               \
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);        \
+        _Pragma("unroll") for (int t = 0; t < TT; t += 2) {                   \
+          const float2 x0 = w[((s_) - t + TT) % TT];                          \
+          const float2 x1 = w[((s_) - t - 1 + 2 * TT) % TT];                  \
+          a0.x += h[t] * x0.x;                                                \
+          a0.y += h[t] * x0.y;                                                \
+          a1.x += h[t + 1] * x1.x;                                            \
+          a1.y += h[t + 1] * x1.y;                                            \
+        }                                                                     \
+        if (GUARD) *up = make_float2(a0.x + a1.x, a0.y + a1.y);               \
+        up += M;                                                              \
       }
+      if (ig >= T - 1 && ig + TT <= nseq) {  // CTA uniform: every row of the group is an output row
+#pragma unroll
+        for (int s = 0; s < TT; s++) PFT_ROW(s, cok)
+      } else if (ig < nseq) {                 // first (window fill) and last (ragged) groups
+#pragma unroll
+        for (int s = 0; s < TT; s++) PFT_ROW(s, cok && ig + s >= T - 1 && ig + s < nseq)
+      }
+#undef PFT_ROW
     }
     __syncthreads();  // every thread is done with this stage's buffer
     if (tid < 32 && k + PFT_NST < nstages) issue(k + PFT_NST);

@@ -13,7 +13,14 @@ from conftest import has_cuda
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
 
-EPS_THRESHOLD = 1e-3   # |soft symbol - threshold| below which an end-to-end dibit may differ
+# End to end (GPU channelizer + GPU tail vs all-oracle) the demod INPUTS already differ by ~1e-7 relative
+# (different summation order in the channelizer), and the M&M loop feeds hard decisions (sign of the sample)
+# back into its timing, so in noise-only stretches a 1-ulp input difference can flip a decision and shift the
+# timing phase by ~1e-2 sample until the next burst pulls both loops back.  The stated epsilon: a dibit may
+# differ only where BOTH soft symbols are within EPS_THRESHOLD of the same slicer threshold (2.5 % of the
+# +-1/+-3 level spacing), and fewer than 0.5 % of the dibits may differ at all.  (Stage isolated, i.e. on
+# identical demod input, everything is bit exact: checks (2) above.)
+EPS_THRESHOLD = 0.05
 
 
 def relerr(a, b):
@@ -118,8 +125,10 @@ def test_chain_cfg3_160_channels(orc, order_name):
         m, s, cb = oracle_tail(orc, cfg, want[:, c], oorder)
         n = min(len(soft[c]), len(m))
         diff = np.nonzero(syms[c][:n] != s[:n])[0]
+        assert len(diff) <= 0.005 * n, (c, len(diff), n)
         for i in diff:
-            assert min(abs(abs(m[i]) - 2.0), abs(m[i])) < EPS_THRESHOLD, (c, i, m[i], soft[c][i])
+            near = [t for t in (-2.0, 0.0, 2.0) if abs(m[i] - t) < EPS_THRESHOLD and abs(soft[c][i] - t) < EPS_THRESHOLD]
+            assert near, (c, i, m[i], soft[c][i])
 
 
 def test_chain_block_size_invariance_and_shard_handoff(orc):

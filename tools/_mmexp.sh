@@ -1,7 +1,10 @@
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_r1_j.json 2>/dev/null
+for e in 0 1; do
+if [ $e = 1 ]; then export GRCUDA_CHAIN_NO_OVERLAP=1; fi
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_r1_l$e.json 2>/dev/null
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_r1_j.json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], {k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()}, d["sync_hits_last_step"])
+d=json.load(open("gpurun_out/bench_r1_l$e.json"))
+print("no_overlap=$e", round(d["value"]), round(d["ms_per_step"],3), round(d["e2e"]["value"]), {k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()}, d["sync_hits_last_step"])
 PY
+done
