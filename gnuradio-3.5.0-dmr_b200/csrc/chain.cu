@@ -111,6 +111,7 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)p->omega * 1.25) + 64;
   h->max_hits = std::max<int>(4096, (int)(M * (size_t)h->max_sym / 32));
   int rc = 0;
+  rc = rc ? rc : pfb_reserve_rows(h->pfb, (long)R);  // no allocation (= device-wide sync) once blocks are flowing
   rc = rc ? rc : h->Y.reserve((h->YH + R) * M * sizeof(float2));
   if (!h->fused) rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
   rc = rc ? rc : h->Fb[0].reserve((KEEP + R) * M * sizeof(float));

@@ -1088,6 +1088,9 @@ const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
   if (order) *order = h->order;
   return h->rt_host.data();
 }
+// sizes the channelizer's intermediate once (a later growth would cudaFree = device-wide synchronisation in the
+// middle of a stream of blocks, which can deadlock against NCCL operations a peer is waiting to pair up)
+int pfb_reserve_rows(grcuda_pfb* h, long rows) { return h->d_u.reserve((size_t)rows * h->M * sizeof(float2)); }
 const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }
 float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }
 void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }

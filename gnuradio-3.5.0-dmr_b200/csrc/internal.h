@@ -23,4 +23,5 @@ const float* fir_fff_front_taps(grcuda_fir_fff* h);  // device copy of demod_fro
 // reversed taps / order / gain of the stand-alone plans (host copies)
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order);
 float quad_gain(grcuda_quad* h);
+int pfb_reserve_rows(grcuda_pfb* h, long rows);
 }  // namespace grb

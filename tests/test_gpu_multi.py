@@ -1,0 +1,26 @@
+"""Two-GPU parity of the time-sharded chain over NCCL (tools/shard_parity.py): halo exchange + loop-state ring must
+reproduce the single-chain run bit for bit.  Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ngpus() < 2, reason="needs two CUDA devices")
+def test_two_time_shards_equal_one_chain():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tools", "shard_parity.py"), "--steps", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "shard parity ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
