@@ -177,6 +177,14 @@ def run_ours(args):
     halo_in = x[: Th + halo] if world > 1 else None
     tail_rows = x[x.shape[0] - (Th + halo):] if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
+    tail_ts = torch.cuda.Stream() if world > 1 else None
+
+    def drain():
+        if world > 1:
+            with torch.cuda.stream(tail_ts):
+                ring.finish()
+            torch.cuda.current_stream().wait_stream(tail_ts)
+        ch.join(stream)
 
     def step(s, last):
         if world == 1:
@@ -186,16 +194,24 @@ def run_ours(args):
         ring.wait_all(works)
         ch.seek_async(plan.abs_start(s) - halo, stream)
         ch.process_front_device(x, halo + R, stream)                # all ranks concurrently
-        if ring.recv_state(state, s):                               # loop state of block b-1 (ring)
-            ch.import_state(state, stream)
-        ch.process_tail_device(stream)
-        ch.export_state(state, stream)
-        ring.send_state(state, s, last)
+        # The tails form ONE serial chain over all blocks of all ranks (block b's clock recovery starts from block
+        # b-1's final loop state), so they run on a side stream: this rank's main stream goes on to the next halo
+        # exchange and front while its tail waits for the left neighbour's state.
+        with torch.cuda.stream(tail_ts):
+            ts = tail_ts.cuda_stream
+            if ring.recv_state(state, s):                           # loop state of block b-1 (ring)
+                ch.import_state(state, ts)
+            ch.process_tail_device(ts)
+            ch.export_state(state, ts)
+            ring.send_state(state, s, last)
 
     total_steps = args.warmup + args.steps
     for s in range(args.warmup):
         step(s, total_steps - 1)
-    ch.join(stream)
+    if world > 1:
+        with torch.cuda.stream(tail_ts):
+            ring.prepost_recv(state, args.warmup)   # lets the neighbour's last warm-up send complete before the sync
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -207,8 +223,7 @@ def run_ours(args):
     e0.record()
     for s in range(args.warmup, total_steps):
         step(s, total_steps - 1)
-    ring.finish()
-    ch.join(stream)      # the tails run on the chain's own stream: the timed region ends when the last one has
+    drain()              # the tails run on a side stream: the timed region ends when the last one has
     e1.record()
     torch.cuda.synchronize()
     if world > 1:

@@ -141,6 +141,7 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
     return nullptr;
   }
   h->pipeline = getenv("GRCUDA_CHAIN_NO_OVERLAP") == nullptr;
+  if (h->pipeline && pfb_prefer_coresident_fft(h->pfb) != GRCUDA_OK) { delete h; return nullptr; }
   return h;
 }
 

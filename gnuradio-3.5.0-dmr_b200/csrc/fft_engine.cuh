@@ -114,8 +114,8 @@ template <int R0, int R1, int R2, int R3> struct FftFixedCfg {
 // (an 8000-point row needs 64 KB of work space and ~100 registers x 400 threads).  One stage
 // buffer only: work + stage = 131 KB, which leaves room for a CTA of the (long, latency bound)
 // clock-recovery kernel of the previous block on the same SM.
-template <int DIR, int R0, int R1, int R2, int R3, int MINB, bool STAGED>
-__global__ void __launch_bounds__(FftFixedCfg<R0, R1, R2, R3>::THREADS, MINB) fft_fixed_kernel(const FftArgs a) {
+template <int DIR, int R0, int R1, int R2, int R3, bool STAGED>
+__device__ __forceinline__ void fft_fixed_body(const FftArgs& a) {
   constexpr int N = R0 * R1 * R2 * R3;
   constexpr int NP = FftFixedCfg<R0, R1, R2, R3>::NP;
   constexpr int PADDIV = (NP > 1 && (R0 % 2 == 0)) ? R0 : 0;
@@ -176,6 +176,18 @@ __global__ void __launch_bounds__(FftFixedCfg<R0, R1, R2, R3>::THREADS, MINB) ff
       __syncthreads();  // the next group's first pass overwrites the rows read above
     }
   }
+}
+
+// Two entry points over the same body: MINB = resident CTAs per SM the register allocation must allow, or an
+// explicit register cap NREG (chosen so that a CTA co-resides with the clock-recovery kernel of the
+// previous block: 13 warps x 128 registers leave no room for it).
+template <int DIR, int R0, int R1, int R2, int R3, int MINB, bool STAGED>
+__global__ void __launch_bounds__(FftFixedCfg<R0, R1, R2, R3>::THREADS, MINB) fft_fixed_kernel(const FftArgs a) {
+  fft_fixed_body<DIR, R0, R1, R2, R3, STAGED>(a);
+}
+template <int DIR, int R0, int R1, int R2, int R3, int NREG, bool STAGED>
+__global__ void __maxnreg__(NREG) fft_fixed_kernel_r(const FftArgs a) {
+  fft_fixed_body<DIR, R0, R1, R2, R3, STAGED>(a);
 }
 
 // ---- generic plan: runtime radices, ping-pong rows, any thread count ---------------------------

@@ -30,14 +30,20 @@ struct FftPlan {
   std::string desc;
 };
 
-struct FixedEntry { int n, r0, r1, r2, r3, minb; fft_kernel_t fwd, bwd, fwd_s, bwd_s; };
+struct FixedEntry { int n, r0, r1, r2, r3, minb; fft_kernel_t fwd, bwd, fwd_s, bwd_s; int nreg; };
 #define FX(R0, R1, R2, R3, MB)                                                                       \
   { (R0) * (R1) * (R2) * (R3), R0, R1, R2, R3, MB, fft_fixed_kernel<-1, R0, R1, R2, R3, MB, false>, \
     fft_fixed_kernel<1, R0, R1, R2, R3, MB, false>, fft_fixed_kernel<-1, R0, R1, R2, R3, MB, true>, \
-    fft_fixed_kernel<1, R0, R1, R2, R3, MB, true> }
+    fft_fixed_kernel<1, R0, R1, R2, R3, MB, true>, 0 }
+// same plan with an explicit register cap instead of a launch bound
+#define FXR(R0, R1, R2, R3, NR)                                                                          \
+  { (R0) * (R1) * (R2) * (R3), R0, R1, R2, R3, 1, fft_fixed_kernel_r<-1, R0, R1, R2, R3, NR, false>,   \
+    fft_fixed_kernel_r<1, R0, R1, R2, R3, NR, false>, fft_fixed_kernel_r<-1, R0, R1, R2, R3, NR, true>, \
+    fft_fixed_kernel_r<1, R0, R1, R2, R3, NR, true>, NR }
 // For a given n the FIRST entry is the default; GRCUDA_FFT_VARIANT=<k> selects the k-th.
 static const FixedEntry kFixed[] = {
     FX(20, 20, 20, 1, 1), FX(20, 20, 20, 1, 2), FX(10, 10, 10, 8, 1), FX(10, 10, 10, 8, 2),  // 8000
+    FXR(20, 20, 20, 1, 96), FXR(20, 20, 20, 1, 104), FXR(20, 20, 20, 1, 112), FXR(20, 20, 20, 1, 88),  // 8000, variants 4..7
     FX(16, 16, 16, 1, 2), FX(16, 16, 16, 1, 3), FX(16, 16, 16, 1, 1), FX(8, 8, 8, 8, 2), FX(8, 8, 8, 8, 4),  // 4096
     FX(16, 10, 1, 1, 2), FX(16, 10, 1, 1, 3), FX(10, 4, 4, 1, 4),  // 160
     FX(2, 1, 1, 1, 4), FX(4, 1, 1, 1, 4), FX(8, 1, 1, 1, 4), FX(16, 1, 1, 1, 4), FX(5, 1, 1, 1, 4),
@@ -79,7 +85,7 @@ static int build_twiddles(FftPlan* p) {
   return GRCUDA_OK;
 }
 
-FftPlan* fft_plan_create(int n, int dir) {
+FftPlan* fft_plan_create(int n, int dir, bool coresident) {
   if (n <= 0) {
     set_error(GRCUDA_ERANGE, "gri_fftw: invalid fft_size");  // gri_fft.cc:104-105
     return nullptr;
@@ -91,11 +97,15 @@ FftPlan* fft_plan_create(int n, int dir) {
   {
     int want = 0, seen = 0;
     if (const char* v = getenv("GRCUDA_FFT_VARIANT")) want = atoi(v);
+    const bool forced = getenv("GRCUDA_FFT_VARIANT") != nullptr;
     for (const FixedEntry& e : kFixed)
       if (e.n == n) {
         if (!fe || seen == want) fe = &e;
         seen++;
       }
+    if (coresident && !forced)  // measured (profiles/): up to 88 registers x 13 warps co-reside, 96 do not
+      for (const FixedEntry& e : kFixed)
+        if (e.n == n && e.nreg > 0 && e.nreg <= 88) { fe = &e; break; }
   }
   if (n == 1) {
     p->kind = 2;  // trivial copy through the naive kernel

@@ -8,7 +8,10 @@ namespace grb {
 
 struct FftPlan;
 // dir: -1 forward, +1 backward (unnormalised).  Returns nullptr with the error set.
-FftPlan* fft_plan_create(int n, int dir);
+// coresident: prefer the register-capped build of the plan (where one exists): slower on an empty
+// machine, but its CTAs fit on an SM next to a CTA of the clock-recovery kernel, which the chain
+// runs concurrently with the next block's front.
+FftPlan* fft_plan_create(int n, int dir, bool coresident = false);
 void fft_plan_destroy(FftPlan* p);
 // rows: [nrows][n] complex.  window: n device floats or nullptr.  in_rot/out_rot: element
 // rotations implementing ifftshift on load / fftshift on store.

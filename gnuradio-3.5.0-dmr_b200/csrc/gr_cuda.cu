@@ -845,11 +845,16 @@ struct grcuda_mm : PlanBase {
     // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
     const int grid = (nchan + MMW_CH - 1) / MMW_CH;
     if (max_omega <= 5.0f) {
-      mm_ws_kernel<128><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);  // 47 KB: co-resides with the front kernels
+      // 47 KB: co-resides with the front kernels
+      if (order == GRCUDA_ORDER_SSE) mm_ws_kernel<128, GR_ORDER_SSE><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);
+      else mm_ws_kernel<128, GR_ORDER_GENERIC><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);
     } else {
-      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512, GR_ORDER_SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)mm_ws_smem_bytes(512)));
-      mm_ws_kernel<512><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
+      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512, GR_ORDER_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)mm_ws_smem_bytes(512)));
+      if (order == GRCUDA_ORDER_SSE) mm_ws_kernel<512, GR_ORDER_SSE><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
+      else mm_ws_kernel<512, GR_ORDER_GENERIC><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
     }
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
@@ -1090,6 +1095,14 @@ const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
 }
 // sizes the channelizer's intermediate once (a later growth would cudaFree = device-wide synchronisation in the
 // middle of a stream of blocks, which can deadlock against NCCL operations a peer is waiting to pair up)
+// the chain overlaps the channelizer with the previous block's clock recovery: use the FFT build that co-resides
+int pfb_prefer_coresident_fft(grcuda_pfb* h) {
+  FftPlan* p = fft_plan_create((int)h->M, +1, true);
+  if (!p) return grcuda_last_error_code();
+  fft_plan_destroy(h->fft);
+  h->fft = p;
+  return GRCUDA_OK;
+}
 int pfb_reserve_rows(grcuda_pfb* h, long rows) { return h->d_u.reserve((size_t)rows * h->M * sizeof(float2)); }
 const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }
 float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }

@@ -24,4 +24,5 @@ const float* fir_fff_front_taps(grcuda_fir_fff* h);  // device copy of demod_fro
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order);
 float quad_gain(grcuda_quad* h);
 int pfb_reserve_rows(grcuda_pfb* h, long rows);
+int pfb_prefer_coresident_fft(grcuda_pfb* h);
 }  // namespace grb

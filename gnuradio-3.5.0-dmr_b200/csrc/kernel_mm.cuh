@@ -70,7 +70,7 @@ static inline size_t mm_ws_smem_bytes(int ring) {
   return (size_t)(ring + 8) * MMW_CH * 4 + 129 * 8 * 4 + MMW_Q * MMW_CH * 4 + 3 * MMW_CH * 4 + 256;
 }
 
-template <int RING>
+template <int RING, int ORDER>
 __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
   float* ring = mmw_smem;                            // [RING + 8][64]; rows RING..RING+7 mirror rows 0..7
@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
     int clamped = clamp0 ? 1 : 0;
     bool careful = false;  // the lane's next step goes through the one-symbol path below
     const MMParams mp = a.p;
-    const int order = a.order;
+    constexpr int order = ORDER;
     const int max_out = valid ? a.max_out : 0;
+    float sl = last < 0.f ? -1.0f : 1.0f;  // slice(last_sample) (:89-93), carried so that it is off the critical chain
     const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
     while (true) {
       // ---- four symbols, committed only while nothing unusual happens ---------------------------
@@ -173,16 +174,18 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         for (int i = 0; i < 8; i++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(src + i * RP));
         // imu = (int) rint(mu * 128): the product is exact, the FFMA rounds once to nearest even
         const unsigned imu = (unsigned)__float_as_int(__fmaf_rn(mu, 128.0f, MMW_MAGIC)) & 0xffu;
-        const unsigned ta = tab_s + imu * 32u;
+        const unsigned ta = imu * 32u + tab_s;  // one IMAD
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cf[0]), "=f"(cf[1]), "=f"(cf[2]), "=f"(cf[3]) : "r"(ta));
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(cf[4]), "=f"(cf[5]), "=f"(cf[6]), "=f"(cf[7]) : "r"(ta));
         const float o = mmse8(cf, v, order);
         // mm_update (gr_math.cuh) restated for the shortest dependent chain.  fmul(+-1, x) is exact,
         // so mm_val = slice(last)*o - slice(o)*last is one of four sums, each rounded once exactly
         // like the reference's subtraction
-        const bool ln = last < 0.f, on = o < 0.f;
-        const float mm_val = ln ? (on ? __fadd_rn(-o, last) : __fsub_rn(-o, last))
-                                : (on ? __fadd_rn(o, last) : __fsub_rn(o, last));
+        // slice(last)*o is +-o exactly; slice(o)*last is +-last exactly, and x - (-y) == x + y: both
+        // candidates are computed, the sign of o picks one
+        const float so_o = __fmul_rn(sl, o);
+        const bool on = o < 0.f;
+        const float mm_val = on ? __fadd_rn(so_o, last) : __fsub_rn(so_o, last);
         float om = __fadd_rn(omega, __fmul_rn(mp.gain_omega, mm_val));
         om = __fadd_rn(mp.omega_mid, branchless_clip(__fsub_rn(om, mp.omega_mid), mp.omega_relative_limit));
         const float m2 = __fadd_rn(__fadd_rn(mu, om), __fmul_rn(mp.gain_mu, mm_val));
@@ -192,11 +195,14 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
         const float mu2 = __fsub_rn(m2, __fsub_rn(t, MMW_MAGIC));
         unsigned ob = __float_as_uint(o);
         if (ob == MMW_EMPTY) ob = 0x7fc00000u;
-        const bool plain = m2 >= 0.f && m2 < 4194304.0f;  // forward step, floor trick valid (false for NaN)
+        // forward step with the floor trick valid: 0 <= m2 < 2^22, one unsigned compare on the bit pattern
+        // (negative values, -0, NaN and Inf all have larger patterns)
+        const bool plain = __float_as_uint(m2) < 0x4a800000u;
         if (fast && ii <= fs8) {
           if (plain) {
             mmw_stq(q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP, ob);
             mu = mu2; omega = om; last = o;
+            sl = on ? -1.0f : 1.0f;
             ii += adv;
             oo++;
           } else {
@@ -230,6 +236,7 @@ __global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
           hi = max(hi, ii);
           ii += mm_update(s, mp, o);
           mu = s.mu; omega = s.omega; last = s.last_sample;
+          sl = last < 0.f ? -1.0f : 1.0f;
           if (ii < 0) { ii = 0; clamped++; }
           // the ring still holds rows >= hi - BACK (the loader never overwrites rows >= pub_ii - BACK
           // and every published position is <= hi); older rows keep coming from global memory

@@ -57,6 +57,7 @@ class RingExchanger:
             self.halo_group = self.state_group = None
         self._pending = None     # the state send in flight (non-blocking: see send_state)
         self._send_buf = None
+        self._prerecv = None     # (step, work) of a receive posted ahead of its step
 
     def exchange_halo(self, my_tail_rows, halo_out, step):
         """Sends the last halo rows of my block to the right neighbour and receives my left neighbour's
@@ -68,10 +69,23 @@ class RingExchanger:
                dist.P2POp(dist.irecv, halo_out, p.left, group=self.halo_group)]
         return dist.batch_isend_irecv(ops)
 
+    def prepost_recv(self, state_buf, step):
+        """Posts the receive of the state `step` will need without waiting for it.  Call it before a device-wide
+        synchronisation that has to outlive a step boundary (e.g. between warm-up and timed steps): the left
+        neighbour's pending send can only complete against a posted receive."""
+        p = self.plan
+        if p.world == 1 or not p.has_left_state(step) or self._prerecv is not None:
+            return
+        self._prerecv = (step, dist.irecv(state_buf, src=p.left, group=self.state_group))
+
     def recv_state(self, state_buf, step):
         p = self.plan
         if p.world == 1 or not p.has_left_state(step):
             return False
+        if self._prerecv is not None and self._prerecv[0] == step:
+            self._prerecv[1].wait()
+            self._prerecv = None
+            return True
         dist.recv(state_buf, src=p.left, group=self.state_group)
         return True
 

@@ -1,4 +1,11 @@
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/shard_parity.py > gpurun_out/shard160.log 2>&1; grep -v Warning gpurun_out/shard160.log | grep -v "^\[rank" | tail -4
-if grep -q "shard parity ok" gpurun_out/shard160.log; then
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/shard_parity.py --numchans 8000 --rows 1200 --steps 2 > gpurun_out/shard8000.log 2>&1; grep -v Warning gpurun_out/shard8000.log | grep -v "^\[rank" | tail -4
-fi
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+run() {
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_tmp$1.json 2>/dev/null
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_tmp$1.json"))
+print("$1", round(d["value"]), round(d["ms_per_step"],3), round(d["e2e"]["value"]), {k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()}, d["sync_hits_last_step"])
+PY
+}
+run overlap
+GRCUDA_CHAIN_NO_OVERLAP=1 run serial
