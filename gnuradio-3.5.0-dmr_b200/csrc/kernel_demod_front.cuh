@@ -46,6 +46,15 @@ struct DemodFrontArgs {
                          // padded): the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
 };
 
+// accumulator slot of union block j (first four blocks: the reference's "first nblocks%4 blocks go to xmm4"
+// prologue; then round robin), and whether block j is the first one to touch its slot
+__host__ __device__ constexpr int df_slot(int j, int P) { return j < 4 ? (j < P ? (P & 3) : (j & 3)) : (j & 3); }
+__host__ __device__ constexpr bool df_first(int j, int delta, int P) {
+  for (int jj = delta; jj < j; jj++)
+    if (df_slot(jj, P) == df_slot(j, P)) return false;
+  return true;
+}
+
 template <int RHO, int QM>
 __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   extern __shared__ __align__(16) float df_smem[];  // taps [4][DF_MAXB*4], atan table [260], d tile [drows][32]
@@ -81,6 +90,35 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       return make_float2(0.f, 0.f);
     };
     const long yi0 = d_row0 + r0 - ybase;                   // buffer row of the first d row of this warp
+    // interior tiles (all but the first / last row tile and a ragged last channel group): no bounds
+    // checks, one running pointer
+    if (c0 + 32 <= a.M && d_row0 - 1 >= ybase && d_row0 + drows <= ybase + yrows) {
+      const size_t M = (size_t)a.M;
+      const float2* __restrict__ p = a.y + (size_t)(yi0 - 1) * M + c;
+      float2 prev = __ldg(p);
+      p += M;
+      float* dt = dtile + r0 * 32 + lane;
+      int r = r0;
+      for (; r + 4 <= r1; r += 4) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldg(p + u * M);
+        p += 4 * M;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          dt[u * 32] = quad_demod(v[u], prev, a.gain, tab);
+          prev = v[u];
+        }
+        dt += 4 * 32;
+      }
+      for (; r < r1; r++) {
+        const float2 cur = __ldg(p);
+        p += M;
+        *dt = quad_demod(cur, prev, a.gain, tab);
+        dt += 32;
+        prev = cur;
+      }
+    } else {
     float2 prev = ld(yi0 - 1);
     int r = r0;
     for (; r + 4 <= r1; r += 4) {
@@ -103,6 +141,7 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       dtile[r * 32 + lane] = (cok && yi >= 0 && yi < yrows) ? quad_demod(cur, prev, a.gain, tab) : 0.f;
       prev = cur;
     }
+    }
   }
   __syncthreads();
 
@@ -112,13 +151,46 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
     const long a0 = tile_start + 4L * g;
     if (a0 + 3 < a.abs_row0 || a0 >= a.abs_row0 + a.nrows) continue;  // warp uniform
     float acc[4][4][4];  // [output r][slot][lane]
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int s = 0; s < 4; s++)
-#pragma unroll
-        for (int l = 0; l < 4; l++) acc[r][s][l] = 0.f;
     const float* dcol = dtile + (size_t)(4 * g) * 32 + lane;  // union block j lane l -> dcol[(4j+l)*32]
+    int j;
+    if (J >= 8) {
+      // Every slot is first touched by one of the union blocks 0..7 at a compile-time known place: that
+      // product initialises the accumulator instead of being added to zero.  0 + p and p differ only for
+      // p = -0 (the reference's accumulators are never -0), which can only change the sign of an all-zero
+      // result: the `+ 0.0f` at the end restores it.  Saves the 64 zeroings and 64 of the additions.
+#define DF_BLOCK8(j_)                                                                      \
+      {                                                                                    \
+        float x[4];                                                                        \
+        _Pragma("unroll") for (int l = 0; l < 4; l++) x[l] = dcol[(4 * (j_) + l) * 32];    \
+        _Pragma("unroll") for (int r = 0; r < 4; r++) {                                    \
+          constexpr int dummy = 0; (void)dummy;                                            \
+          const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;                                 \
+          const int nbm = (RHO > 0 && r < RHO) ? ((QM + 2) & 3) : ((QM + 1) & 3);          \
+          const int P = delta + nbm;                                                       \
+          const int al = ((r - RHO) % 4 + 4) % 4;                                          \
+          const int slot = df_slot((j_), P);                                               \
+          if ((j_) >= delta) {                                                             \
+            const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                          \
+            const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                   \
+            _Pragma("unroll") for (int l = 0; l < 4; l++) {                                \
+              const float pr = GR_FMUL(t[l], x[l]);                                        \
+              acc[r][slot][l] = df_first((j_), delta, P) ? pr : GR_FADD(acc[r][slot][l], pr); \
+            }                                                                              \
+          }                                                                                \
+        }                                                                                  \
+      }
+      DF_BLOCK8(0) DF_BLOCK8(1) DF_BLOCK8(2) DF_BLOCK8(3) DF_BLOCK8(4) DF_BLOCK8(5) DF_BLOCK8(6) DF_BLOCK8(7)
+#undef DF_BLOCK8
+      j = 8;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+          for (int l = 0; l < 4; l++) acc[r][s][l] = 0.f;
+      j = 0;
+    }
 
     // one union block for all four outputs; SLOT_OF = accumulator slot of this block (see below)
 #define DF_BLOCK(j_, SLOT_OF)                                                              \
@@ -143,11 +215,13 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
     }
     // first four union blocks: slot = (j < P) ? P&3 : j&3, all compile-time
 #define DF_SLOT_PRO(jc) (((jc) < P) ? (P & 3) : ((jc) & 3))
-    if (J > 0) DF_BLOCK(0, DF_SLOT_PRO(0))
-    if (J > 1) DF_BLOCK(1, DF_SLOT_PRO(1))
-    if (J > 2) DF_BLOCK(2, DF_SLOT_PRO(2))
-    if (J > 3) DF_BLOCK(3, DF_SLOT_PRO(3))
-    int j = 4;
+    if (j == 0) {
+      if (J > 0) DF_BLOCK(0, DF_SLOT_PRO(0))
+      if (J > 1) DF_BLOCK(1, DF_SLOT_PRO(1))
+      if (J > 2) DF_BLOCK(2, DF_SLOT_PRO(2))
+      if (J > 3) DF_BLOCK(3, DF_SLOT_PRO(3))
+      j = 4;
+    }
     for (; j + 4 <= J; j += 4) {
       DF_BLOCK(j + 0, 0)
       DF_BLOCK(j + 1, 1)
@@ -170,7 +244,7 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       for (int l = 0; l < 4; l++)
         d[l] = GR_FADD(GR_FADD(acc[r][(0 + P) & 3][l], acc[r][(1 + P) & 3][l]),
                        GR_FADD(acc[r][(3 + P) & 3][l], acc[r][(2 + P) & 3][l]));
-      const float out = GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3]));
+      const float out = GR_FADD(GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3])), 0.0f);  // (-0) + 0 = +0, else unchanged
       const long row = a0 + r - a.abs_row0;
       if (c < a.M && row >= 0 && row < a.nrows) a.f[row * a.M + c] = out;
     }

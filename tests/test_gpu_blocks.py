@@ -139,7 +139,8 @@ def test_fir_fff_batched_device_layout(B, orc):
             assert np.array_equal(got[:, c], orc.fir_fff(taps, 1, x[:, c], order=order)), c
 
 
-@pytest.mark.parametrize("ntaps", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 29, 30, 31, 32, 61, 111, 129])
+@pytest.mark.parametrize("ntaps", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
+                                   35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 61, 111, 129])
 def test_quad_demod_fir_fff_fused_bit_exact(B, orc, ntaps):
     """The fused discriminator + matched-filter kernel == quadrature_demod_cf followed by fir_filter_fff (SSE
     order), bit for bit, for every (ntaps-1) mod 4 / ((ntaps-1)/4) mod 4 instantiation, ragged channel counts,
