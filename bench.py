@@ -33,6 +33,17 @@ STAGE_BYTES = {  # algorithmic HBM bytes per input sample, per stage (DESIGN.md 
 }
 
 
+ROOFLINE_NOTES = {   # which roofline really bounds each stage (ncu evidence under profiles/)
+    "pfb_fir": "HBM stream (TMA staged)",
+    "pfb_fft": "HBM and FP32 issue (~87 instructions per point)",
+    "rrc_fir": "FP32-issue bound, not HBM bound: the reference's SSE summation order forbids FMA (separate IEEE multiply "
+               "and add per tap) and the table arctangent needs a correctly rounded division; ncu: issue active 64 %, "
+               "dram 14 % of peak; DRAM traffic = algorithmic bytes",
+    "mm_slicer": "latency bound: one sequential recursion per channel, 250 warps at single-warp instruction latency; runs "
+                 "concurrently with the next block's front",
+}
+
+
 def chain_config(max_rows, keep_bytes=False):
     import numpy as np
     from grb200 import chain, firdes
@@ -117,7 +128,7 @@ def run_reference(args):
     cfg = chain_config(args.cpu_rows)
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(6)
-    rows = args.cpu_rows
+    rows = args.cpu_rows                                   # one step = one bounded sample of the workload
     x, _ = synth.wideband_compose(rng, M, min(rows, 64), [], noise_sigma=1.0)  # white noise rows (cost is data independent)
     x = np.tile(x, rows // min(rows, 64) + 1)[: rows * M]
     kw = dict(M=M, pfb_taps=cfg.pfb_taps, quad_gain=cfg.quad_gain, rrc_taps=cfg.rrc_taps, omega=cfg.omega,
@@ -291,7 +302,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "peak_kind": peak_kind,
                 "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": None,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "avg_launch_ms": stage_ms[dom] / max(stage_ln[dom], 1), "stages": stages}
+                "avg_launch_ms": stage_ms[dom] / max(stage_ln[dom], 1), "stages": stages,
+                "note": ROOFLINE_NOTES.get(dom, "")}
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp):
         try:
@@ -306,18 +318,25 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import refharness as Rh
             if Rh.available():
-                rows_cpu = args.cpu_rows
+                rows_cpu = min(args.cpu_rows, R)
                 xs = x[halo + Th: halo + Th + rows_cpu].cpu().numpy().reshape(-1)
                 cores = os.cpu_count() or 1
-                s0, s1, nh, _ = Rh.bench_chain(M=M, pfb_taps=cfg.pfb_taps, quad_gain=cfg.quad_gain, rrc_taps=cfg.rrc_taps,
-                                               omega=cfg.omega, gain_omega=cfg.gain_omega, mu=cfg.mu, gain_mu=cfg.gain_mu,
-                                               limit=cfg.omega_relative_limit, slicer_alpha=cfg.slicer_alpha,
-                                               symbol_map=cfg.symbol_map, access_code=cfg.access_code, threshold=cfg.threshold,
-                                               x=xs, nthreads=cores, fft_fast=True)
-                cpu = {"value": rows_cpu * M / (s0 + s1) / 1e6, "unit": "MS/s", "cores": cores, "kind": "reference",
-                       "sample": "first %d rows (%.1f M samples) of the GPU workload; reference blocks (oracle/_ref) on %d host "
-                                 "threads, channelizer %.2f s + demod %.2f s; FFTW stand-in = scalar float32 FFT"
-                                 % (rows_cpu, rows_cpu * M / 1e6, cores, s0, s1), "sync_hits": nh}
+                kw = dict(M=M, pfb_taps=cfg.pfb_taps, quad_gain=cfg.quad_gain, rrc_taps=cfg.rrc_taps, omega=cfg.omega,
+                          gain_omega=cfg.gain_omega, mu=cfg.mu, gain_mu=cfg.gain_mu, limit=cfg.omega_relative_limit,
+                          slicer_alpha=cfg.slicer_alpha, symbol_map=cfg.symbol_map, access_code=cfg.access_code,
+                          threshold=cfg.threshold, x=xs, nthreads=cores, fft_fast=True)
+                # bounded sample: repeat the pass over the sample until ~cpu_seconds of CPU work have been timed
+                s0 = s1 = 0.0
+                reps = nh = 0
+                while reps < 1 or (s0 + s1 < args.cpu_seconds and reps < 64):
+                    a0, a1, nh, _ = Rh.bench_chain(**kw)
+                    s0, s1, reps = s0 + a0, s1 + a1, reps + 1
+                cpu = {"value": reps * rows_cpu * M / (s0 + s1) / 1e6, "unit": "MS/s", "cores": cores, "kind": "reference",
+                       "sample": "%d passes over the first %d rows (%.1f M samples each) of the GPU workload; the reference's own "
+                                 "blocks (oracle/_ref, SSE FIRs) on %d host threads, channelizer time-sharded and demod tail "
+                                 "channel-sharded; channelizer %.2f s + demod %.2f s; FFTW absent -> scalar float32 "
+                                 "mixed-radix FFT stand-in" % (reps, rows_cpu, rows_cpu * M / 1e6, cores, s0, s1),
+                       "sync_hits": nh}
         except Exception as e:  # the baseline must never take the bench down
             cpu = {"value": None, "unit": "MS/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
 
@@ -348,7 +367,8 @@ def main():
     ap.add_argument("--rows", type=int, default=12500, help="channel-rate rows per step per GPU (12500 = 1 s of signal)")
     ap.add_argument("--active", type=int, default=800, help="channels carrying DMR bursts (10 % occupancy)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the CPU baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of one pass of the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work to time for the baseline beside the GPU number")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
