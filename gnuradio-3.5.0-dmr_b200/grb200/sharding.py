@@ -74,7 +74,9 @@ class RingExchanger:
         synchronisation that has to outlive a step boundary (e.g. between warm-up and timed steps): the left
         neighbour's pending send can only complete against a posted receive."""
         p = self.plan
-        if p.world == 1 or not p.has_left_state(step) or self._prerecv is not None:
+        # Only rank 0's state comes from the PREVIOUS step (the last rank's block); every other rank's left
+        # neighbour produces it during `step` itself, so a receive posted ahead would outlive the synchronisation.
+        if p.world == 1 or p.rank != 0 or not p.has_left_state(step) or self._prerecv is not None:
             return
         self._prerecv = (step, dist.irecv(state_buf, src=p.left, group=self.state_group))
 
