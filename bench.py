@@ -365,6 +365,18 @@ def run_ours(args):
     return 0
 
 
+def _watchdog(seconds):
+    """A multi-rank run that stops making progress must fail loudly instead of hanging the box."""
+    import signal
+
+    def on_alarm(signum, frame):
+        sys.stderr.write("bench.py: no result after %d s, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+    signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(seconds)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,6 +392,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the reference arm's steps are bounded samples (--cpu-rows) so that K steps finish within minutes
+    _watchdog(1500)
     args.steps_ref = max(1, args.steps)
     args.warmup_ref = max(0, args.warmup)
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -183,6 +183,7 @@ struct FirCore {
     a.in = d_in; a.out = d_out; a.nout = nout; a.decim = decim; a.ntaps = ntaps; a.J = J;
     a.rtp = d_rtp.as<float>(); a.tile_out = tile_out; a.pitch = pitch;
     a.rotate = rotate ? 1 : 0; a.theta = theta; a.out_index0 = out_index0;
+    for (int r = 0; r < FIR_R; r++) a.rot_step[r] = make_float2((float)cos(theta * r), (float)sin(theta * r));
     const long ntiles = (nout + tile_out - 1) / tile_out;
     const int grid = (int)std::min<long>(ntiles, max_ctas);
     if (ctaps) fir_decim_kernel<true><<<grid, threads, smem, s>>>(a);

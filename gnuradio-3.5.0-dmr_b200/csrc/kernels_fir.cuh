@@ -36,6 +36,7 @@ struct FirArgs {
   int rotate;
   double theta;
   long out_index0;
+  float2 rot_step[8];  // e^{j theta r}, r < FIR_R (evaluated in double on the host)
 };
 
 #define FIR_R 8
@@ -61,12 +62,25 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
     const long in_valid = (a.nout - 1) * (long)D + a.ntaps;  // number of valid input items
     __syncthreads();  // previous tile fully consumed (also orders the taps fill)
     const int span = rows_n * D;
-    for (int s = threadIdx.x; s < span; s += blockDim.x) {
-      const int n = s / D, p = s - n * D;
-      const long gi = in_base + s;
-      float2 v = make_float2(0.f, 0.f);
-      if (gi < in_valid) v = __ldg(a.in + gi);
-      xs[(size_t)p * a.pitch + fir_phys(n)] = v;
+    {
+      // Phase-split fill, global -> shared without register staging (cp.async, 8 B per element: the
+      // scatter by phase rules out a bulk copy) and without a division per element: element
+      // s = tid + k*blockDim goes to (n, p) = (s / D, s % D), advanced incrementally.
+      const int bd = blockDim.x, dn = bd / D, dp = bd - dn * D;
+      int n = threadIdx.x / D, p = threadIdx.x - n * D;
+      const float2* __restrict__ g = a.in + in_base;
+      const long nvalid = in_valid - in_base;  // elements of this tile that exist
+      const unsigned xs_s = smem_u32(xs);
+      for (int s = threadIdx.x; s < span; s += bd) {
+        const unsigned dst = xs_s + (unsigned)(p * a.pitch + fir_phys(n)) * 8u;
+        if (s < nvalid) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g + s) : "memory");
+        else xs[(size_t)p * a.pitch + fir_phys(n)] = make_float2(0.f, 0.f);
+        n += dn;
+        p += dp;
+        if (p >= D) { p -= D; n++; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
@@ -107,14 +121,14 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
         }
       }
       if (a.rotate) {
+        // closed form of the reference's running rotator (gr_rotator.h:40-50): e^{j theta (index)}.  One
+        // double-precision sincos per thread for its first output, the next seven by the host's step table
+        const double ph = a.theta * (double)(a.out_index0 + o_base + o0);
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const float2 rot0 = make_float2((float)cs, (float)sn);
 #pragma unroll
-        for (int r = 0; r < FIR_R; r++) {
-          const double ph = a.theta * (double)(a.out_index0 + o_base + o0 + r);
-          double s, c;
-          sincos(ph, &s, &c);
-          const float2 rot = make_float2((float)c, (float)s);
-          acc[r] = cmul(acc[r], rot);
-        }
+        for (int r = 0; r < FIR_R; r++) acc[r] = cmul(acc[r], cmul(rot0, a.rot_step[r]));
       }
       // 8 consecutive float2 = 64 B per thread; neighbouring threads are contiguous
       float2* o = a.out + o_base + o0;
