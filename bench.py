@@ -267,7 +267,7 @@ def run_ours(args):
     d2h = 0
     for _ in range(e2e_steps):
         ch2.process_host(host.data_ptr(), R)
-        _, nh = ch2.read_hits(1 << 16)
+        _, nh = ch2.read_hits_array(1 << 16)      # the step's result: {channel, bit index} of every sync word found
         d2h += 4 + min(nh, 1 << 16) * 16
     torch.cuda.synchronize()
     te = time.perf_counter() - t0

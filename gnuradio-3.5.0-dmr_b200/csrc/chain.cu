@@ -340,6 +340,7 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
     return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, minr, h->max_rows);
   const size_t M = h->M;
   int nsub = h->keep_bytes ? 1 : std::max(1, std::min(8, nrows / std::max(minr, 256)));
+  if (const char* e = getenv("GRCUDA_CHAIN_HOST_SUBBLOCKS")) nsub = std::max(1, std::min(atoi(e), nrows / std::max(minr, 1)));
   const int sub = (nrows + nsub - 1) / nsub;
   int rc;
   if (!h->copy_stream) {

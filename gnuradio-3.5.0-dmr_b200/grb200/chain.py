@@ -149,11 +149,20 @@ class DmrChain:
         _l.check(self.L.grcuda_dmr_chain_result_get(self.h, C.byref(r)))
         return r
 
+    HIT_DTYPE = np.dtype([("channel", np.int32), ("pad", np.int32), ("bit_index", np.int64)])   # == grcuda_hit
+
+    def read_hits_array(self, max_hits=1 << 20):
+        """Sync hits of the last block as a numpy record array (fields channel, bit_index) + the total count.
+        One D2H copy into the array's memory: no per-hit Python work."""
+        if getattr(self, "_hitbuf", None) is None or len(self._hitbuf) < max_hits:
+            self._hitbuf = np.empty(max_hits, self.HIT_DTYPE)
+        n = _l.check(self.L.grcuda_dmr_chain_read_hits(self.h, self._hitbuf.ctypes.data_as(C.c_void_p), int(max_hits)))
+        return self._hitbuf[:min(n, max_hits)], n
+
     def read_hits(self, max_hits=1 << 20):
-        buf = (_l.Hit * max_hits)()
-        n = _l.check(self.L.grcuda_dmr_chain_read_hits(self.h, buf, max_hits))
-        m = min(n, max_hits)
-        return [(buf[i].channel, buf[i].bit_index) for i in range(m)], n
+        """[(channel, absolute bit index), ...] of the last block, and the total count."""
+        a, n = self.read_hits_array(max_hits)
+        return list(zip(a["channel"].tolist(), a["bit_index"].tolist())), n
 
     # -- result readback helpers (tests / examples; use torch for big device-side consumers) --
     def _d2h(self, ptr, nbytes):
