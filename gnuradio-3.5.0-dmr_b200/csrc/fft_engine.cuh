@@ -54,6 +54,11 @@ __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j,
     if (FROM_GLOBAL) {
       // STAGED: the row was brought into shared memory by a bulk copy while the previous row was computed
       const float2* __restrict__ g = STAGED ? staged_row : a.in + row * (long)N;
+      if (a.window == nullptr && a.in_rot == 0) {  // uniform: plain rows (the channelizer's case): base + immediates
+        const float2* __restrict__ gj = g + j;
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = STAGED ? gj[r * nb] : __ldg(gj + r * nb);
+      } else
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const int i = j + r * nb;
@@ -68,8 +73,16 @@ __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j,
         v[r] = x;
       }
     } else {
+      // phys(j + r*nb) = phys(j) + r*(nb + nb/PADDIV) when PADDIV divides nb: one address register + immediates
+      if (PADDIV && (nb % (PADDIV ? PADDIV : 1)) == 0) {
+        const float2* __restrict__ sp = srow + fft_phys_c<PADDIV>(j);
+        const int st = nb + nb / (PADDIV ? PADDIV : 1);
 #pragma unroll
-      for (int r = 0; r < R; r++) v[r] = srow[fft_phys_c<PADDIV>(j + r * nb)];
+        for (int r = 0; r < R; r++) v[r] = sp[r * st];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = srow[fft_phys_c<PADDIV>(j + r * nb)];
+      }
     }
   }
   if (!FROM_GLOBAL && !TO_GLOBAL) __syncthreads();  // in-place: every read precedes every write
@@ -80,6 +93,11 @@ __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j,
     const int o0 = (j - k) * R + k;
     if (TO_GLOBAL) {
       float2* __restrict__ g = a.out + row * (long)N;
+      if (a.out_rot == 0) {  // uniform
+        float2* __restrict__ go = g + o0;
+#pragma unroll
+        for (int r = 0; r < R; r++) go[r * Ns] = v[r];
+      } else
 #pragma unroll
       for (int r = 0; r < R; r++) {
         int o = o0 + r * Ns + a.out_rot;
@@ -87,8 +105,15 @@ __device__ __forceinline__ void fft_pass(const FftArgs& a, int N, int Ns, int j,
         g[o] = v[r];
       }
     } else {
+      if (PADDIV && (Ns % (PADDIV ? PADDIV : 1)) == 0) {  // same strength reduction on the way out
+        float2* __restrict__ sp = srow + fft_phys_c<PADDIV>(o0);
+        const int st = Ns + Ns / (PADDIV ? PADDIV : 1);
 #pragma unroll
-      for (int r = 0; r < R; r++) srow[fft_phys_c<PADDIV>(o0 + r * Ns)] = v[r];
+        for (int r = 0; r < R; r++) sp[r * st] = v[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) srow[fft_phys_c<PADDIV>(o0 + r * Ns)] = v[r];
+      }
     }
   }
   if (!TO_GLOBAL) __syncthreads();

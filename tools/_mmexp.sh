@@ -1,5 +1,17 @@
-timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_r1_n2b.json 2> gpurun_out/bench_r1_n2b.err; grep '^{' gpurun_out/bench_r1_n2b.json | python -c "
+timeout 600 python -m pytest tests/test_gpu_blocks.py -m gpu -q -x -k "fft or pfb" 2>&1 | tail -2
+run() {
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_tmp$1.json 2>/dev/null
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_tmp$1.json"))
+print("$1", round(d["value"]), round(d["ms_per_step"],3), round(d["e2e"]["value"]), {k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()}, d["sync_hits_last_step"])
+PY
+}
+run overlap
+GRCUDA_CHAIN_NO_OVERLAP=1 run serial
+timeout 200 python tools/bench_blocks.py 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print(d['n_gpus'], round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), {k: round(v['ms_per_step'],3) for k,v in d['roofline']['stages'].items()}, d['sync_hits_last_step'])
-"; grep -v Warning gpurun_out/bench_r1_n2b.err | tail -3
+for k,v in d.items():
+    if isinstance(v,dict): print(k, {a: round(b,3) for a,b in v.items()})
+"
