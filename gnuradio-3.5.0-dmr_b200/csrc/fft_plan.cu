@@ -103,9 +103,12 @@ FftPlan* fft_plan_create(int n, int dir, bool coresident) {
         if (!fe || seen == want) fe = &e;
         seen++;
       }
-    if (coresident && !forced)  // measured (profiles/): up to 88 registers x 13 warps co-reside, 96 do not
+    if (coresident && !forced) {  // measured (profiles/): next to the 48-register tail kernel, 13 warps x 104 registers
+      const FixedEntry* best = nullptr;  // co-reside and 112 do not
       for (const FixedEntry& e : kFixed)
-        if (e.n == n && e.nreg > 0 && e.nreg <= 88) { fe = &e; break; }
+        if (e.n == n && e.nreg > 0 && e.nreg <= 104 && (!best || e.nreg > best->nreg)) best = &e;
+      if (best) fe = best;
+    }
   }
   if (n == 1) {
     p->kind = 2;  // trivial copy through the naive kernel

@@ -70,8 +70,9 @@ static inline size_t mm_ws_smem_bytes(int ring) {
   return (size_t)(ring + 8) * MMW_CH * 4 + 129 * 8 * 4 + MMW_Q * MMW_CH * 4 + 3 * MMW_CH * 4 + 256;
 }
 
+// 48 registers: 6 warps x 48 leave room on the SM for the big-tile front kernels this kernel runs next to
 template <int RING, int ORDER>
-__global__ void __launch_bounds__(MMW_THREADS) mm_ws_kernel(const MMArgs a) {
+__global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
   float* ring = mmw_smem;                            // [RING + 8][64]; rows RING..RING+7 mirror rows 0..7
   float* tab = ring + (RING + 8) * MMW_CH;           // [129][8] interpolator coefficients
