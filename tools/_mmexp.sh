@@ -1,9 +1,17 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py > gpurun_out/bench_r1_v7.json 2> gpurun_out/bench_r1_v7.err; tail -2 gpurun_out/bench_r1_v7.err
+timeout 600 python -m pytest tests/test_gpu_blocks.py -m gpu -q -x -k "fft or pfb" 2>&1 | tail -2
+run() {
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_tmp$1.json 2>/dev/null
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_r1_v7.json"))
-print(round(d["value"]), round(d["ms_per_step"],3), round(d["e2e"]["value"]), d["gpu_launches"], round(d["cpu_baseline"]["value"],1), d["cpu_baseline"]["cores"], d["clocks"], d["roofline"]["kernel"], round(d["roofline"]["frac"],3), d["roofline"]["traffic"])
-print({k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()})
+d=json.load(open("gpurun_out/bench_tmp$1.json"))
+print("$1", round(d["value"]), round(d["ms_per_step"],3), {k: round(v["ms_per_step"],3) for k,v in d["roofline"]["stages"].items()}, d["sync_hits_last_step"])
 PY
+}
+run overlap
+GRCUDA_CHAIN_NO_OVERLAP=1 run serial
+timeout 200 python tools/bench_blocks.py 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for k,v in d.items():
+    if isinstance(v,dict) and 'fft' in k: print(k, {a: round(b,3) for a,b in v.items()})
+"
