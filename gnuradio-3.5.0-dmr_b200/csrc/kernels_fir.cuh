@@ -98,22 +98,19 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
 #pragma unroll
           for (int u = 0; u < FIR_R; u++) {
             // tap q = q0+u multiplies window slot (u + r) mod R for output r
+            // packed FP32 (FFMA2): one instruction updates the real and the imaginary accumulator
             if (CTAPS) {
               const float2 t = reinterpret_cast<const float2*>(taps_s)[p * J + q0 + u];
 #pragma unroll
               for (int r = 0; r < FIR_R; r++) {
                 const float2 x = w[(u + r) % FIR_R];
-                acc[r].x += t.x * x.x - t.y * x.y;
-                acc[r].y += t.x * x.y + t.y * x.x;
+                // (t.x + j t.y)(x.x + j x.y) = t.x * (x.x, x.y) + t.y * (-x.y, x.x)
+                acc[r] = cfma(make_float2(-x.y, x.x), t.y, cfma(x, t.x, acc[r]));
               }
             } else {
               const float t = taps_s[p * J + q0 + u];
 #pragma unroll
-              for (int r = 0; r < FIR_R; r++) {
-                const float2 x = w[(u + r) % FIR_R];
-                acc[r].x += t * x.x;
-                acc[r].y += t * x.y;
-              }
+              for (int r = 0; r < FIR_R; r++) acc[r] = cfma(w[(u + r) % FIR_R], t, acc[r]);
             }
             // slot u (holding xp[o0+q0+u]) is dead now: refill with xp[o0 + q0 + u + R]
             w[u] = xrow[fir_phys(o0 + q0 + u + FIR_R)];
