@@ -45,7 +45,7 @@ __device__ __forceinline__ int fir_phys(int n) { return n + (n >> 3); }
 
 template <bool CTAPS>
 __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
-  extern __shared__ float2 fir_smem[];
+  extern __shared__ __align__(16) float2 fir_smem[];
   const int D = a.decim, J = a.J;
   float2* xs = fir_smem;                                   // [D][pitch]
   float* taps_s = reinterpret_cast<float*>(xs + (size_t)D * a.pitch);  // [D][J] (x2 if complex)
@@ -71,6 +71,18 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
       const float2* __restrict__ g = a.in + in_base;
       const long nvalid = in_valid - in_base;  // elements of this tile that exist
       const unsigned xs_s = smem_u32(xs);
+      if (dp == 0 && (dn & 7) == 0 && (long)span <= nvalid) {
+        // common case (D divides the block size, interior tile): the phase is fixed per thread and
+        // n advances by a multiple of 8, so the padded address advances by a constant
+        unsigned dst = xs_s + (unsigned)(p * a.pitch + fir_phys(n)) * 8u;
+        const unsigned dstep = (unsigned)(dn + (dn >> 3)) * 8u;
+        const float2* __restrict__ src = g + threadIdx.x;
+        for (int s = threadIdx.x; s < span; s += bd) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+          dst += dstep;
+          src += bd;
+        }
+      } else
       for (int s = threadIdx.x; s < span; s += bd) {
         const unsigned dst = xs_s + (unsigned)(p * a.pitch + fir_phys(n)) * 8u;
         if (s < nvalid) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g + s) : "memory");
@@ -90,17 +102,26 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
     for (int r = 0; r < FIR_R; r++) acc[r] = make_float2(0.f, 0.f);
     if (o0 < tile_n) {
       for (int p = 0; p < D; p++) {
-        const float2* xrow = xs + (size_t)p * a.pitch;
+        // o0 and q0 are multiples of 8 = FIR_R, so phys(o0 + q0 + u) = 9*(o0 + q0)/8 + u: one running
+        // pointer per phase row and compile-time offsets u
+        const float2* xw = xs + (size_t)p * a.pitch + fir_phys(o0);
         float2 w[FIR_R];  // sliding window: w[r] = xp[p][o0 + q + r]
 #pragma unroll
-        for (int r = 0; r < FIR_R; r++) w[r] = xrow[fir_phys(o0 + r)];
-        for (int q0 = 0; q0 < J; q0 += FIR_R) {
+        for (int r = 0; r < FIR_R; r++) w[r] = xw[r];
+        const float* tq = taps_s + (size_t)p * J * (CTAPS ? 2 : 1);
+        for (int q0 = 0; q0 < J; q0 += FIR_R, xw += FIR_R + 1, tq += FIR_R * (CTAPS ? 2 : 1)) {
+          float tv[FIR_R * (CTAPS ? 2 : 1)];  // the 8 taps of this group: two (four) LDS.128
+#pragma unroll
+          for (int v4 = 0; v4 < FIR_R * (CTAPS ? 2 : 1) / 4; v4++) {
+            const float4 t4 = reinterpret_cast<const float4*>(tq)[v4];
+            tv[4 * v4] = t4.x; tv[4 * v4 + 1] = t4.y; tv[4 * v4 + 2] = t4.z; tv[4 * v4 + 3] = t4.w;
+          }
 #pragma unroll
           for (int u = 0; u < FIR_R; u++) {
             // tap q = q0+u multiplies window slot (u + r) mod R for output r
             // packed FP32 (FFMA2): one instruction updates the real and the imaginary accumulator
             if (CTAPS) {
-              const float2 t = reinterpret_cast<const float2*>(taps_s)[p * J + q0 + u];
+              const float2 t = make_float2(tv[2 * u], tv[2 * u + 1]);
 #pragma unroll
               for (int r = 0; r < FIR_R; r++) {
                 const float2 x = w[(u + r) % FIR_R];
@@ -108,12 +129,12 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirArgs a) {
                 acc[r] = cfma(make_float2(-x.y, x.x), t.y, cfma(x, t.x, acc[r]));
               }
             } else {
-              const float t = taps_s[p * J + q0 + u];
+              const float t = tv[u];
 #pragma unroll
               for (int r = 0; r < FIR_R; r++) acc[r] = cfma(w[(u + r) % FIR_R], t, acc[r]);
             }
             // slot u (holding xp[o0+q0+u]) is dead now: refill with xp[o0 + q0 + u + R]
-            w[u] = xrow[fir_phys(o0 + q0 + u + FIR_R)];
+            w[u] = xw[FIR_R + 1 + u];
           }
         }
       }
