@@ -46,6 +46,24 @@ struct DemodFrontArgs {
                          // padded): the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
 };
 
+// Packed FP32 (Blackwell FMUL2 / FADD2): two independent IEEE roundings per instruction, so the results are
+// the reference's bits.  Only used where ptxas cannot contract: a packed multiply feeding SCALAR adds, and packed
+// adds of accumulators (ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false).
+__device__ __forceinline__ void df_mul2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+  unsigned long long a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+__device__ __forceinline__ void df_add2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+  unsigned long long a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+
 // accumulator slot of union block j (first four blocks: the reference's "first nblocks%4 blocks go to xmm4"
 // prologue; then round robin), and whether block j is the first one to touch its slot
 __host__ __device__ constexpr int df_slot(int j, int P) { return j < 4 ? (j < P ? (P & 3) : (j & 3)) : (j & 3); }
@@ -172,10 +190,11 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
           if ((j_) >= delta) {                                                             \
             const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                          \
             const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                   \
-            _Pragma("unroll") for (int l = 0; l < 4; l++) {                                \
-              const float pr = GR_FMUL(t[l], x[l]);                                        \
-              acc[r][slot][l] = df_first((j_), delta, P) ? pr : GR_FADD(acc[r][slot][l], pr); \
-            }                                                                              \
+            float pr[4];                                                                   \
+            df_mul2(t[0], t[1], x[0], x[1], pr[0], pr[1]);                                 \
+            df_mul2(t[2], t[3], x[2], x[3], pr[2], pr[3]);                                 \
+            _Pragma("unroll") for (int l = 0; l < 4; l++)                                  \
+              acc[r][slot][l] = df_first((j_), delta, P) ? pr[l] : GR_FADD(acc[r][slot][l], pr[l]); \
           }                                                                                \
         }                                                                                  \
       }
@@ -208,8 +227,11 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
         if ((j_) >= delta) {                                                               \
           const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                            \
           const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                     \
+          float pr[4];                                                                     \
+          df_mul2(t[0], t[1], x[0], x[1], pr[0], pr[1]);                                   \
+          df_mul2(t[2], t[3], x[2], x[3], pr[2], pr[3]);                                   \
           _Pragma("unroll") for (int l = 0; l < 4; l++)                                    \
-            acc[r][slot][l] = GR_FADD(acc[r][slot][l], GR_FMUL(t[l], x[l]));               \
+            acc[r][slot][l] = GR_FADD(acc[r][slot][l], pr[l]);                             \
         }                                                                                  \
       }                                                                                    \
     }
@@ -241,9 +263,12 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       const int P = delta + nbm;
       float d[4];
 #pragma unroll
-      for (int l = 0; l < 4; l++)
-        d[l] = GR_FADD(GR_FADD(acc[r][(0 + P) & 3][l], acc[r][(1 + P) & 3][l]),
-                       GR_FADD(acc[r][(3 + P) & 3][l], acc[r][(2 + P) & 3][l]));
+      for (int l = 0; l < 4; l += 2) {  // (acc0 + acc1) + (acc3 + acc2), two lanes per packed add
+        float s0, s1, u0, u1;
+        df_add2(acc[r][(0 + P) & 3][l], acc[r][(0 + P) & 3][l + 1], acc[r][(1 + P) & 3][l], acc[r][(1 + P) & 3][l + 1], s0, s1);
+        df_add2(acc[r][(3 + P) & 3][l], acc[r][(3 + P) & 3][l + 1], acc[r][(2 + P) & 3][l], acc[r][(2 + P) & 3][l + 1], u0, u1);
+        df_add2(s0, s1, u0, u1, d[l], d[l + 1]);
+      }
       const float out = GR_FADD(GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3])), 0.0f);  // (-0) + 0 = +0, else unchanged
       const long row = a0 + r - a.abs_row0;
       if (c < a.M && row >= 0 && row < a.nrows) a.f[row * a.M + c] = out;

@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_blocks.py -m gpu -q -x -k "fft or pfb" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_blocks.py tests/test_gpu_chain.py -m gpu -q -x -k "fused or chain" 2>&1 | tail -2
 run() {
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_tmp$1.json 2>/dev/null
 python - <<PY
@@ -9,9 +9,3 @@ PY
 }
 run overlap
 GRCUDA_CHAIN_NO_OVERLAP=1 run serial
-timeout 200 python tools/bench_blocks.py 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-for k,v in d.items():
-    if isinstance(v,dict) and 'fft' in k: print(k, {a: round(b,3) for a,b in v.items()})
-"
