@@ -840,8 +840,6 @@ struct grcuda_mm : PlanBase {
       a.slicer_levels = slicer_levels; a.slicer_alpha = slicer_alpha; a.slicer_beta = slicer_beta;
     }
     a.order = order; a.mmse_eff = tabs.mmse_eff;
-    a.debug = 0;
-    if (const char* e = getenv("GRCUDA_MM_DEBUG")) a.debug = atoi(e);
     // look-ahead ring depth in rows: ~120 rows is >= 24 symbols up to 5 samples/symbol (several HBM round
     // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
     const int grid = (nchan + MMW_CH - 1) / MMW_CH;

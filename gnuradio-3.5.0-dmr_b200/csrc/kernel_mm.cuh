@@ -271,10 +271,9 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
     const int slv = a.slicer_levels, kbits = a.corr.bits_per_symbol;
     const float s_alpha = a.slicer_alpha, s_beta = a.slicer_beta;
     const CorrParams cp = a.corr.p;
-    const bool discard = a.debug == 1;
     // window form of the correlator: valid when a match cannot raise its flag inside the same 16 bits
     const int code_len = cp.flag_bit ? 64 - (__ffsll((long long)cp.flag_bit) - 1) : 0;
-    const bool windowed = corr_on && kbits == 2 && bp == nullptr && code_len >= 16 && a.debug != 3;
+    const bool windowed = corr_on && kbits == 2 && bp == nullptr && code_len >= 16;
     const int flag_shift = 64 - code_len;
     const unsigned code_hi = (unsigned)(cp.access_code >> 32), code_lo = (unsigned)cp.access_code;
     const unsigned mask_hi = (unsigned)(cp.mask >> 32), mask_lo = (unsigned)cp.mask;
@@ -317,8 +316,7 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
         if (full) {
 #pragma unroll
           for (int i = 0; i < MMW_PB; i++) mmw_stq(slot[i], MMW_EMPTY);
-          if (discard) {
-          } else if (windowed) {
+          if (windowed) {
             // Eight dibits = 16 bits at once.  Before bit j the data register is (data << j) | (the
             // first j new bits), so all 16 mismatch counts are independent funnel shifts + popcounts;
             // a match at bit j lands in the flag register at bit (64 - len) + (15 - j) after the 16
@@ -366,7 +364,7 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
             const unsigned w0 = mmw_ldq(slot[0]);
             if (w0 != MMW_EMPTY) {
               mmw_stq(slot[0], MMW_EMPTY);
-              if (!discard) emit(__uint_as_float(w0));
+              emit(__uint_as_float(w0));
               consumed++;
             } else if (consumed == dn - 1) {
               finished = true;

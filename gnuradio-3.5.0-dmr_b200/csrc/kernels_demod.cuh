@@ -91,7 +91,6 @@ struct MMCorrFuse {
 
 struct MMArgs {
   MMCorrFuse corr;
-  int debug;             // experiments only (GRCUDA_MM_DEBUG): 1 = post warp discards, 2 = core skips the queue
   const float* in;       // [ninput][nchan], row 0 has absolute index abs_row0
   long ninput;
   long abs_row0;

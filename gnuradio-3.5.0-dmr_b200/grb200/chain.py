@@ -106,7 +106,10 @@ class DmrChain:
                                                       _sp(stream)))
 
     def process_device(self, d_in, nrows, stream=None):
-        """d_in: torch CUDA tensor (or raw pointer int) addressing history_rows() rows + nrows new rows."""
+        """d_in: torch CUDA tensor (or raw pointer int) addressing history_rows() rows + nrows new rows.
+        stream: a CUDA stream handle (e.g. torch.cuda.current_stream().cuda_stream) the front is ordered on; None =
+        the chain's own (non-blocking) stream, which is NOT ordered after work queued on other streams: d_in must
+        be complete before the call."""
         ptr = d_in if isinstance(d_in, int) else d_in.data_ptr()
         _l.check(self.L.grcuda_dmr_chain_process_device(self.h, C.c_void_p(ptr), int(nrows),
                                                         _sp(stream)))
