@@ -392,7 +392,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the reference arm's steps are bounded samples (--cpu-rows) so that K steps finish within minutes
-    _watchdog(1500)
+    _watchdog(900)
     args.steps_ref = max(1, args.steps)
     args.warmup_ref = max(0, args.warmup)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
