@@ -44,7 +44,7 @@ int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int 
   if (rc) return rc;
   DemodFrontArgs a;
   a.y = y; a.f = f; a.abs_row0 = abs_row0; a.nrows = nrows; a.M = M; a.hist = demod_front_history(ntaps);
-  a.gain = gain; a.atan_table = tabs.atan; a.ntaps = ntaps; a.tp = d_tp;
+  a.gain = gain; a.one = 1.0f; a.atan_table = tabs.atan; a.ntaps = ntaps; a.tp = d_tp;
   const int n1 = ntaps - 1, rho = n1 & 3;
   a.q = n1 >> 2;
   df_kernel_t k;

@@ -843,18 +843,14 @@ struct grcuda_mm : PlanBase {
     // look-ahead ring depth in rows: ~120 rows is >= 24 symbols up to 5 samples/symbol (several HBM round
     // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
     const int grid = (nchan + MMW_CH - 1) / MMW_CH;
-    if (max_omega <= 5.0f) {
-      // 47 KB: co-resides with the front kernels
-      if (order == GRCUDA_ORDER_SSE) mm_ws_kernel<128, GR_ORDER_SSE><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);
-      else mm_ws_kernel<128, GR_ORDER_GENERIC><<<grid, MMW_THREADS, mm_ws_smem_bytes(128), s>>>(a);
-    } else {
-      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512, GR_ORDER_SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)mm_ws_smem_bytes(512)));
-      GRB_CUDA(cudaFuncSetAttribute((const void*)mm_ws_kernel<512, GR_ORDER_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)mm_ws_smem_bytes(512)));
-      if (order == GRCUDA_ORDER_SSE) mm_ws_kernel<512, GR_ORDER_SSE><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
-      else mm_ws_kernel<512, GR_ORDER_GENERIC><<<grid, MMW_THREADS, mm_ws_smem_bytes(512), s>>>(a);
-    }
+    // 47 KB with the 128-row ring (co-resides with the front kernels), 143 KB with the 512-row one
+    typedef void (*mm_kernel_t)(const MMArgs);
+    const bool deep = max_omega > 5.0f;
+    const mm_kernel_t k = deep ? (order == GRCUDA_ORDER_SSE ? mm_ws_kernel<512, GR_ORDER_SSE> : mm_ws_kernel<512, GR_ORDER_GENERIC>)
+                               : (order == GRCUDA_ORDER_SSE ? mm_ws_kernel<128, GR_ORDER_SSE> : mm_ws_kernel<128, GR_ORDER_GENERIC>);
+    const size_t smem = mm_ws_smem_bytes(deep ? 512 : 128);
+    GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+    k<<<grid, MMW_THREADS, smem, s>>>(a);
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
   }

@@ -31,7 +31,7 @@
 namespace grb {
 
 #define DF_RT 256        // output rows per CTA tile (multiple of 4)
-#define DF_THREADS 256
+#define DF_THREADS 256  // 2 CTAs per SM at 96 registers, and still 2 next to a CTA of the clock-recovery kernel (320 x 320 tiles are 6 % faster alone, slower in the pipelined chain)
 #define DF_MAXB 34       // max aligned blocks per output window -> ntaps <= 4*DF_MAXB - 7
 
 struct DemodFrontArgs {
@@ -40,28 +40,40 @@ struct DemodFrontArgs {
   long abs_row0;
   int nrows, M, hist;
   float gain;
+  float one;             // 1.0f, opaque to the compiler (see df_acc2)
   const float* atan_table;
   int ntaps, q;          // ntaps - 1 = 4*q + rho
   const float* tp;       // [4][DF_MAXB * 4] device: tp[al][p] = rt[p - al] (reversed taps shifted by al, zero
                          // padded): the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
 };
 
-// Packed FP32 (Blackwell FMUL2 / FADD2): two independent IEEE roundings per instruction, so the results are
-// the reference's bits.  Only used where ptxas cannot contract: a packed multiply feeding SCALAR adds, and packed
-// adds of accumulators (ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false).
-__device__ __forceinline__ void df_mul2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
-  unsigned long long a, b, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+// Packed FP32 (Blackwell FMUL2 / FFMA2 / FADD2): two independent IEEE roundings per instruction, so the results are
+// the reference's bits.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, so the
+// accumulation acc + p is issued as fma(p, 1, acc) with the 1 coming from a kernel argument: p * 1 is exact, hence
+// the FFMA2 rounds the same p + acc once (also for signed zeros), and ptxas cannot fold the multiply above into it.
+typedef unsigned long long df_u64;
+__device__ __forceinline__ df_u64 df_pack(float a0, float a1) {
+  df_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a0), "f"(a1));
+  return r;
 }
-__device__ __forceinline__ void df_add2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
-  unsigned long long a, b, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+__device__ __forceinline__ void df_unpack(df_u64 v, float& a0, float& a1) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(v));
+}
+__device__ __forceinline__ df_u64 df_mul2(df_u64 a, df_u64 b) {
+  df_u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ df_u64 df_add2(df_u64 a, df_u64 b) {
+  df_u64 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+  return r;
+}
+__device__ __forceinline__ df_u64 df_acc2(df_u64 p, df_u64 ones, df_u64 acc) {  // acc + p, two lanes
+  df_u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(ones), "l"(acc));
+  return r;
 }
 
 // accumulator slot of union block j (first four blocks: the reference's "first nblocks%4 blocks go to xmm4"
@@ -164,60 +176,23 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   __syncthreads();
 
   // ---- phase 2: RRC FIR, four outputs per thread per step --------------------------------------
-  const float4* tp4 = reinterpret_cast<const float4*>(taps_s);  // tp4[al * DF_MAXB + b] = taps of block b for alignment al
+  const ulonglong2* tp2 = reinterpret_cast<const ulonglong2*>(taps_s);  // tp2[al * DF_MAXB + b] = taps of block b for alignment al
+  const df_u64 ones = df_pack(a.one, a.one);
   for (int g = warp; g < DF_RT / 4; g += DF_THREADS / 32) {
     const long a0 = tile_start + 4L * g;
     if (a0 + 3 < a.abs_row0 || a0 >= a.abs_row0 + a.nrows) continue;  // warp uniform
-    float acc[4][4][4];  // [output r][slot][lane]
+    df_u64 acc[4][4][2];  // [output r][slot][lane pair]
     const float* dcol = dtile + (size_t)(4 * g) * 32 + lane;  // union block j lane l -> dcol[(4j+l)*32]
     int j;
-    if (J >= 8) {
-      // Every slot is first touched by one of the union blocks 0..7 at a compile-time known place: that
-      // product initialises the accumulator instead of being added to zero.  0 + p and p differ only for
-      // p = -0 (the reference's accumulators are never -0), which can only change the sign of an all-zero
-      // result: the `+ 0.0f` at the end restores it.  Saves the 64 zeroings and 64 of the additions.
-#define DF_BLOCK8(j_)                                                                      \
-      {                                                                                    \
-        float x[4];                                                                        \
-        _Pragma("unroll") for (int l = 0; l < 4; l++) x[l] = dcol[(4 * (j_) + l) * 32];    \
-        _Pragma("unroll") for (int r = 0; r < 4; r++) {                                    \
-          constexpr int dummy = 0; (void)dummy;                                            \
-          const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;                                 \
-          const int nbm = (RHO > 0 && r < RHO) ? ((QM + 2) & 3) : ((QM + 1) & 3);          \
-          const int P = delta + nbm;                                                       \
-          const int al = ((r - RHO) % 4 + 4) % 4;                                          \
-          const int slot = df_slot((j_), P);                                               \
-          if ((j_) >= delta) {                                                             \
-            const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                          \
-            const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                   \
-            float pr[4];                                                                   \
-            df_mul2(t[0], t[1], x[0], x[1], pr[0], pr[1]);                                 \
-            df_mul2(t[2], t[3], x[2], x[3], pr[2], pr[3]);                                 \
-            _Pragma("unroll") for (int l = 0; l < 4; l++)                                  \
-              acc[r][slot][l] = df_first((j_), delta, P) ? pr[l] : GR_FADD(acc[r][slot][l], pr[l]); \
-          }                                                                                \
-        }                                                                                  \
-      }
-      DF_BLOCK8(0) DF_BLOCK8(1) DF_BLOCK8(2) DF_BLOCK8(3) DF_BLOCK8(4) DF_BLOCK8(5) DF_BLOCK8(6) DF_BLOCK8(7)
-#undef DF_BLOCK8
-      j = 8;
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int s = 0; s < 4; s++)
-#pragma unroll
-          for (int l = 0; l < 4; l++) acc[r][s][l] = 0.f;
-      j = 0;
-    }
-
-    // one union block for all four outputs; SLOT_OF = accumulator slot of this block (see below)
-#define DF_BLOCK(j_, SLOT_OF)                                                              \
+    // one union block for all four outputs.  SLOT_OF = accumulator slot of this block, FIRST_OF = the block is the
+    // first to touch that slot (its products initialise the accumulator); both fold to constants once the r loop
+    // is unrolled
+#define DF_BLOCK(j_, SLOT_OF, FIRST_OF)                                                    \
     {                                                                                      \
       float x[4];                                                                          \
       _Pragma("unroll") for (int l = 0; l < 4; l++) x[l] = dcol[(4 * (j_) + l) * 32];      \
+      const df_u64 x01 = df_pack(x[0], x[1]), x23 = df_pack(x[2], x[3]);                   \
       _Pragma("unroll") for (int r = 0; r < 4; r++) {                                      \
-        /* folded to constants once the r loop is unrolled */                              \
         const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;                                   \
         const int nbm = (RHO > 0 && r < RHO) ? ((QM + 2) & 3) : ((QM + 1) & 3);            \
         const int P = delta + nbm;                                                         \
@@ -225,34 +200,52 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
         const int slot = SLOT_OF;                                                          \
         (void)P;                                                                           \
         if ((j_) >= delta) {                                                               \
-          const float4 t4 = tp4[al * DF_MAXB + ((j_) - delta)];                            \
-          const float t[4] = {t4.x, t4.y, t4.z, t4.w};                                     \
-          float pr[4];                                                                     \
-          df_mul2(t[0], t[1], x[0], x[1], pr[0], pr[1]);                                   \
-          df_mul2(t[2], t[3], x[2], x[3], pr[2], pr[3]);                                   \
-          _Pragma("unroll") for (int l = 0; l < 4; l++)                                    \
-            acc[r][slot][l] = GR_FADD(acc[r][slot][l], pr[l]);                             \
+          const ulonglong2 t = tp2[al * DF_MAXB + ((j_) - delta)];                         \
+          const df_u64 p01 = df_mul2(t.x, x01), p23 = df_mul2(t.y, x23);                   \
+          if (FIRST_OF) {                                                                  \
+            acc[r][slot][0] = p01;                                                         \
+            acc[r][slot][1] = p23;                                                         \
+          } else {                                                                         \
+            acc[r][slot][0] = df_acc2(p01, ones, acc[r][slot][0]);                         \
+            acc[r][slot][1] = df_acc2(p23, ones, acc[r][slot][1]);                         \
+          }                                                                                \
         }                                                                                  \
       }                                                                                    \
+    }
+    if (J >= 8) {
+      // Every slot is first touched by one of the union blocks 0..7 at a compile-time known place: that
+      // product initialises the accumulator instead of being added to zero.  0 + p and p differ only for
+      // p = -0 (the reference's accumulators are never -0), which can only change the sign of an all-zero
+      // result: the `+ 0.0f` at the end restores it.  Saves the zeroings and 64 of the additions.
+#define DF_BLOCK8(j_) DF_BLOCK(j_, df_slot((j_), P), df_first((j_), delta, P))
+      DF_BLOCK8(0) DF_BLOCK8(1) DF_BLOCK8(2) DF_BLOCK8(3) DF_BLOCK8(4) DF_BLOCK8(5) DF_BLOCK8(6) DF_BLOCK8(7)
+#undef DF_BLOCK8
+      j = 8;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int s = 0; s < 4; s++) acc[r][s][0] = acc[r][s][1] = 0ull;
+      j = 0;
     }
     // first four union blocks: slot = (j < P) ? P&3 : j&3, all compile-time
 #define DF_SLOT_PRO(jc) (((jc) < P) ? (P & 3) : ((jc) & 3))
     if (j == 0) {
-      if (J > 0) DF_BLOCK(0, DF_SLOT_PRO(0))
-      if (J > 1) DF_BLOCK(1, DF_SLOT_PRO(1))
-      if (J > 2) DF_BLOCK(2, DF_SLOT_PRO(2))
-      if (J > 3) DF_BLOCK(3, DF_SLOT_PRO(3))
+      if (J > 0) DF_BLOCK(0, DF_SLOT_PRO(0), false)
+      if (J > 1) DF_BLOCK(1, DF_SLOT_PRO(1), false)
+      if (J > 2) DF_BLOCK(2, DF_SLOT_PRO(2), false)
+      if (J > 3) DF_BLOCK(3, DF_SLOT_PRO(3), false)
       j = 4;
     }
     for (; j + 4 <= J; j += 4) {
-      DF_BLOCK(j + 0, 0)
-      DF_BLOCK(j + 1, 1)
-      DF_BLOCK(j + 2, 2)
-      DF_BLOCK(j + 3, 3)
+      DF_BLOCK(j + 0, 0, false)
+      DF_BLOCK(j + 1, 1, false)
+      DF_BLOCK(j + 2, 2, false)
+      DF_BLOCK(j + 3, 3, false)
     }
-    if (j < J) { DF_BLOCK(j, 0) j++; }
-    if (j < J) { DF_BLOCK(j, 1) j++; }
-    if (j < J) { DF_BLOCK(j, 2) j++; }
+    if (j < J) { DF_BLOCK(j, 0, false) j++; }
+    if (j < J) { DF_BLOCK(j, 1, false) j++; }
+    if (j < J) { DF_BLOCK(j, 2, false) j++; }
 #undef DF_BLOCK
 #undef DF_SLOT_PRO
     // combine: true accumulator a lives in slot (a + P) & 3
@@ -261,15 +254,14 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;
       const int nbm = (RHO > 0 && r < RHO) ? ((QM + 2) & 3) : ((QM + 1) & 3);
       const int P = delta + nbm;
-      float d[4];
+      df_u64 d[2];  // lanes (0, 1) and (2, 3) of (acc0 + acc1) + (acc3 + acc2)
 #pragma unroll
-      for (int l = 0; l < 4; l += 2) {  // (acc0 + acc1) + (acc3 + acc2), two lanes per packed add
-        float s0, s1, u0, u1;
-        df_add2(acc[r][(0 + P) & 3][l], acc[r][(0 + P) & 3][l + 1], acc[r][(1 + P) & 3][l], acc[r][(1 + P) & 3][l + 1], s0, s1);
-        df_add2(acc[r][(3 + P) & 3][l], acc[r][(3 + P) & 3][l + 1], acc[r][(2 + P) & 3][l], acc[r][(2 + P) & 3][l + 1], u0, u1);
-        df_add2(s0, s1, u0, u1, d[l], d[l + 1]);
-      }
-      const float out = GR_FADD(GR_FADD(GR_FADD(d[0], d[2]), GR_FADD(d[1], d[3])), 0.0f);  // (-0) + 0 = +0, else unchanged
+      for (int h = 0; h < 2; h++)
+        d[h] = df_add2(df_add2(acc[r][(0 + P) & 3][h], acc[r][(1 + P) & 3][h]),
+                       df_add2(acc[r][(3 + P) & 3][h], acc[r][(2 + P) & 3][h]));
+      float e0, e1;
+      df_unpack(df_add2(d[0], d[1]), e0, e1);  // (d0 + d2, d1 + d3)
+      const float out = GR_FADD(GR_FADD(e0, e1), 0.0f);  // (-0) + 0 = +0, else unchanged
       const long row = a0 + r - a.abs_row0;
       if (c < a.M && row >= 0 && row < a.nrows) a.f[row * a.M + c] = out;
     }

@@ -9,24 +9,33 @@
 // therefore moved out of the warp that carries it.  A CTA owns 64 neighbouring channels (two
 // groups of 32, lane = channel) and six warps:
 //
-//   warps 4,5  CORE    the Mueller & Mueller recursion only, four symbols per trip.  The 8 input
-//                      samples and the interpolator taps are fetched from shared memory
-//                      speculatively, the step is computed, and a predicate (input landed, queue
-//                      slots free, ordinary forward step) decides whether the new state is
-//                      committed.  floor()/rint() are done with the 1.5*2^23 trick (one FADD/FFMA
-//                      instead of a conversion-unit round trip); the timing-error term picks one of
-//                      the four exactly equivalent sums.  Anything unusual (a backward step, the
-//                      last few symbols of a call, |mu| >= 2^22) takes a plain one-symbol path that
-//                      reads the input straight from global memory.
-//   warps 2,3  POST    takes soft symbols from a shared-memory queue, eight at a time: soft symbol
+//   warps 2,3  CORE    the Mueller & Mueller recursion only, MMW_TRIP symbols per trip, branch free.  The 8
+//                      input samples and the interpolator row are fetched from shared memory
+//                      speculatively, the step is computed, and one predicate (input landed, queue
+//                      slots free, ordinary forward step) selects whether the new state is kept; the
+//                      soft symbol of a step that is not kept is stored to a scratch word.  floor()
+//                      and rint() are done with the 1.5*2^23 trick (one FADD / FFMA instead of a
+//                      conversion-unit round trip), and the two shared-memory addresses of the NEXT
+//                      step (ring slot of row ii, interpolator row of mu) are carried as state and
+//                      derived from those two results by integer multiply-adds, so the loads of step
+//                      k+1 hang off the last addition of step k by three instructions.  The
+//                      timing-error term picks one of the four exactly equivalent sums.  Anything
+//                      unusual (a backward step, the last few symbols of a call, mu >= 2^15, more
+//                      than 2^22 rows in one call) takes a plain one-symbol path that reads the input
+//                      straight from global memory.
+//   warps 4,5  POST    takes soft symbols from a shared-memory queue, eight at a time: soft symbol
 //                      -> HBM, 4-level (or binary) slicer, dibit map, bit unpack, access-code
 //                      correlation over a 16-bit window (__popc over the 64-bit shift register at
 //                      all 16 positions at once; only the registers are carried), sync-hit list.
 //   warps 0,1  LOADER  keeps a per-lane ring of the lane's input column in shared memory filled
 //                      RING-8 rows ahead of the loop with cp.async (LDGSTS: no register staging) and
 //                      publishes how far the data has landed.  HBM latency never meets the loop.
-//                      (A core warp shares its scheduler (warp id % 4) with a loader warp and wins
-//                      the arbitration: the higher warp id goes first.)
+//   (warp id % 4 = scheduler: the core warps have theirs to themselves, loader and post share.)
+//
+// Measured (ncu source counters, profiles/README.md): ~66 instructions and ~320 cycles per symbol; the
+// interpolator rows (one per lane, 32 bytes) cost 13.6 shared-memory wavefronts per LDS.128 instead of 4.
+// A table replicated per bank group removes those conflicts but its 16-33 KB push the kernel past the
+// 48 KB at which it co-resides with the front kernels, and the kernel time did not move: not kept.
 //
 // Warps talk through shared memory only (all six are co-resident by construction, so spinning is
 // safe).  Queue slots carry their own full/empty state (a reserved NaN pattern = empty), so no
@@ -42,10 +51,13 @@ namespace grb {
 #define MMW_BACK 8            // rows kept behind the furthest position for (rare) backward steps
 #define MMW_Q 32              // soft-symbol queue depth per lane
 #define MMW_PB 8              // symbols the post warp takes per batch
+#define MMW_TRIP 8            // symbols the core warp attempts per trip (between two looks at the other warps' words)
 #define MMW_EMPTY 0x7fc0deadu // queue slot is empty (a quiet-NaN payload the arithmetic cannot produce
                               // from finite data; a colliding input NaN is re-encoded as 0x7fc00000)
 #define MMW_CH 64             // channels per CTA
 #define MMW_THREADS 192
+#define MMW_TABREP 1          // copies of the interpolator table in shared memory, one per bank group (below)
+#define MMW_TABROW (2 * MMW_TABREP * 16)  // bytes per interpolator row: [2 halves][MMW_TABREP copies][4 floats]
 #define MMW_MAGIC 12582912.0f // 1.5 * 2^23: adding it leaves round(x) / floor(x) in the low mantissa bits
 #define MMW_MAGIC_BITS 0x4b400000
 
@@ -67,27 +79,40 @@ __device__ __forceinline__ void mmw_stq(unsigned addr, unsigned v) {
 }
 
 static inline size_t mm_ws_smem_bytes(int ring) {
-  return (size_t)(ring + 8) * MMW_CH * 4 + 129 * 8 * 4 + MMW_Q * MMW_CH * 4 + 3 * MMW_CH * 4 + 256;
+  return (size_t)(ring + 8) * MMW_CH * 4 + 129 * MMW_TABROW + MMW_Q * MMW_CH * 4 + 4 * MMW_CH * 4 + 256;
 }
 
-// 48 registers: 6 warps x 48 leave room on the SM for the big-tile front kernels this kernel runs next to
+// 6 warps x 64 registers leave room on the SM for the big-tile front kernels this kernel runs next to; at 48 the
+// core loop's ten shared-memory loads per symbol were issued one at a time, each just before its use
+#define MMW_REGS 48
 template <int RING, int ORDER>
-__global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
+__global__ void __maxnreg__(MMW_REGS) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
-  float* ring = mmw_smem;                            // [RING + 8][64]; rows RING..RING+7 mirror rows 0..7
-  float* tab = ring + (RING + 8) * MMW_CH;           // [129][8] interpolator coefficients
-  unsigned* q = reinterpret_cast<unsigned*>(tab + 129 * 8);    // [MMW_Q][64]
+  // Interpolator table, [129 rows][2 halves][MMW_TABREP copies][4 floats]: a lane's LDS.128 of its row (every lane
+  // has its own mu) goes to the copy lane % MMW_TABREP, so that the eight lanes of a quarter warp spread over
+  // MMW_TABREP disjoint bank groups whatever their rows are (the plain [129][8] table cost 13.6 wavefronts per load
+  // instead of 4; 8 copies would make it exactly 4 but cost 33 KB: the kernel must stay under 48 KB to co-reside
+  // with the 128 KB tiles of the branch filter)
+  float* tab = mmw_smem;
+  float* ring = tab + 129 * (MMW_TABROW / 4);        // [RING + 8][64]; rows RING..RING+7 mirror rows 0..7
+  unsigned* q = reinterpret_cast<unsigned*>(ring + (RING + 8) * MMW_CH);    // [MMW_Q][64]
   int* pub_ii = reinterpret_cast<int*>(q + MMW_Q * MMW_CH);    // [64] core -> loader: current input position
   int* pub_filled = pub_ii + MMW_CH;                           // [64] loader -> core: rows < this have landed
   int* pub_done = pub_filled + MMW_CH;                         // [64] core -> loader/post: symbols produced + 1
-  unsigned char* smap = reinterpret_cast<unsigned char*>(pub_done + MMW_CH);  // [256] gr_map_bb table
+  int* dump = pub_done + MMW_CH;                               // [64] where the queue store of an uncommitted step lands
+  unsigned char* smap = reinterpret_cast<unsigned char*>(dump + MMW_CH);  // [256] gr_map_bb table
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int role = warp >> 1;                        // 0 loader, 1 post, 2 core
+  // warp -> scheduler is warp id % 4: the core warps (2, 3) have a scheduler each to themselves; the loader (0, 1)
+  // and post (4, 5) warps share the other two
+  const int role = warp < 2 ? 0 : warp < 4 ? 2 : 1;  // 0 loader, 1 post, 2 core
   const int cl = (warp & 1) * 32 + lane;             // channel within the CTA
   const int c = blockIdx.x * MMW_CH + cl;
   const bool valid = c < a.nchan;
-  for (int i = threadIdx.x; i < 129 * 8; i += MMW_THREADS) tab[i] = a.mmse_eff[i];
+  for (int i = threadIdx.x; i < 129 * 8 * MMW_TABREP; i += MMW_THREADS) {
+    const int rep = i % MMW_TABREP, j = (i / MMW_TABREP) & 7, row = i / (8 * MMW_TABREP);
+    tab[row * (MMW_TABROW / 4) + (j >> 2) * (MMW_TABREP * 4) + rep * 4 + (j & 3)] = a.mmse_eff[row * 8 + j];
+  }
   for (int i = threadIdx.x; i < 256; i += MMW_THREADS) smap[i] = a.corr.map[i];
   for (int i = threadIdx.x; i < MMW_Q * MMW_CH; i += MMW_THREADS) q[i] = MMW_EMPTY;
 
@@ -114,6 +139,7 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
   const float* __restrict__ col = a.in + (valid ? c : 0);
   const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(ring + cl);
   const unsigned q_lane = (unsigned)__cvta_generic_to_shared(q + cl);
+  const unsigned dump_lane = (unsigned)__cvta_generic_to_shared(dump + cl);
   constexpr unsigned RP = MMW_CH * 4;  // ring / queue row pitch in bytes
 
   if (role == 0) {
@@ -158,26 +184,39 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
     const int max_out = valid ? a.max_out : 0;
     float sl = last < 0.f ? -1.0f : 1.0f;  // slice(last_sample) (:89-93), carried so that it is off the critical chain
     const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    // The two shared-memory addresses of a step are carried as state, so that the next step's loads hang off the
+    // floor / rint of this step by three integer instructions instead of going through mu and ii:
+    //   iib = ii * 256 + cl * 4   byte offset of (row ii, this lane) in an unbounded ring; & RMASK = the ring slot
+    //   ta  = imu * MMW_TABROW + (lane % MMW_TABREP) * 16   shared-memory address of this lane's copy of the interpolator row for the CURRENT mu
+    constexpr unsigned RMASK = RING * RP - 4;
+    constexpr int FAR = 1 << 22;  // rows beyond this go through the one-symbol path (iib stays inside 31 bits)
+    const unsigned rep16 = (unsigned)(lane % MMW_TABREP) * 16u;
+    const unsigned tak = (128u * MMW_TABROW - MMW_TABROW) * (unsigned)MMW_MAGIC_BITS + rep16 + tab_s;
+    auto ta_of = [&](float m) {
+      return ((unsigned)__float_as_int(__fmaf_rn(m, 128.0f, MMW_MAGIC)) & 0xffu) * (unsigned)MMW_TABROW + rep16 + tab_s;
+    };
+    int iib = ii * 256 + cl * 4;
+    unsigned ta = ta_of(mu);
     while (true) {
-      // ---- four symbols, committed only while nothing unusual happens ---------------------------
+      // ---- MMW_TRIP symbols, committed only while nothing unusual happens ---------------------------
       // rows < pub_filled have landed; (ii <= fs8) == (ii + 8 <= pub_filled && ii < ni)
-      const int fs8 = min(mmw_ldv(pub_filled + cl), ninput - 1) - 8;
-      // the post warp empties slots in order, so a free slot oo+3 means oo..oo+3 are free
-      const bool qfree4 = mmw_ldq(q_lane + (unsigned)((oo + 3) & (MMW_Q - 1)) * RP) == MMW_EMPTY;
-      const bool fast = !careful && oo + 4 <= max_out && qfree4;
+      const int fs8 = min(min(mmw_ldv(pub_filled + cl), ninput - 1) - 8, FAR);
+      const int fs8b = fs8 * 256 + 255;  // ii <= fs8  <=>  iib <= fs8b  (cl * 4 < 256)
+      // the post warp empties slots in order, so a free slot oo+TRIP-1 means oo..oo+TRIP-1 are free
+      const bool qfree = mmw_ldq(q_lane + (unsigned)((oo + MMW_TRIP - 1) & (MMW_Q - 1)) * RP) == MMW_EMPTY;
+      const bool fast = !careful && oo + MMW_TRIP <= max_out && qfree;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < MMW_TRIP; k++) {
         // speculative fetch: any address inside the ring is readable; the predicate below says
         // whether rows ii..ii+7 of this lane's column are really the ones in these slots
-        const unsigned src = ring_lane + ((unsigned)ii & (RING - 1)) * RP;
+        const unsigned src = ring_s + ((unsigned)iib & RMASK);
         float v[8], cf[8];
+        const unsigned tad = ta;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cf[0]), "=f"(cf[1]), "=f"(cf[2]), "=f"(cf[3]) : "r"(tad));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(cf[4]), "=f"(cf[5]), "=f"(cf[6]), "=f"(cf[7]) : "r"(tad), "n"(MMW_TABREP * 16));
 #pragma unroll
         for (int i = 0; i < 8; i++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(src + i * RP));
-        // imu = (int) rint(mu * 128): the product is exact, the FFMA rounds once to nearest even
-        const unsigned imu = (unsigned)__float_as_int(__fmaf_rn(mu, 128.0f, MMW_MAGIC)) & 0xffu;
-        const unsigned ta = imu * 32u + tab_s;  // one IMAD
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cf[0]), "=f"(cf[1]), "=f"(cf[2]), "=f"(cf[3]) : "r"(ta));
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(cf[4]), "=f"(cf[5]), "=f"(cf[6]), "=f"(cf[7]) : "r"(ta));
         const float o = mmse8(cf, v, order);
         // mm_update (gr_math.cuh) restated for the shortest dependent chain.  fmul(+-1, x) is exact,
         // so mm_val = slice(last)*o - slice(o)*last is one of four sums, each rounded once exactly
@@ -190,43 +229,55 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
         float om = __fadd_rn(omega, __fmul_rn(mp.gain_omega, mm_val));
         om = __fadd_rn(mp.omega_mid, branchless_clip(__fsub_rn(om, mp.omega_mid), mp.omega_relative_limit));
         const float m2 = __fadd_rn(__fadd_rn(mu, om), __fmul_rn(mp.gain_mu, mm_val));
-        // floor(m2) by adding 1.5*2^23 rounding towards minus infinity: exact for 0 <= m2 < 2^22
-        const float t = __fadd_rd(m2, MMW_MAGIC);
-        const int adv = __float_as_int(t) - MMW_MAGIC_BITS;
-        const float mu2 = __fsub_rn(m2, __fsub_rn(t, MMW_MAGIC));
+        // floor(m2) by adding 1.5*2^23 rounding towards minus infinity, rint(m2 * 128) by the FFMA (the product is
+        // exact, the sum rounds once to nearest even): both exact for 0 <= m2 < 2^15.  The next mu is
+        // m2 - floor(m2) (exact), so the next imu = rint(mu * 128) = rint(m2 * 128) - 128 * floor(m2): the
+        // interpolator row of the next step needs neither the new mu nor a conversion
+        const unsigned tb = (unsigned)__float_as_int(__fadd_rd(m2, MMW_MAGIC));
+        const unsigned ub = (unsigned)__float_as_int(__fmaf_rn(m2, 128.0f, MMW_MAGIC));
+        // imu * ROW = ub * ROW - tb * 128 * ROW + (128 * ROW - ROW) * MMW_MAGIC_BITS (mod 2^32); no mask is needed: tan
+        // is only ever committed for a plain step, where imu is in [0, 128]
+        const unsigned tan = ub * (unsigned)MMW_TABROW + (tb * (0u - 128u * MMW_TABROW) + tak);
+        const int iibn = (int)(tb * 256u + ((unsigned)iib - 256u * (unsigned)MMW_MAGIC_BITS));  // ii + floor(m2)
+        const float mu2 = __fsub_rn(m2, __fsub_rn(__uint_as_float(tb), MMW_MAGIC));
         unsigned ob = __float_as_uint(o);
         if (ob == MMW_EMPTY) ob = 0x7fc00000u;
-        // forward step with the floor trick valid: 0 <= m2 < 2^22, one unsigned compare on the bit pattern
+        // forward step with the tricks valid: 0 <= m2 < 2^15, one unsigned compare on the bit pattern
         // (negative values, -0, NaN and Inf all have larger patterns)
-        const bool plain = __float_as_uint(m2) < 0x4a800000u;
-        if (fast && ii <= fs8) {
-          if (plain) {
-            mmw_stq(q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP, ob);
-            mu = mu2; omega = om; last = o;
-            sl = on ? -1.0f : 1.0f;
-            ii += adv;
-            oo++;
-          } else {
-            careful = true;  // nothing committed: the step is redone below
-          }
-        }
+        const bool plain = __float_as_uint(m2) < 0x47000000u;
+        // branch free commit: the state registers are selected and the queue store of an uncommitted step goes to
+        // a scratch word (a branch here costs more than the whole arithmetic of the step and splits the four
+        // symbols into basic blocks)
+        const bool ok = fast && iib <= fs8b;
+        const bool commit = ok && plain;
+        mmw_stq(commit ? q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP : dump_lane, ob);
+        mu = commit ? mu2 : mu;
+        omega = commit ? om : omega;
+        last = commit ? o : last;
+        sl = commit ? (on ? -1.0f : 1.0f) : sl;
+        iib = commit ? iibn : iib;
+        ta = commit ? tan : ta;
+        oo += commit ? 1 : 0;
+        careful = careful || (ok && !plain);  // nothing committed: the step is redone below
       }
+      ii = iib >> 8;
+      careful = careful || ii >= FAR;
       mmw_stv(pub_ii + cl, ii);
       // ---- one symbol the plain way: backward steps, the tail of a call, out-of-range mu --------
       // (the whole input is in global memory before the kernel starts; the ring is only a latency
       // optimisation, so this path depends on nobody)
       const bool act = oo < max_out && ii < ni;
       if (!__any_sync(0xffffffffu, act)) break;
-      const bool tail = oo + 4 > max_out;  // fewer than four output slots left in this call
+      const bool tail = oo + MMW_TRIP > max_out;  // fewer than a trip's output slots left in this call
       if (__any_sync(0xffffffffu, act && (careful || tail))) {
         const unsigned qslot = q_lane + (unsigned)(oo & (MMW_Q - 1)) * RP;
         if (act && (careful || tail) && mmw_ldq(qslot) == MMW_EMPTY) {
           float v[8], cf[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) v[i] = __ldg(col + (size_t)(ii + i) * nchan);
-          const float* tp = tab + 8 * mm_imu(mu);
+          const float* tp = tab + (MMW_TABROW / 4) * mm_imu(mu);  // copy 0 of the row
 #pragma unroll
-          for (int i = 0; i < 8; i++) cf[i] = tp[i];
+          for (int i = 0; i < 8; i++) cf[i] = tp[(i >> 2) * (MMW_TABREP * 4) + (i & 3)];
           const float o = mmse8(cf, v, order);
           unsigned ob = __float_as_uint(o);
           if (ob == MMW_EMPTY) ob = 0x7fc00000u;
@@ -242,6 +293,8 @@ __global__ void __maxnreg__(48) mm_ws_kernel(const MMArgs a) {
           // the ring still holds rows >= hi - BACK (the loader never overwrites rows >= pub_ii - BACK
           // and every published position is <= hi); older rows keep coming from global memory
           careful = ii < max(hi - MMW_BACK, ii0);
+          iib = ii * 256 + cl * 4;
+          ta = ta_of(mu);
           mmw_stv(pub_ii + cl, min(ii, hi));
         }
       }

@@ -16,6 +16,8 @@ stallcols = [i for i, x in enumerate(h) if x.startswith('stall_') and 'Not Issue
 samples, execd, agg = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
 recs = []
 for r in rows[2:]:
+    if r and r[0] in ('Kernel Name', 'Address'):
+        break  # a second view of the same kernel follows: the first one is enough
     if len(r) <= iex:
         continue
     off = int(r[ia], 16) - base
