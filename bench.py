@@ -171,6 +171,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
     R = args.rows
@@ -204,6 +206,11 @@ def run_ours(args):
         works = ring.exchange_halo(tail_rows, halo_in, s)          # NCCL send/recv of the input halo
         ring.wait_all(works)
         ch.seek_async(plan.abs_start(s) - halo, stream)
+        if plan.front_after_own_tail:
+            # world >= 3: between two of its tails a rank has (world - 1) tail slots of idle time, more than one front
+            # takes, so the front does not need to run underneath the rank's own tail (where the two slow each other
+            # down by 20-50 %): the serial tail chain, which caps the whole job, then runs at its stand-alone speed
+            torch.cuda.current_stream().wait_stream(tail_ts)
         ch.process_front_device(x, halo + R, stream)                # all ranks concurrently
         # The tails form ONE serial chain over all blocks of all ranks (block b's clock recovery starts from block
         # b-1's final loop state), so they run on a side stream: this rank's main stream goes on to the next halo
@@ -353,6 +360,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows_per_step_per_gpu": R, "samples_per_step_per_gpu": samples_per_step,
                    "active_channels": int(args.active), "halo_rows": halo, "sharding": "time blocks, block = step*N + rank",
+                   "front_vs_own_tail": "after" if plan.front_after_own_tail else "overlapped",
                    "l2": "input block (%.0f MB) and every intermediate are larger than the 126 MB L2" % (samples_per_step * 8 / 1e6)},
         "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": (Th + R) * M * 8, "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps, "api": "grcuda_dmr_chain_process_host + grcuda_dmr_chain_read_hits (pinned host input)"},

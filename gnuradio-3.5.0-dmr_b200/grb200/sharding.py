@@ -40,6 +40,14 @@ class TimeShardPlan:
     def right(self):
         return (self.rank + 1) % self.world
 
+    @property
+    def front_after_own_tail(self):
+        """Scheduling policy of a rank's two streams.  The tails of all blocks form one serial chain, so a rank's tail
+        occupies one slot in `world`; with world >= 3 the remaining slots are longer than a front, and running the
+        front strictly after the rank's previous tail keeps both at their stand-alone speed.  With 1 or 2 ranks the
+        front has to overlap the tail to keep the device busy."""
+        return self.world >= 3
+
     def has_left_state(self, step):
         """False only for the very first block of the stream (it starts from the constructor state)."""
         return self.block_index(step) > 0
