@@ -37,8 +37,8 @@ ROOFLINE_NOTES = {   # which roofline really bounds each stage (DESIGN.md sectio
     "pfb_fir": "HBM stream (TMA staged)",
     "pfb_fft": "HBM and FP32 issue (~87 instructions per point)",
     "rrc_fir": "FP32-issue bound, not HBM bound: the reference's SSE summation order forbids FMA (separate IEEE multiply "
-               "and add per tap) and the table arctangent needs a correctly rounded division; ncu: issue active 64 %, "
-               "dram 14 % of peak; DRAM traffic = algorithmic bytes",
+               "and add per tap) and the table arctangent needs a correctly rounded division; ncu: issue active 55 %, "
+               "dram 17 % of peak; DRAM traffic = algorithmic bytes",
     "mm_slicer": "latency bound: one sequential recursion per channel, 250 warps at single-warp instruction latency; runs "
                  "concurrently with the next block's front",
 }
