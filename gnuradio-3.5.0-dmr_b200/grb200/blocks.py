@@ -208,6 +208,75 @@ class pfb_channelizer_ccf(_Block):
                                                                _dp(d_out), _torch_stream()))
 
 
+class pfb_arb_resampler_ccf(_Block):
+    """gr_make_pfb_arb_resampler_ccf(float rate, taps, unsigned filter_size=32)
+    (gr_pfb_arb_resampler_ccf.cc:42-205).  `nchan` > 1 is the batched [time][channel] form (one schedule for all
+    channels); ValueError for fewer than 2 taps / a non-positive rate."""
+    _destroy = "grcuda_pfb_arb_resampler_ccf_destroy"
+    in_dtype, out_dtype = np.complex64, np.complex64
+
+    def __init__(self, rate, taps, filter_size=32, nchan=1):
+        t = _f32(taps)
+        self.L = _l.load()
+        self.nchan = int(nchan)
+        self.h = _l.check_handle(self.L.grcuda_pfb_arb_resampler_ccf_create(C.c_float(rate), _p(t), len(t), int(filter_size),
+                                                                            self.nchan))
+
+    def set_rate(self, rate):
+        _l.check(self.L.grcuda_pfb_arb_resampler_ccf_set_rate(self.h, C.c_float(rate)))
+
+    def history(self):
+        return int(self.L.grcuda_pfb_arb_resampler_ccf_history(self.h))
+
+    def relative_rate(self):
+        return float(self.L.grcuda_pfb_arb_resampler_ccf_relative_rate(self.h))
+
+    def taps_per_filter(self):
+        return int(self.L.grcuda_pfb_arb_resampler_ccf_taps_per_filter(self.h))
+
+    def filter_taps(self, i, derivative=False):
+        """print_taps() as data: the taps of polyphase filter i."""
+        out = np.zeros(self.taps_per_filter(), np.float32)
+        _l.check(self.L.grcuda_pfb_arb_resampler_ccf_get_taps(self.h, int(i), int(bool(derivative)), _p(out), len(out)))
+        return out
+
+    def general_work(self, noutput_items, in_items):
+        """in_items: complex64 items from the first history item on.  Returns (out, consumed)."""
+        x = _c64(in_items)
+        out = np.empty(max(noutput_items, 0), np.complex64)
+        consumed = C.c_int(0)
+        n = _l.check(self.L.grcuda_pfb_arb_resampler_ccf_work(self.h, int(noutput_items), len(x), _p(x), _p(out),
+                                                              C.byref(consumed)))
+        return out[:n], consumed.value
+
+    def work_device(self, noutput_rows, ninput_rows, d_in, d_out):
+        """d_in: [ninput_rows][nchan] complex64 on the device (row 0 = first history row); d_out: [>= noutput_rows][nchan].
+        Returns (rows produced, rows consumed)."""
+        consumed = C.c_int(0)
+        n = _l.check(self.L.grcuda_pfb_arb_resampler_ccf_work_device(self.h, int(noutput_rows), int(ninput_rows), _dp(d_in),
+                                                                     _dp(d_out), C.byref(consumed), _torch_stream()))
+        return n, consumed.value
+
+    def run(self, x, chunk_out=None):
+        """vector_source -> block -> vector_sink over the new items x (zero history in front, like gr_buffer)."""
+        x = _c64(x)
+        buf = np.concatenate([np.zeros(self.history() - 1, np.complex64), x])
+        rate = self.relative_rate()
+        pos, outs, first = 0, [], True
+        while True:
+            nout = chunk_out or int((len(buf) - pos) * rate) + 16
+            o, c = self.general_work(nout, buf[pos:])
+            outs.append(o)
+            pos += c
+            if len(o) == 0 and c == 0:
+                if first:
+                    first = False
+                    continue
+                break
+            first = False
+        return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
 class fft_vcc(_Block):
     """gr_make_fft_vcc(int fft_size, bool forward, const std::vector<float>& window, bool shift=false)
     (gr_fft_vcc.cc:34-64, gr_fft_vcc_fftw.cc:51-103).  IndexError for fft_size <= 0."""

@@ -8,6 +8,7 @@
  *     gr_make_fir_filter_ccf / gr_make_fir_filter_fff        filter/gr_fir_filter_XXX.h.t
  *     gr_make_freq_xlating_fir_filter_ccf                    filter/gr_freq_xlating_fir_filter_XXX.h.t
  *     gr_make_pfb_channelizer_ccf                            filter/gr_pfb_channelizer_ccf.h:31-34
+ *     gr_make_pfb_arb_resampler_ccf                          filter/gr_pfb_arb_resampler_ccf.h:36-39
  *     gr_make_fft_vcc                                        general/gr_fft_vcc.h:32-33
  *     gr_make_quadrature_demod_cf                            general/gr_quadrature_demod_cf.h
  *     digital_make_clock_recovery_mm_ff                      gr-digital/include/digital_clock_recovery_mm_ff.h:37-40
@@ -211,6 +212,53 @@ class gr_pfb_channelizer_ccf : public gr_block {
 inline gr_pfb_channelizer_ccf_sptr gr_make_pfb_channelizer_ccf(unsigned int numchans, const std::vector<float>& taps,
                                                                float oversample_rate) {
   return GR_B200_INITIAL_SPTR(new gr_pfb_channelizer_ccf(numchans, taps, oversample_rate));
+}
+
+/* ---- gr_pfb_arb_resampler_ccf (filter/gr_pfb_arb_resampler_ccf.cc:42-205) ------------------------------ */
+class gr_pfb_arb_resampler_ccf;
+typedef GR_B200_SPTR(gr_pfb_arb_resampler_ccf) gr_pfb_arb_resampler_ccf_sptr;
+gr_pfb_arb_resampler_ccf_sptr gr_make_pfb_arb_resampler_ccf(float rate, const std::vector<float>& taps,
+                                                            unsigned int filter_size = 32);
+class gr_pfb_arb_resampler_ccf : public gr_block {
+  friend gr_pfb_arb_resampler_ccf_sptr gr_make_pfb_arb_resampler_ccf(float, const std::vector<float>&, unsigned int);
+  grcuda_pfb_arb* d_plan;
+  gr_pfb_arb_resampler_ccf(float rate, const std::vector<float>& taps, unsigned int filter_size)
+      : gr_block("pfb_arb_resampler_ccf", gr_make_io_signature(1, 1, sizeof(gr_complex)),
+                 gr_make_io_signature(1, 1, sizeof(gr_complex))),                            /* :45-47 */
+        d_plan(grcuda_pfb_arb_resampler_ccf_create(rate, taps.data(), (int)taps.size(), filter_size, 1)) {
+    if (!d_plan) throw_last_error("gr_pfb_arb_resampler_ccf");
+    set_relative_rate(grcuda_pfb_arb_resampler_ccf_relative_rate(d_plan));                   /* .h:162 */
+    set_history(grcuda_pfb_arb_resampler_ccf_history(d_plan));                               /* :121 */
+  }
+ public:
+  ~gr_pfb_arb_resampler_ccf() { grcuda_pfb_arb_resampler_ccf_destroy(d_plan); }
+  void set_rate(float rate) {                                   /* .h:159-163 */
+    check_rc(grcuda_pfb_arb_resampler_ccf_set_rate(d_plan, rate), "set_rate");
+    set_relative_rate(rate);
+  }
+  void print_taps() {                                           /* :142-153 */
+    const int T = grcuda_pfb_arb_resampler_ccf_taps_per_filter(d_plan), n = grcuda_pfb_arb_resampler_ccf_filter_size(d_plan);
+    std::vector<float> t(T);
+    for (int i = 0; i < n; i++) {
+      grcuda_pfb_arb_resampler_ccf_get_taps(d_plan, i, 0, t.data(), T);
+      printf("filter[%d]: [", i);
+      for (int j = 0; j < T; j++) printf(" %.4e", t[j]);
+      printf("]\n");
+    }
+  }
+  int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                   gr_vector_void_star& output_items) {
+    int consumed = 0;
+    int r = check_rc(grcuda_pfb_arb_resampler_ccf_work(d_plan, noutput_items, ninput_items[0], cin(input_items[0]),
+                                                       cout_(output_items[0]), &consumed),
+                     "general_work");
+    consume_each(consumed);                                     /* :203 */
+    return r;
+  }
+};
+inline gr_pfb_arb_resampler_ccf_sptr gr_make_pfb_arb_resampler_ccf(float rate, const std::vector<float>& taps,
+                                                                   unsigned int filter_size) {
+  return GR_B200_INITIAL_SPTR(new gr_pfb_arb_resampler_ccf(rate, taps, filter_size));
 }
 
 /* ---- gr_fft_vcc (general/gr_fft_vcc.cc:34-64, gr_fft_vcc_fftw.cc:51-103) ---------------------------- */

@@ -238,6 +238,33 @@ int grcuda_correlate_access_code_bb_work_symbols_device(grcuda_corr* h, const un
                                                         grcuda_hit* d_hits, int max_hits, int* d_nhits,
                                                         void* stream);
 
+/* ---- 8f rank 3  gr_pfb_arb_resampler_ccf ------------------------------------------------------
+ * replaces gr_pfb_arb_resampler_ccf::general_work and its 2 x filter_size gr_fir_ccf objects
+ * (gr_pfb_arb_resampler_ccf.cc:42-205; set_rate .h:159-163): the 12.5 kS/s -> integer samples/symbol
+ * resampler the reference's own 4FSK chains put in front of clock recovery.  Constructor arguments of
+ * gr_make_pfb_arb_resampler_ccf(rate, taps, filter_size) + nchan: the batched form resamples nchan
+ * channels laid out [time][channel] with ONE schedule (nchan = 1 is the reference's stream).
+ * history = taps_per_filter + 1; relative_rate = rate; the first work() returns 0 (:166-169).
+ * `ninput_items` counts from the first history item, like the reference's ninput_items[0];
+ * *consumed is what the reference passes to consume_each().  Output is bit identical to the reference
+ * built with gr_fir_ccf_generic and within 1e-6 relative of the SSE class (bar: 1e-4). */
+typedef struct grcuda_pfb_arb grcuda_pfb_arb;
+grcuda_pfb_arb* grcuda_pfb_arb_resampler_ccf_create(float rate, const float* taps, int ntaps, unsigned filter_size,
+                                                    int nchan);
+void grcuda_pfb_arb_resampler_ccf_destroy(grcuda_pfb_arb* h);
+int grcuda_pfb_arb_resampler_ccf_set_rate(grcuda_pfb_arb* h, float rate);
+unsigned grcuda_pfb_arb_resampler_ccf_history(grcuda_pfb_arb* h);
+double grcuda_pfb_arb_resampler_ccf_relative_rate(grcuda_pfb_arb* h);
+int grcuda_pfb_arb_resampler_ccf_taps_per_filter(grcuda_pfb_arb* h);
+int grcuda_pfb_arb_resampler_ccf_filter_size(grcuda_pfb_arb* h);
+/* print_taps (:142-153) as data: taps of one polyphase filter (derivative != 0: of the derivative bank) */
+int grcuda_pfb_arb_resampler_ccf_get_taps(grcuda_pfb_arb* h, int filter, int derivative, float* out, int cap);
+int grcuda_pfb_arb_resampler_ccf_work(grcuda_pfb_arb* h, int noutput_items, int ninput_items, const grcuda_complex* in,
+                                      grcuda_complex* out, int* consumed);
+int grcuda_pfb_arb_resampler_ccf_work_device(grcuda_pfb_arb* h, int noutput_items, int ninput_items,
+                                             const grcuda_complex* d_in, grcuda_complex* d_out, int* consumed,
+                                             void* stream);
+
 /* ---- flagship pipeline: wideband -> PFB -> batched 4FSK demod -> sync search ---------------
  * One object that owns the HBM-resident intermediates and per-channel loop state and runs
  *   pfb_channelizer_ccf -> quadrature_demod_cf -> fir_filter_fff(RRC) -> clock_recovery_mm_ff

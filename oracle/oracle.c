@@ -474,6 +474,113 @@ void orc_corr_work(orc_corr_state* s, const unsigned char* in, long n, unsigned 
   }
 }
 
+
+/* ---- gr_pfb_arb_resampler_ccf ------------------------------------------------------------------ */
+void orc_arb_set_rate(orc_arb_state* s, float rate) { /* gr_pfb_arb_resampler_ccf.h:159-163 */
+  s->dec_rate = (unsigned)floor(s->int_rate / rate);
+  s->flt_rate = (s->int_rate / rate) - s->dec_rate;
+  s->rate = rate;
+}
+static void arb_create_taps(const orc_arb_state* s, const float* newtaps, int ntaps, float* ours) { /* :90-125 */
+  /* filter i gets taps tmp[i + j*int_rate], j < taps_per_filter (ourtaps[int_rate-1-i], set on ourfilter[i]) */
+  const unsigned T = s->taps_per_filter;
+  for (unsigned i = 0; i < s->int_rate; i++)
+    for (unsigned j = 0; j < T; j++) {
+      const unsigned k = i + j * s->int_rate;
+      ours[(size_t)i * T + j] = k < (unsigned)ntaps ? newtaps[k] : 0.0f;
+    }
+}
+int orc_arb_init(orc_arb_state* s, float rate, const float* taps, int ntaps, unsigned filter_size) { /* :42-84 */
+  memset(s, 0, sizeof *s);
+  if (ntaps < 2 || filter_size < 1) return -1; /* create_diff_taps reads an unset `tap` for fewer than 2 taps */
+  s->acc = 0;
+  s->int_rate = filter_size;
+  orc_arb_set_rate(s, rate);
+  s->last_filter = 0;
+  s->start_index = 0;
+  s->taps_per_filter = (unsigned)ceil((double)ntaps / (double)filter_size);
+  float* d = (float*)malloc(sizeof(float) * (size_t)ntaps);
+  float tap = 0;
+  for (int i = 0; i < ntaps - 1; i++) { /* :127-140 */
+    tap = taps[i + 1] - taps[i];
+    d[i] = tap;
+  }
+  d[ntaps - 1] = tap;
+  s->taps = (float*)malloc(sizeof(float) * (size_t)s->int_rate * s->taps_per_filter);
+  s->dtaps = (float*)malloc(sizeof(float) * (size_t)s->int_rate * s->taps_per_filter);
+  arb_create_taps(s, taps, ntaps, s->taps);
+  arb_create_taps(s, d, ntaps, s->dtaps);
+  free(d);
+  s->updated = 1;
+  return 0;
+}
+void orc_arb_free(orc_arb_state* s) {
+  free(s->taps);
+  free(s->dtaps);
+  s->taps = s->dtaps = 0;
+}
+/* gr_fir_ccf_generic::filter (gr_fir_XXX_generic.cc.t:28-55, N_UNROLL 2): d_taps = reversed taps */
+static orc_cpx arb_filter(const float* fwd, unsigned n, const orc_cpx* in) {
+  float a0r = 0, a0i = 0, a1r = 0, a1i = 0;
+  unsigned i = 0;
+  for (; i + 2 <= n; i += 2) {
+    const float t0 = fwd[n - 1 - i], t1 = fwd[n - 2 - i];
+    a0r += t0 * in[i].re; a0i += t0 * in[i].im;
+    a1r += t1 * in[i + 1].re; a1i += t1 * in[i + 1].im;
+  }
+  for (; i < n; i++) {
+    const float t0 = fwd[n - 1 - i];
+    a0r += t0 * in[i].re; a0i += t0 * in[i].im;
+  }
+  orc_cpx r = {a0r + a1r, a0i + a1i};
+  return r;
+}
+static int arb_run(orc_arb_state* s, const orc_cpx* in, int ninput, orc_cpx* out, int noutput, int* count_of,
+                   unsigned short* filt_of, float* acc_of, int* consumed) { /* :155-205 */
+  if (consumed) *consumed = 0;
+  if (s->updated) {
+    s->updated = 0;
+    return 0;
+  }
+  int i = 0, count = s->start_index;
+  unsigned j = s->last_filter;
+  const unsigned T = s->taps_per_filter;
+  const int max_input = ninput - (int)T;
+  while (i < noutput && count < max_input) {
+    while (j < s->int_rate && i < noutput) {
+      if (out) {
+        const orc_cpx o0 = arb_filter(s->taps + (size_t)j * T, T, in + count);
+        const orc_cpx o1 = arb_filter(s->dtaps + (size_t)j * T, T, in + count);
+        out[i].re = o0.re + o1.re * s->acc;
+        out[i].im = o0.im + o1.im * s->acc;
+      }
+      if (count_of) count_of[i] = count;
+      if (filt_of) filt_of[i] = (unsigned short)j;
+      if (acc_of) acc_of[i] = s->acc;
+      i++;
+      s->acc += s->flt_rate;
+      j += s->dec_rate + (int)floorf(s->acc);
+      s->acc = fmodf(s->acc, 1.0f);
+    }
+    if (i < noutput) {
+      const float ss = (float)(int)(j / s->int_rate); /* `float ss = (int)(j / d_int_rate); count += ss;` */
+      count = (int)((float)count + ss);
+      j = j % s->int_rate;
+    }
+  }
+  s->last_filter = j;
+  s->start_index = count - ninput > 0 ? count - ninput : 0;
+  if (consumed) *consumed = count < ninput ? count : ninput;
+  return i;
+}
+int orc_arb_general_work(orc_arb_state* s, const orc_cpx* in, int ninput, orc_cpx* out, int noutput, int* consumed) {
+  return arb_run(s, in, ninput, out, noutput, 0, 0, 0, consumed);
+}
+int orc_arb_schedule(orc_arb_state* s, int ninput, int noutput, int* count_of, unsigned short* filt_of, float* acc_of,
+                     int* consumed) {
+  return arb_run(s, 0, ninput, 0, noutput, count_of, filt_of, acc_of, consumed);
+}
+
 /* ---- gr_firdes ------------------------------------------------------------------------------ */
 static double izero(double x) { /* gr_firdes.cc:35-51 */
   double sum, u, halfx, temp;

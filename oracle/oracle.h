@@ -108,6 +108,25 @@ int orc_corr_init(orc_corr_state* s, const char* access_code, int threshold); /*
 void orc_corr_work(orc_corr_state* s, const unsigned char* in, long n, unsigned char* out);
 unsigned orc_count_bits64(unsigned long long x); /* gr_count_bits.cc:75-93 */
 
+/* gr_pfb_arb_resampler_ccf (gr_pfb_arb_resampler_ccf.cc:42-84 ctor, :90-125 create_taps, :127-140
+ * create_diff_taps, :155-205 general_work; header :159-163 set_rate).  history = taps_per_filter + 1.
+ * Filters use the ccf dot product in the generic order (2 accumulators); the SSE class differs by ~1e-7. */
+typedef struct {
+  unsigned int_rate, dec_rate, last_filter, taps_per_filter;
+  float flt_rate, acc, rate;
+  int start_index, updated;
+  float* taps;  /* [int_rate][taps_per_filter]  taps of filter i in FORWARD order (as handed to set_taps) */
+  float* dtaps; /* same for the derivative filters */
+} orc_arb_state;
+int orc_arb_init(orc_arb_state* s, float rate, const float* taps, int ntaps, unsigned filter_size);
+void orc_arb_set_rate(orc_arb_state* s, float rate);
+void orc_arb_free(orc_arb_state* s);
+/* returns produced; *consumed = what consume_each got.  in[0] = first history item. */
+int orc_arb_general_work(orc_arb_state* s, const orc_cpx* in, int ninput, orc_cpx* out, int noutput, int* consumed);
+/* the index recurrence alone: which input offset / filter / interpolation weight output i uses.
+ * Arrays may be NULL.  Same return values and state update as general_work. */
+int orc_arb_schedule(orc_arb_state* s, int ninput, int noutput, int* count_of, unsigned short* filt_of, float* acc_of,
+                     int* consumed);
 /* gr_firdes (gr_firdes.cc:57-147,601-655,720-782): tap / window design on the host. */
 int orc_firdes_window(int win_type, int ntaps, double beta, float* out);
 int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win_type, double beta, float* out, int cap);

@@ -28,6 +28,12 @@ class CorrState(C.Structure):
                [("threshold", C.c_uint)]
 
 
+class ArbState(C.Structure):
+    _fields_ = [("int_rate", C.c_uint), ("dec_rate", C.c_uint), ("last_filter", C.c_uint), ("taps_per_filter", C.c_uint),
+                ("flt_rate", C.c_float), ("acc", C.c_float), ("rate", C.c_float), ("start_index", C.c_int),
+                ("updated", C.c_int), ("taps", C.POINTER(C.c_float)), ("dtaps", C.POINTER(C.c_float))]
+
+
 class Rotator(C.Structure):
     _fields_ = [("phase", C.c_float * 2), ("incr", C.c_float * 2), ("counter", C.c_uint)]
 
@@ -296,3 +302,72 @@ def mmse_table():
 
 def atan_table():
     return np.ctypeslib.as_array(lib().orc_atan_table(), shape=(257,)).copy()
+
+
+# ---- gr_pfb_arb_resampler_ccf -----------------------------------------------------------------------
+class ArbResampler:
+    """orc_arb_* (gr_pfb_arb_resampler_ccf.cc): a stateful block; run() plays the scheduler around it."""
+
+    def __init__(self, rate, taps, filter_size=32):
+        t = np.ascontiguousarray(taps, np.float32)
+        self.s = ArbState()
+        if lib().orc_arb_init(C.byref(self.s), C.c_float(rate), _p(t), len(t), int(filter_size)) != 0:
+            raise ValueError("pfb_arb_resampler_ccf: needs at least 2 taps and 1 filter")
+
+    def __del__(self):
+        try:
+            lib().orc_arb_free(C.byref(self.s))
+        except Exception:
+            pass
+
+    history = property(lambda self: int(self.s.taps_per_filter) + 1)
+
+    def set_rate(self, rate):
+        lib().orc_arb_set_rate(C.byref(self.s), C.c_float(rate))
+
+    def filter_taps(self, i):
+        T = int(self.s.taps_per_filter)
+        return np.array([self.s.taps[i * T + j] for j in range(T)], np.float32)
+
+    def general_work(self, noutput, in_items):
+        """in_items starts at the first history item.  Returns (out, consumed)."""
+        x = np.ascontiguousarray(in_items, np.complex64)
+        out = np.zeros(max(noutput, 1), np.complex64)
+        consumed = C.c_int(0)
+        r = lib().orc_arb_general_work(C.byref(self.s), _p(x), len(x), _p(out), int(noutput), C.byref(consumed))
+        return out[:r], consumed.value
+
+    def schedule(self, ninput, noutput):
+        cnt = np.zeros(max(noutput, 1), np.int32)
+        flt = np.zeros(max(noutput, 1), np.uint16)
+        acc = np.zeros(max(noutput, 1), np.float32)
+        consumed = C.c_int(0)
+        r = lib().orc_arb_schedule(C.byref(self.s), int(ninput), int(noutput), _p(cnt), _p(flt), _p(acc), C.byref(consumed))
+        return cnt[:r], flt[:r], acc[:r], consumed.value
+
+    def run(self, x, chunk_out=None):
+        """vector_source -> block -> vector_sink over the new items x (zero history in front)."""
+        return run_general(self, x, chunk_out, float(self.s.rate))
+
+
+def run_general(block, x, chunk_out, rate):
+    """Scheduler loop shared with oracle/refharness.py's run_arb: `block.general_work(noutput, items from the first
+    history item)` -> (out, consumed); stops when a call neither produces nor consumes (after the first, which
+    returns 0 by contract)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    h = block.history - 1
+    buf = np.concatenate([np.zeros(h, np.complex64), x])
+    pos, outs, first = 0, [], True
+    while True:
+        avail = len(buf) - pos
+        nout = chunk_out or int(avail * rate) + 16
+        o, c = block.general_work(nout, buf[pos:])
+        outs.append(o)
+        pos += c
+        if len(o) == 0 and c == 0:
+            if first:
+                first = False
+                continue
+            break
+        first = False
+    return np.concatenate(outs) if outs else np.zeros(0, np.complex64)

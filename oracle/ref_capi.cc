@@ -14,6 +14,7 @@
 #include <gr_fir_filter_fff.h>
 #include <gr_freq_xlating_fir_filter_ccf.h>
 #include <gr_pfb_channelizer_ccf.h>
+#include <gr_pfb_arb_resampler_ccf.h>
 #include <gr_fft_vcc.h>
 #include <gr_quadrature_demod_cf.h>
 #include <gr_math.h>
@@ -83,6 +84,11 @@ grref_block* grref_make_freq_xlating_fir_filter_ccf(int decim, const float* taps
 grref_block* grref_make_pfb_channelizer_ccf(unsigned numchans, const float* taps, int ntaps, float oversample) {
   return guarded([&] {
     return gr_block_sptr(gr_make_pfb_channelizer_ccf(numchans, std::vector<float>(taps, taps + ntaps), oversample));
+  });
+}
+grref_block* grref_make_pfb_arb_resampler_ccf(float rate, const float* taps, int ntaps, unsigned filter_size) {
+  return guarded([&] {
+    return gr_block_sptr(gr_make_pfb_arb_resampler_ccf(rate, std::vector<float>(taps, taps + ntaps), filter_size));
   });
 }
 grref_block* grref_make_fft_vcc(int fft_size, int forward, const float* window, int nwin, int shift) {

@@ -44,6 +44,7 @@ def dir_makers():
         "grref_make_pfb_channelizer_ccf", "grref_make_fft_vcc", "grref_make_quadrature_demod_cf",
         "grref_make_clock_recovery_mm_ff", "grref_make_pager_slicer_fb", "grref_make_binary_slicer_fb",
         "grref_make_map_bb", "grref_make_unpack_k_bits_bb", "grref_make_correlate_access_code_bb",
+        "grref_make_pfb_arb_resampler_ccf",
     ]
 
 
@@ -148,6 +149,37 @@ def pfb_channelizer_ccf(numchans, taps, oversample_rate=1.0):
     t = np.ascontiguousarray(taps, np.float32)
     return RefBlock(lib().grref_make_pfb_channelizer_ccf(int(numchans), _fp(t), len(t), C.c_float(oversample_rate)),
                     np.complex64, np.complex64, nin=numchans, out_vlen=numchans)
+
+
+def pfb_arb_resampler_ccf(rate, taps, filter_size=32):
+    t = np.ascontiguousarray(taps, np.float32)
+    return RefBlock(lib().grref_make_pfb_arb_resampler_ccf(C.c_float(rate), _fp(t), len(t), int(filter_size)),
+                    np.complex64, np.complex64)
+
+
+def run_arb(block, x, rate, chunk_out=None):
+    """gr_pfb_arb_resampler_ccf over the whole stream x (new items): the scheduler's part is played here --
+    history-prefixed aligned buffer, ninput_items counted from the first history item, consume_each honoured."""
+    x = np.ascontiguousarray(x, np.complex64)
+    hist = block.history
+    raw, ptr, view = aligned_stream(x, hist, np.complex64)
+    total = len(view)
+    pos, outs, first = 0, [], True
+    while True:
+        avail = total - pos
+        nout = chunk_out or int(avail * rate) + 16
+        out = np.zeros(nout, np.complex64)
+        r = block.general_work(nout, [ptr + pos * 8], [avail], out)
+        c = block.consumed
+        outs.append(out[:r].copy())
+        pos += c
+        if r == 0 and c == 0:
+            if first:
+                first = False
+                continue
+            break
+        first = False
+    return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
 
 
 def fft_vcc(fft_size, forward, window, shift=False):

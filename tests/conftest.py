@@ -22,6 +22,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_next():
+    """Fixtures of the SURVEY 8f blocks (tests/golden/make_golden.py next)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures_next.npz"))
+
+
+@pytest.fixture(scope="session")
 def orc():
     """The plain-C oracle restatement (built on demand with gcc)."""
     import orc as _orc

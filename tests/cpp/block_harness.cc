@@ -103,6 +103,9 @@ static int cmd_run(int argc, char** argv) {
       for (unsigned j = 0; j < M; j++)
         memcpy(streams[j].data() + m * sizeof(gr_complex), in.data() + (m * M + j) * sizeof(gr_complex), sizeof(gr_complex));
     out = run_block(*b, streams, max_noutput);
+  } else if (kind == "arb") {
+    auto b = gr_make_pfb_arb_resampler_ccf((float)atof(argv[3]), floats(argv[4]), (unsigned)atoi(argv[5]));
+    out = run_block(*b, streams, max_noutput);
   } else if (kind == "fft") {
     auto b = gr_make_fft_vcc(atoi(argv[3]), atoi(argv[4]) != 0, floats(argv[5]), atoi(argv[6]) != 0);
     out = run_block(*b, streams, max_noutput);

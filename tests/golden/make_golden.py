@@ -170,7 +170,35 @@ def fixtures():
     return fx
 
 
+def fixtures_next():
+    """SURVEY.md 8f blocks (the callers either side of the path), same recipe: the reference's own classes on small
+    seeded inputs.  Kept in a file of its own so that ref_fixtures.npz stays byte-identical."""
+    import refharness as R
+    from grb200 import firdes
+    fx = {}
+    rng = np.random.default_rng(20)
+    # rank 3: gr_pfb_arb_resampler_ccf, the 12.5 kS/s -> 4 samples/symbol resampler of a 4FSK chain (rate 1.536), a
+    # decimating rate, and ragged tap counts (taps_per_filter padding); SSE filters (what x86-64 runs) and generic
+    x = (rng.standard_normal(3000) + 1j * rng.standard_normal(3000)).astype(np.complex64)
+    fx["arb_x"] = x
+    for tag, rate, nf, taps in (
+            ("up", 19200.0 / 12500.0, 32, np.asarray(firdes.low_pass(32, 32 * 12500.0, 5000.0, 2500.0), np.float32)),
+            ("down", 0.731, 32, (rng.standard_normal(32 * 9 + 5) * 0.1).astype(np.float32)),
+            ("few", 2.5, 16, (rng.standard_normal(77) * 0.1).astype(np.float32))):
+        fx["arb_%s_taps" % tag] = taps
+        fx["arb_%s_args" % tag] = np.array([rate, nf])
+        for impl, nm in ((1, "sse"), (0, "generic")):
+            R.set_fir_impl(impl)
+            fx["arb_%s_y_%s" % (tag, nm)] = R.run_arb(R.pfb_arb_resampler_ccf(rate, taps, nf), x, rate, chunk_out=211)
+    R.set_fir_impl(1)
+    return fx
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        np.savez_compressed(os.path.join(HERE, "ref_fixtures_next.npz"), **fixtures_next())
+        print("wrote ref_fixtures_next.npz", os.path.getsize(os.path.join(HERE, "ref_fixtures_next.npz")) // 1024, "KiB")
+        return
     with open(os.path.join(HERE, "kats.json"), "w") as f:
         json.dump(kats(), f, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_fixtures.npz"), **fixtures())

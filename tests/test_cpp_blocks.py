@@ -113,6 +113,22 @@ def test_pfb_channelizer_block(harness, tmp_path, orc, M, T, os_rate):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_pfb_arb_resampler_block(harness, tmp_path, orc):
+    """gr_make_pfb_arb_resampler_ccf under the scheduler: forecast = noutput + history - 1 (gr_block default),
+    consume_each honoured, first general_work returns 0; bit identical to the generic-order reference."""
+    rng = np.random.default_rng(23)
+    x = (rng.standard_normal(12000) + 1j * rng.standard_normal(12000)).astype(np.complex64)
+    taps = (rng.standard_normal(32 * 9 + 1) * 0.1).astype(np.float32)
+    for rate, chunk in ((1.536, 600), (0.41, 333)):
+        y = run(harness, tmp_path, ["arb", rate, taps, 32], x, np.complex64, max_noutput=chunk)
+        want = orc.ArbResampler(rate, taps, 32).run(x)
+        # the scheduler stops when forecast() no longer fits: the last few outputs are not asked for
+        assert len(want) - 2 * chunk <= len(y) <= len(want)
+        assert np.array_equal(y.view(np.uint32), want[:len(y)].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
 def test_fft_vcc_block(harness, tmp_path, orc):
     rng = np.random.default_rng(5)
     N, nvec = 4096, 40

@@ -90,6 +90,26 @@ def main():
     ms = timeit(lambda: q.work_device(rows, M, xq, d), 10, flush)
     out["quadrature_demod_cf_100M"] = {"ms": ms, "alg_GBps": 12.0 * rows * M / ms / 1e6, "frac_hbm": 12.0 * rows * M / ms / 1e6 / peak}
     del x, y, xq, d
+    # pfb_arb_resampler_ccf batched over the cfg5 channel block: 12 500 rows x 8000 channels -> 19 200 rows
+    # (12.5 kS/s -> 4 samples/symbol), 17 taps per filter; algorithmic bytes 8 B per input item + 8 B per output item
+    rate = 19200.0 / 12500.0
+    rtaps = np.asarray(firdes.low_pass(32, 32 * 12500.0, 5000.0, 2500.0), np.float32)
+    arb = B.pfb_arb_resampler_ccf(rate, rtaps, 32, nchan=M)
+    hrow = arb.history() - 1
+    xin = torch.view_as_complex(torch.randn((hrow + rows, M, 2), generator=g, device=dev))
+    yout = torch.empty((int(rows * rate) + 64, M), dtype=torch.complex64, device=dev)
+    arb.work_device(1, 1, xin, yout)                       # the "updated" call
+    produced = [0]
+
+    def run_arb():
+        n, _ = arb.work_device(yout.shape[0], xin.shape[0], xin, yout)
+        produced[0] = n
+    ms = timeit(run_arb, 10, flush)
+    byt = 8.0 * rows * M + 8.0 * produced[0] * M
+    out["pfb_arb_resampler_ccf_8000ch"] = {"ms": ms, "rows_out": produced[0], "taps_per_filter": arb.taps_per_filter(),
+                                           "MSps_in": rows * M / ms / 1e3, "alg_GBps": byt / ms / 1e6,
+                                           "frac_hbm": byt / ms / 1e6 / peak}
+    del xin, yout
     # raw copy rates of the box (pinned), 800 MB like one bench block
     h = torch.empty(100_000_000, dtype=torch.complex64, pin_memory=True)
     dd = torch.empty(100_000_000, dtype=torch.complex64, device=dev)
