@@ -678,6 +678,129 @@ int grcuda_pfb_channelizer_ccf_work(grcuda_pfb* h, int nout, const grcuda_comple
 }  // extern "C"
 
 // =============================================================================================
+// 8f rank 3: gr_pfb_decimator_ccf = decim branch filters + one bin of the decim-point backward DFT
+// =============================================================================================
+// out[i] = sum_j e^{+j 2 pi j chan / M} * sum_t taps[j + t M] * in_{M-1-j}[i + T-1-t]   (gr_pfb_decimator_ccf.cc:127-175).
+// On the interleaved stream X[m M + s] = in_s[m] this is ONE decimate-by-M FIR with the composite complex taps
+// h[k] = e^{+j 2 pi (k mod M) chan / M} * taps[k], k = j + t M:  out[i] = sum_k h[k] X[(i + T) M - 1 - k],
+// i.e. exactly what fir_decim_kernel<complex taps> computes -- the FFT the reference "abuses" for the
+// de-spinning (:151-153) is not needed for a single bin.
+struct grcuda_pfb_decim : PlanBase {
+  unsigned M = 1, chan = 0, T = 0;
+  bool updated = true, tiled = false;
+  std::vector<float> taps, new_taps;
+  bool taps_pending = false;
+  FirCore core;
+  DevBuf d_g, d_stage;   // composite taps in window order (warp kernel); [stream][len] staging of the host form
+  PinBuf pin_in;
+  int build(const std::vector<float>& t) {
+    cudaDeviceSynchronize();
+    taps = t;
+    T = (unsigned)ceil((double)t.size() / (double)M);                      // :80
+    const size_t L = (size_t)M * T;
+    std::vector<float> h(2 * L, 0.f);                                      // forward order, complex
+    for (size_t k = 0; k < L; k++) {
+      const float tv = k < t.size() ? t[k] : 0.f;
+      const double ph = 2.0 * M_PI * (double)(((unsigned long long)(k % M) * chan) % M) / (double)M;
+      h[2 * k] = (float)(tv * cos(ph));
+      h[2 * k + 1] = (float)(tv * sin(ph));
+    }
+    std::vector<float> rev(2 * L);                                         // window order g[n] = h[L-1-n] = reversed taps
+    for (size_t n = 0; n < L; n++) { rev[2 * n] = h[2 * (L - 1 - n)]; rev[2 * n + 1] = h[2 * (L - 1 - n) + 1]; }
+    core.decim = (int)M;
+    tiled = L <= 4096 && core.upload(rev.data(), (int)L, true) == GRCUDA_OK;  // else: too large for the tile
+    int rc = d_g.reserve(rev.size() * sizeof(float));
+    if (rc) return rc;
+    GRB_CUDA(cudaMemcpy(d_g.p, rev.data(), rev.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return GRCUDA_OK;
+  }
+  bool gate() {  // "return 0 once after set_taps" (:136-139); a pending set_taps is applied here
+    std::lock_guard<std::mutex> lk(mu);
+    if (taps_pending) {
+      taps_pending = false;
+      build(new_taps);
+      updated = true;
+    }
+    if (updated) { updated = false; return true; }
+    return false;
+  }
+  int run(const float2* d_rows, float2* d_out, long nout, cudaStream_t s) {
+    if (nout <= 0) return GRCUDA_OK;
+    if (tiled) return core.launch(d_rows, d_out, nout, false, 0.0, 0, s);
+    const long warps = std::min<long>(nout, (long)sm_count() * 64);
+    pfb_decim_warp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(d_rows, d_out, nout, (int)M, d_g.as<float2>(),
+                                                                           (int)(M * T));
+    GRB_LAUNCH_CHECK();
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_pfb_decim* grcuda_pfb_decimator_ccf_create(unsigned decim, const float* taps, int ntaps, unsigned channel) {
+  if (decim < 1 || ntaps < 1 || !taps) { set_error(GRCUDA_EINVAL, "pfb_decimator_ccf: bad decimation / taps"); return nullptr; }
+  if (!device_ok()) return nullptr;
+  grcuda_pfb_decim* h = new grcuda_pfb_decim;
+  h->M = decim;
+  h->chan = channel;
+  if (h->base_init() || h->build(std::vector<float>(taps, taps + ntaps))) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_pfb_decimator_ccf_destroy(grcuda_pfb_decim* h) { delete h; }
+int grcuda_pfb_decimator_ccf_set_taps(grcuda_pfb_decim* h, const float* taps, int ntaps) {
+  if (ntaps < 1 || !taps) return set_error(GRCUDA_EINVAL, "pfb_decimator_ccf: no taps");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->new_taps.assign(taps, taps + ntaps);
+  h->taps_pending = true;
+  return GRCUDA_OK;
+}
+unsigned grcuda_pfb_decimator_ccf_history(grcuda_pfb_decim* h) {  // :107 set_history(taps_per_filter)
+  std::lock_guard<std::mutex> lk(h->mu);
+  return h->taps_pending ? (unsigned)ceil((double)h->new_taps.size() / (double)h->M) : h->T;
+}
+int grcuda_pfb_decimator_ccf_taps_per_filter(grcuda_pfb_decim* h) { return (int)grcuda_pfb_decimator_ccf_history(h); }
+int grcuda_pfb_decimator_ccf_decimation(grcuda_pfb_decim* h) { return (int)h->M; }
+// d_in_rows: [history-1 + noutput][decim] interleaved (row m = the m-th item of every stream); one output per row
+int grcuda_pfb_decimator_ccf_work_device(grcuda_pfb_decim* h, long noutput_items, const grcuda_complex* d_in_rows,
+                                         grcuda_complex* d_out, void* stream) {
+  if (h->gate()) return 0;
+  int rc = h->run((const float2*)d_in_rows, (float2*)d_out, noutput_items, h->pick(stream));
+  return rc ? rc : (int)std::min<long>(noutput_items, 0x7fffffffL);
+}
+int grcuda_pfb_decimator_ccf_work_interleaved(grcuda_pfb_decim* h, int noutput_items, const grcuda_complex* in_rows,
+                                              grcuda_complex* out) {
+  if (h->gate()) return 0;
+  if (noutput_items <= 0) return 0;
+  const size_t rows = (size_t)noutput_items + h->T - 1, M = h->M;
+  int rc;
+  if ((rc = h->d_in.reserve(rows * M * sizeof(float2))) || (rc = h->d_out.reserve((size_t)noutput_items * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in_rows, rows * M * sizeof(float2), h->stream))) return rc;
+  if ((rc = h->run(h->d_in.as<float2>(), h->d_out.as<float2>(), noutput_items, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)noutput_items * sizeof(float2), h->stream))) return rc;
+  return noutput_items;
+}
+// the reference's own form: decim separate streams, each from its first history item (gr_stream_to_streams output)
+int grcuda_pfb_decimator_ccf_work(grcuda_pfb_decim* h, int noutput_items, const grcuda_complex* const* in, grcuda_complex* out) {
+  if (h->gate()) return 0;
+  if (noutput_items <= 0) return 0;
+  const size_t len = (size_t)noutput_items + h->T - 1, M = h->M;
+  int rc;
+  if ((rc = h->pin_in.reserve(M * len * sizeof(float2))) || (rc = h->d_stage.reserve(M * len * sizeof(float2))) ||
+      (rc = h->d_in.reserve(M * len * sizeof(float2))) || (rc = h->d_out.reserve((size_t)noutput_items * sizeof(float2))))
+    return rc;
+  for (size_t j = 0; j < M; j++) memcpy((char*)h->pin_in.p + j * len * sizeof(float2), in[j], len * sizeof(float2));
+  GRB_CUDA(cudaMemcpyAsync(h->d_stage.p, h->pin_in.p, M * len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  dim3 tb(32, 8), tg((unsigned)((len + 31) / 32), (unsigned)((M + 31) / 32));
+  transpose_streams_kernel<<<tg, tb, 0, h->stream>>>(h->d_stage.as<float2>(), h->d_in.as<float2>(), (int)M, (int)len);
+  GRB_LAUNCH_CHECK();
+  if ((rc = h->run(h->d_in.as<float2>(), h->d_out.as<float2>(), noutput_items, h->stream))) return rc;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)noutput_items * sizeof(float2), h->stream))) return rc;
+  return noutput_items;
+}
+
+}  // extern "C"
+
+// =============================================================================================
 // a5 / a6: gr_fft_vcc
 // =============================================================================================
 struct grcuda_fft : PlanBase {

@@ -380,4 +380,29 @@ __global__ void transpose_streams_kernel(const float2* __restrict__ src, float2*
   }
 }
 
+// gr_pfb_decimator_ccf when the composite filter does not fit fir_decim_kernel's shared-memory tile (decim x taps
+// too large): one warp per output, lanes stride over the window, so the loads of the window and of the composite taps
+// are coalesced; the taps_per_filter-fold overlap of consecutive windows is served by L1/L2.
+//   out[i] = sum_{n < L} g[n] * x[i * decim + n]     (g = composite complex taps in window order)
+__global__ void __launch_bounds__(256) pfb_decim_warp_kernel(const float2* __restrict__ x, float2* __restrict__ out, long nout,
+                                                             int decim, const float2* __restrict__ g, int L) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long i = warp0; i < nout; i += nwarps) {
+    const float2* w = x + (size_t)i * decim;
+    float ar = 0.f, ai = 0.f;
+    for (int n = lane; n < L; n += 32) {
+      const float2 v = __ldg(w + n), t = __ldg(g + n);
+      ar = fmaf(t.x, v.x, fmaf(-t.y, v.y, ar));
+      ai = fmaf(t.x, v.y, fmaf(t.y, v.x, ai));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ar += __shfl_xor_sync(0xffffffffu, ar, o);
+      ai += __shfl_xor_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) out[i] = make_float2(ar, ai);
+  }
+}
+
 }  // namespace grb

@@ -277,6 +277,60 @@ class pfb_arb_resampler_ccf(_Block):
         return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
 
 
+class pfb_decimator_ccf(_Block):
+    """gr_make_pfb_decimator_ccf(unsigned decim, taps, unsigned channel) (gr_pfb_decimator_ccf.cc:35-175): the
+    polyphase decimator that pulls ONE channel out of the wideband stream."""
+    _destroy = "grcuda_pfb_decimator_ccf_destroy"
+
+    def __init__(self, decim, taps, channel):
+        t = _f32(taps)
+        self.L = _l.load()
+        self.M = int(decim)
+        self.h = _l.check_handle(self.L.grcuda_pfb_decimator_ccf_create(self.M, _p(t), len(t), int(channel)))
+
+    def set_taps(self, taps):
+        t = _f32(taps)
+        _l.check(self.L.grcuda_pfb_decimator_ccf_set_taps(self.h, _p(t), len(t)))
+
+    def history(self):
+        return int(self.L.grcuda_pfb_decimator_ccf_history(self.h))
+
+    def taps_per_filter(self):
+        return int(self.L.grcuda_pfb_decimator_ccf_taps_per_filter(self.h))
+
+    def work(self, noutput_items, input_streams):
+        """input_streams: decim complex64 arrays, each from its first history item.  Returns the outputs."""
+        keep = [_c64(s) for s in input_streams]
+        ptrs = (C.c_void_p * self.M)(*[s.ctypes.data for s in keep])
+        out = np.empty(max(noutput_items, 0), np.complex64)
+        n = _l.check(self.L.grcuda_pfb_decimator_ccf_work(self.h, int(noutput_items), ptrs, _p(out)))
+        return out[:n]
+
+    def work_interleaved(self, noutput_items, rows):
+        x = _c64(rows)
+        out = np.empty(max(noutput_items, 0), np.complex64)
+        n = _l.check(self.L.grcuda_pfb_decimator_ccf_work_interleaved(self.h, int(noutput_items), _p(x), _p(out)))
+        return out[:n]
+
+    def work_device(self, noutput_items, d_in_rows, d_out):
+        return _l.check(self.L.grcuda_pfb_decimator_ccf_work_device(self.h, C.c_long(noutput_items), _dp(d_in_rows), _dp(d_out),
+                                                                    _torch_stream()))
+
+    def run(self, x, chunk=None):
+        """gr_stream_to_streams -> block -> vector_sink over the interleaved new items x (zero history in front)."""
+        x = _c64(x)
+        n = len(x) // self.M
+        h = self.history() - 1
+        rows = np.concatenate([np.zeros((h, self.M), np.complex64), x[:n * self.M].reshape(n, self.M)])
+        assert self.work_interleaved(min(n, 4), rows).size == 0          # the "updated" call
+        out, done, step = [], 0, chunk or max(n, 1)
+        while done < n:
+            m = min(step, n - done)
+            out.append(self.work_interleaved(m, rows[done:done + m + h]))
+            done += m
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+
 class fft_vcc(_Block):
     """gr_make_fft_vcc(int fft_size, bool forward, const std::vector<float>& window, bool shift=false)
     (gr_fft_vcc.cc:34-64, gr_fft_vcc_fftw.cc:51-103).  IndexError for fft_size <= 0."""

@@ -48,7 +48,7 @@ _PTR_RETURNING = [
     "grcuda_pfb_channelizer_ccf_create", "grcuda_fft_vcc_create", "grcuda_quadrature_demod_cf_create",
     "grcuda_clock_recovery_mm_ff_create", "grcuda_pager_slicer_fb_create", "grcuda_binary_slicer_fb_create",
     "grcuda_correlate_access_code_bb_create", "grcuda_dmr_chain_create", "grcuda_malloc_device",
-    "grcuda_pfb_arb_resampler_ccf_create",
+    "grcuda_pfb_arb_resampler_ccf_create", "grcuda_pfb_decimator_ccf_create",
     "grcuda_malloc_pinned", "grcuda_ipc_open",
 ]
 
@@ -77,6 +77,7 @@ def load():
     L.grcuda_freq_xlating_fir_filter_ccf_history.restype = C.c_uint
     L.grcuda_pfb_channelizer_ccf_history.restype = C.c_uint
     L.grcuda_pfb_arb_resampler_ccf_history.restype = C.c_uint
+    L.grcuda_pfb_decimator_ccf_history.restype = C.c_uint
     L.grcuda_pfb_arb_resampler_ccf_relative_rate.restype = C.c_double
     _lib = L
     return L

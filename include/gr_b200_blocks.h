@@ -9,6 +9,7 @@
  *     gr_make_freq_xlating_fir_filter_ccf                    filter/gr_freq_xlating_fir_filter_XXX.h.t
  *     gr_make_pfb_channelizer_ccf                            filter/gr_pfb_channelizer_ccf.h:31-34
  *     gr_make_pfb_arb_resampler_ccf                          filter/gr_pfb_arb_resampler_ccf.h:36-39
+ *     gr_make_pfb_decimator_ccf                              filter/gr_pfb_decimator_ccf.h
  *     gr_make_fft_vcc                                        general/gr_fft_vcc.h:32-33
  *     gr_make_quadrature_demod_cf                            general/gr_quadrature_demod_cf.h
  *     digital_make_clock_recovery_mm_ff                      gr-digital/include/digital_clock_recovery_mm_ff.h:37-40
@@ -212,6 +213,38 @@ class gr_pfb_channelizer_ccf : public gr_block {
 inline gr_pfb_channelizer_ccf_sptr gr_make_pfb_channelizer_ccf(unsigned int numchans, const std::vector<float>& taps,
                                                                float oversample_rate) {
   return GR_B200_INITIAL_SPTR(new gr_pfb_channelizer_ccf(numchans, taps, oversample_rate));
+}
+
+/* ---- gr_pfb_decimator_ccf (filter/gr_pfb_decimator_ccf.cc:35-175) -------------------------------------- */
+class gr_pfb_decimator_ccf;
+typedef GR_B200_SPTR(gr_pfb_decimator_ccf) gr_pfb_decimator_ccf_sptr;
+gr_pfb_decimator_ccf_sptr gr_make_pfb_decimator_ccf(unsigned int decim, const std::vector<float>& taps, unsigned int channel);
+class gr_pfb_decimator_ccf : public gr_sync_block {
+  friend gr_pfb_decimator_ccf_sptr gr_make_pfb_decimator_ccf(unsigned int, const std::vector<float>&, unsigned int);
+  grcuda_pfb_decim* d_plan;
+  gr_pfb_decimator_ccf(unsigned int decim, const std::vector<float>& taps, unsigned int channel)
+      : gr_sync_block("pfb_decimator_ccf", gr_make_io_signature(decim, decim, sizeof(gr_complex)),
+                      gr_make_io_signature(1, 1, sizeof(gr_complex))),                       /* :47-49 */
+        d_plan(grcuda_pfb_decimator_ccf_create(decim, taps.data(), (int)taps.size(), channel)) {
+    if (!d_plan) throw_last_error("gr_pfb_decimator_ccf");
+    set_history(grcuda_pfb_decimator_ccf_history(d_plan));                                   /* :107 */
+  }
+ public:
+  ~gr_pfb_decimator_ccf() { grcuda_pfb_decimator_ccf_destroy(d_plan); }
+  void set_taps(const std::vector<float>& taps) {               /* :75-110 */
+    check_rc(grcuda_pfb_decimator_ccf_set_taps(d_plan, taps.data(), (int)taps.size()), "set_taps");
+    set_history(grcuda_pfb_decimator_ccf_history(d_plan));
+  }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    return check_rc(grcuda_pfb_decimator_ccf_work(d_plan, noutput_items,
+                                                  reinterpret_cast<const grcuda_complex* const*>(input_items.data()),
+                                                  cout_(output_items[0])),
+                    "work");
+  }
+};
+inline gr_pfb_decimator_ccf_sptr gr_make_pfb_decimator_ccf(unsigned int decim, const std::vector<float>& taps,
+                                                           unsigned int channel) {
+  return GR_B200_INITIAL_SPTR(new gr_pfb_decimator_ccf(decim, taps, channel));
 }
 
 /* ---- gr_pfb_arb_resampler_ccf (filter/gr_pfb_arb_resampler_ccf.cc:42-205) ------------------------------ */

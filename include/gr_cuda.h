@@ -265,6 +265,26 @@ int grcuda_pfb_arb_resampler_ccf_work_device(grcuda_pfb_arb* h, int noutput_item
                                              const grcuda_complex* d_in, grcuda_complex* d_out, int* consumed,
                                              void* stream);
 
+/* ---- 8f rank 3  gr_pfb_decimator_ccf -----------------------------------------------------------
+ * replaces gr_pfb_decimator_ccf::work, its decim gr_fir_ccf objects and the decim-point gri_fft it uses to
+ * de-spin ONE channel (gr_pfb_decimator_ccf.cc:44-175).  Constructor arguments of
+ * gr_make_pfb_decimator_ccf(decim, taps, channel).  history = taps_per_filter (:107); one output per input
+ * item of every stream; set_taps is deferred and the first work() after it returns 0 (:136-139).
+ * _work takes the reference's `decim` stream pointers, _work_interleaved / _work_device the same data as rows
+ * [history-1 + noutput][decim] (row m = item m of every stream = decim consecutive samples of the wideband stream). */
+typedef struct grcuda_pfb_decim grcuda_pfb_decim;
+grcuda_pfb_decim* grcuda_pfb_decimator_ccf_create(unsigned decim, const float* taps, int ntaps, unsigned channel);
+void grcuda_pfb_decimator_ccf_destroy(grcuda_pfb_decim* h);
+int grcuda_pfb_decimator_ccf_set_taps(grcuda_pfb_decim* h, const float* taps, int ntaps);
+unsigned grcuda_pfb_decimator_ccf_history(grcuda_pfb_decim* h);
+int grcuda_pfb_decimator_ccf_taps_per_filter(grcuda_pfb_decim* h);
+int grcuda_pfb_decimator_ccf_decimation(grcuda_pfb_decim* h);
+int grcuda_pfb_decimator_ccf_work(grcuda_pfb_decim* h, int noutput_items, const grcuda_complex* const* in, grcuda_complex* out);
+int grcuda_pfb_decimator_ccf_work_interleaved(grcuda_pfb_decim* h, int noutput_items, const grcuda_complex* in_rows,
+                                              grcuda_complex* out);
+int grcuda_pfb_decimator_ccf_work_device(grcuda_pfb_decim* h, long noutput_items, const grcuda_complex* d_in_rows,
+                                         grcuda_complex* d_out, void* stream);
+
 /* ---- flagship pipeline: wideband -> PFB -> batched 4FSK demod -> sync search ---------------
  * One object that owns the HBM-resident intermediates and per-channel loop state and runs
  *   pfb_channelizer_ccf -> quadrature_demod_cf -> fir_filter_fff(RRC) -> clock_recovery_mm_ff

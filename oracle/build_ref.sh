@@ -27,7 +27,7 @@ SRCS=(
   "$CORE/filter/gr_fir_ccf_simd.cc" "$CORE/filter/gr_fir_ccf_x86.cc"
   "$CORE/filter/gr_fir_fff_simd.cc" "$CORE/filter/gr_fir_fff_x86.cc"
   "$CORE/filter/gr_fir_ccc_simd.cc" "$CORE/filter/gr_fir_ccc_x86.cc"
-  "$CORE/filter/gr_pfb_channelizer_ccf.cc" "$CORE/filter/gr_pfb_arb_resampler_ccf.cc"
+  "$CORE/filter/gr_pfb_channelizer_ccf.cc" "$CORE/filter/gr_pfb_arb_resampler_ccf.cc" "$CORE/filter/gr_pfb_decimator_ccf.cc"
   "$CORE/filter/gri_mmse_fir_interpolator.cc"
   "$CORE/general/gr_reverse.cc" "$CORE/general/gr_fast_atan2f.cc" "$CORE/general/gr_count_bits.cc"
   "$CORE/general/gr_quadrature_demod_cf.cc" "$CORE/general/gr_fft_vcc.cc" "$CORE/general/gr_fft_vcc_fftw.cc"
@@ -45,9 +45,9 @@ for s in "${SRCS[@]}"; do
   g++ "${CXXFLAGS[@]}" "${INC[@]}" -c "$s" -o "$o" &
   pids+=($!)
 done
-for s in "$CORE/general/malloc16.c"; do
+for s in "$CORE/general/malloc16.c" "$CORE/filter/gr_sincos.c"; do
   o="$OUT/obj/$(basename "${s%.*}").o"; OBJS+=("$o")
-  gcc -O2 -fPIC -w -I"$CORE/general" -I"$REF/gruel/src/include" -Dgnuradio_core_EXPORTS -c "$s" -o "$o" &
+  gcc -O2 -fPIC -w -I"$CORE/general" -I"$CORE/filter" -I"$REF/gruel/src/include" -Dgnuradio_core_EXPORTS -c "$s" -o "$o" &
   pids+=($!)
 done
 for a in fcomplex_dotprod_sse64 float_dotprod_sse64 ccomplex_dotprod_sse64 \

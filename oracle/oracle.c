@@ -581,6 +581,38 @@ int orc_arb_schedule(orc_arb_state* s, int ninput, int noutput, int* count_of, u
   return arb_run(s, 0, ninput, 0, noutput, count_of, filt_of, acc_of, consumed);
 }
 
+
+/* ---- gr_pfb_decimator_ccf ---------------------------------------------------------------------- */
+int orc_pfb_decimator_taps_per_filter(int decim, int ntaps) { return (int)ceil((double)ntaps / (double)decim); } /* :80 */
+void orc_pfb_decimator_ccf(int decim, const float* taps, int ntaps, unsigned channel, const orc_cpx* const* ins,
+                           long noutput, orc_cpx* out) { /* :127-175 */
+  const int T = orc_pfb_decimator_taps_per_filter(decim, ntaps);
+  float* ft = (float*)malloc(sizeof(float) * (size_t)decim * T); /* filter j: taps[j + t*decim] (:95-103) */
+  for (int j = 0; j < decim; j++)
+    for (int t = 0; t < T; t++) {
+      const long k = j + (long)t * decim;
+      ft[(size_t)j * T + t] = k < ntaps ? taps[k] : 0.0f;
+    }
+  double* wr = (double*)malloc(sizeof(double) * 2 * (size_t)decim);
+  for (int j = 0; j < decim; j++) { /* backward DFT, bin `channel`: e^{+j 2 pi j channel / decim} */
+    const double ph = 2.0 * M_PI * (double)(((unsigned long long)j * channel) % (unsigned)decim) / (double)decim;
+    wr[2 * j] = cos(ph);
+    wr[2 * j + 1] = sin(ph);
+  }
+  for (long i = 0; i < noutput; i++) {
+    double ar = 0, ai = 0;
+    for (int j = decim - 1; j >= 0; j--) {
+      const orc_cpx v = arb_filter(ft + (size_t)j * T, (unsigned)T, ins[decim - 1 - j] + i); /* :148-160 */
+      ar += (double)v.re * wr[2 * j] - (double)v.im * wr[2 * j + 1];
+      ai += (double)v.re * wr[2 * j + 1] + (double)v.im * wr[2 * j];
+    }
+    out[i].re = (float)ar;
+    out[i].im = (float)ai;
+  }
+  free(ft);
+  free(wr);
+}
+
 /* ---- gr_firdes ------------------------------------------------------------------------------ */
 static double izero(double x) { /* gr_firdes.cc:35-51 */
   double sum, u, halfx, temp;

@@ -127,6 +127,13 @@ int orc_arb_general_work(orc_arb_state* s, const orc_cpx* in, int ninput, orc_cp
  * Arrays may be NULL.  Same return values and state update as general_work. */
 int orc_arb_schedule(orc_arb_state* s, int ninput, int noutput, int* count_of, unsigned short* filt_of, float* acc_of,
                      int* consumed);
+/* gr_pfb_decimator_ccf::work (gr_pfb_decimator_ccf.cc:44-65 ctor, :75-110 set_taps, :127-175 work): decim
+ * branch filters (gr_fir_ccf, generic order here) feeding a decim-point BACKWARD DFT of which bin `channel` is
+ * kept.  ins[s] = stream s from its first history item (history = taps_per_filter).  The DFT bin is
+ * evaluated in float64 and rounded once, like orc_dft (FFTW is third party and absent). */
+int orc_pfb_decimator_taps_per_filter(int decim, int ntaps);
+void orc_pfb_decimator_ccf(int decim, const float* taps, int ntaps, unsigned channel, const orc_cpx* const* ins,
+                           long noutput, orc_cpx* out);
 /* gr_firdes (gr_firdes.cc:57-147,601-655,720-782): tap / window design on the host. */
 int orc_firdes_window(int win_type, int ntaps, double beta, float* out);
 int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win_type, double beta, float* out, int cap);

@@ -371,3 +371,18 @@ def run_general(block, x, chunk_out, rate):
             break
         first = False
     return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
+# ---- gr_pfb_decimator_ccf ---------------------------------------------------------------------------
+def pfb_decimator_ccf(decim, taps, channel, x):
+    """x: interleaved stream (len multiple of decim; stream s = x[m*decim + s], gr_stream_to_streams).  Zero history
+    (taps_per_filter - 1 items per stream) is prepended.  Returns the len(x)/decim outputs."""
+    t = np.ascontiguousarray(taps, np.float32)
+    x = np.ascontiguousarray(x, np.complex64)
+    T = lib().orc_pfb_decimator_taps_per_filter(int(decim), len(t))
+    n = len(x) // decim
+    streams = [np.concatenate([np.zeros(T - 1, np.complex64), x[s::decim][:n]]) for s in range(decim)]
+    ptrs = (C.c_void_p * decim)(*[s.ctypes.data for s in streams])
+    out = np.zeros(max(n, 1), np.complex64)
+    lib().orc_pfb_decimator_ccf(int(decim), _p(t), len(t), int(channel), ptrs, C.c_long(n), _p(out))
+    return out[:n]

@@ -15,6 +15,7 @@
 #include <gr_freq_xlating_fir_filter_ccf.h>
 #include <gr_pfb_channelizer_ccf.h>
 #include <gr_pfb_arb_resampler_ccf.h>
+#include <gr_pfb_decimator_ccf.h>
 #include <gr_fft_vcc.h>
 #include <gr_quadrature_demod_cf.h>
 #include <gr_math.h>
@@ -90,6 +91,9 @@ grref_block* grref_make_pfb_arb_resampler_ccf(float rate, const float* taps, int
   return guarded([&] {
     return gr_block_sptr(gr_make_pfb_arb_resampler_ccf(rate, std::vector<float>(taps, taps + ntaps), filter_size));
   });
+}
+grref_block* grref_make_pfb_decimator_ccf(unsigned decim, const float* taps, int ntaps, unsigned channel) {
+  return guarded([&] { return gr_block_sptr(gr_make_pfb_decimator_ccf(decim, std::vector<float>(taps, taps + ntaps), channel)); });
 }
 grref_block* grref_make_fft_vcc(int fft_size, int forward, const float* window, int nwin, int shift) {
   return guarded([&] {

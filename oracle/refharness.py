@@ -44,7 +44,7 @@ def dir_makers():
         "grref_make_pfb_channelizer_ccf", "grref_make_fft_vcc", "grref_make_quadrature_demod_cf",
         "grref_make_clock_recovery_mm_ff", "grref_make_pager_slicer_fb", "grref_make_binary_slicer_fb",
         "grref_make_map_bb", "grref_make_unpack_k_bits_bb", "grref_make_correlate_access_code_bb",
-        "grref_make_pfb_arb_resampler_ccf",
+        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf",
     ]
 
 
@@ -180,6 +180,30 @@ def run_arb(block, x, rate, chunk_out=None):
             break
         first = False
     return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
+def pfb_decimator_ccf(decim, taps, channel):
+    t = np.ascontiguousarray(taps, np.float32)
+    return RefBlock(lib().grref_make_pfb_decimator_ccf(int(decim), _fp(t), len(t), int(channel)), np.complex64, np.complex64,
+                    nin=int(decim))
+
+
+def run_pfb_decimator(block, x, decim, chunk=None):
+    """gr_stream_to_streams -> gr_pfb_decimator_ccf over the interleaved stream x.  The first work() after set_taps
+    returns 0 (gr_pfb_decimator_ccf.cc:136-139)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    n = len(x) // decim
+    hist = block.history
+    keep = [aligned_stream(x[s::decim][:n], hist, np.complex64) for s in range(decim)]
+    out = np.zeros(max(n, 1), np.complex64)
+    assert block.general_work(min(n, 8), [k[1] for k in keep], [n + hist - 1] * decim, out) == 0
+    done, step = 0, chunk or n
+    while done < n:
+        m = min(step, n - done)
+        r = block.general_work(m, [k[1] + done * 8 for k in keep], [m + hist - 1] * decim, out[done:])
+        assert r == m
+        done += r
+    return out[:n]
 
 
 def fft_vcc(fft_size, forward, window, shift=False):

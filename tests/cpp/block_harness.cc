@@ -103,6 +103,15 @@ static int cmd_run(int argc, char** argv) {
       for (unsigned j = 0; j < M; j++)
         memcpy(streams[j].data() + m * sizeof(gr_complex), in.data() + (m * M + j) * sizeof(gr_complex), sizeof(gr_complex));
     out = run_block(*b, streams, max_noutput);
+  } else if (kind == "pfbdec") {
+    const unsigned M = (unsigned)atoi(argv[3]);
+    auto b = gr_make_pfb_decimator_ccf(M, floats(argv[4]), (unsigned)atoi(argv[5]));
+    const size_t n = in.size() / sizeof(gr_complex) / M;
+    streams.assign(M, std::vector<char>(n * sizeof(gr_complex)));
+    for (size_t m = 0; m < n; m++)
+      for (unsigned j = 0; j < M; j++)
+        memcpy(streams[j].data() + m * sizeof(gr_complex), in.data() + (m * M + j) * sizeof(gr_complex), sizeof(gr_complex));
+    out = run_block(*b, streams, max_noutput);
   } else if (kind == "arb") {
     auto b = gr_make_pfb_arb_resampler_ccf((float)atof(argv[3]), floats(argv[4]), (unsigned)atoi(argv[5]));
     out = run_block(*b, streams, max_noutput);

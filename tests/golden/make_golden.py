@@ -191,6 +191,13 @@ def fixtures_next():
             R.set_fir_impl(impl)
             fx["arb_%s_y_%s" % (tag, nm)] = R.run_arb(R.pfb_arb_resampler_ccf(rate, taps, nf), x, rate, chunk_out=211)
     R.set_fir_impl(1)
+    # rank 3: gr_pfb_decimator_ccf, one channel out of 10 / 32 (tile path) and out of 160 (cfg3's channel count)
+    for tag, M, T, ch in (("m10", 10, 7, 3), ("m32", 32, 12, 31), ("m160", 160, 16, 7)):
+        taps = (rng.standard_normal(M * T - 3) * 0.1).astype(np.float32)
+        xin = (rng.standard_normal(M * 120) + 1j * rng.standard_normal(M * 120)).astype(np.complex64)
+        fx["pfbdec_%s_taps" % tag], fx["pfbdec_%s_x" % tag] = taps, xin
+        fx["pfbdec_%s_args" % tag] = np.array([M, ch])
+        fx["pfbdec_%s_y" % tag] = R.run_pfb_decimator(R.pfb_decimator_ccf(M, taps, ch), xin, M, chunk=50)
     return fx
 
 

@@ -113,6 +113,20 @@ def test_pfb_channelizer_block(harness, tmp_path, orc, M, T, os_rate):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_pfb_decimator_block(harness, tmp_path, orc):
+    """gr_make_pfb_decimator_ccf under the scheduler: decim input streams (gr_stream_to_streams), a sync block with
+    history = taps_per_filter."""
+    rng = np.random.default_rng(29)
+    for M, T, ch in ((8, 5, 3), (160, 16, 7)):
+        x = (rng.standard_normal(M * 900) + 1j * rng.standard_normal(M * 900)).astype(np.complex64)
+        taps = (rng.standard_normal(M * T - 2) * 0.1).astype(np.float32)
+        y = run(harness, tmp_path, ["pfbdec", M, taps, ch], x, np.complex64, max_noutput=256)
+        want = orc.pfb_decimator_ccf(M, taps, ch, x)
+        assert len(want) - 256 <= len(y) <= len(want) and relerr(y, want[:len(y)]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
 def test_pfb_arb_resampler_block(harness, tmp_path, orc):
     """gr_make_pfb_arb_resampler_ccf under the scheduler: forecast = noutput + history - 1 (gr_block default),
     consume_each honoured, first general_work returns 0; bit identical to the generic-order reference."""

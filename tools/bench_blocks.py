@@ -110,6 +110,19 @@ def main():
                                            "MSps_in": rows * M / ms / 1e3, "alg_GBps": byt / ms / 1e6,
                                            "frac_hbm": byt / ms / 1e6 / peak}
     del xin, yout
+    # pfb_decimator_ccf: one channel out of M; algorithmic bytes 8 B per input sample (+ 8 B per output = 1/M of that)
+    for Md, Td, tag in ((32, 16, "pfb_decimator_ccf_m32_t16"), (160, 16, "pfb_decimator_ccf_m160_t16")):
+        nrow = 80_000_000 // Md
+        dt = np.asarray(firdes.low_pass(1.0, float(Md), 0.4, 0.2), np.float32)
+        dt = np.resize(dt, Md * Td).astype(np.float32)
+        dec = B.pfb_decimator_ccf(Md, dt, 3)
+        xr = torch.view_as_complex(torch.randn((nrow + Td - 1, Md, 2), generator=g, device=dev))
+        yo = torch.empty(nrow, dtype=torch.complex64, device=dev)
+        dec.work_device(1, xr, yo)
+        ms = timeit(lambda: dec.work_device(nrow, xr, yo), 10, flush)
+        byt = 8.0 * nrow * Md + 8.0 * nrow
+        out[tag] = {"ms": ms, "MSps_in": nrow * Md / ms / 1e3, "alg_GBps": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / peak}
+        del xr, yo
     # raw copy rates of the box (pinned), 800 MB like one bench block
     h = torch.empty(100_000_000, dtype=torch.complex64, pin_memory=True)
     dd = torch.empty(100_000_000, dtype=torch.complex64, device=dev)
