@@ -187,42 +187,66 @@ def run_ours(args):
     plan = sharding.TimeShardPlan(world, rank, R, halo)
     ring = sharding.RingExchanger(plan)
     state = torch.zeros(ch.state_bytes(), dtype=torch.uint8, device=dev)
-    halo_in = x[: Th + halo] if world > 1 else None
-    tail_rows = x[x.shape[0] - (Th + halo):] if world > 1 else None
+    # Two copies of the input block, used alternately: the NCCL halo exchange of step s+1 writes the head of one
+    # while the front of step s still reads the other.  The exchange only depends on INPUT rows, so it is posted one
+    # step ahead on its own stream: the rendezvous of the two neighbours (which are one tail slot apart in time by
+    # construction) then never stalls a front, and its kernels do not sit on SMs next to the persistent FFT CTAs.
+    xbuf = [x, x.clone()] if world > 1 else [x]
     stream = torch.cuda.current_stream().cuda_stream
     tail_ts = torch.cuda.Stream() if world > 1 else None
+    halo_ts = torch.cuda.Stream() if world > 1 else None
+    halo_ev, front_ev = [None, None], [None, None]
+
+    def post_halo(s):
+        """NCCL send/recv of the input halo of step s into xbuf[s % 2] (tap history + warm-up rows of the left block)."""
+        buf = xbuf[s % 2]
+        with torch.cuda.stream(halo_ts):
+            if front_ev[s % 2] is not None:
+                halo_ts.wait_event(front_ev[s % 2])                # the front of step s-2 has read this copy's head
+            works = ring.exchange_halo(buf[buf.shape[0] - (Th + halo):], buf[: Th + halo], s)
+            ring.wait_all(works)
+            halo_ev[s % 2] = torch.cuda.Event()
+            halo_ev[s % 2].record(halo_ts)
 
     def drain():
         if world > 1:
             with torch.cuda.stream(tail_ts):
                 ring.finish()
             torch.cuda.current_stream().wait_stream(tail_ts)
+            torch.cuda.current_stream().wait_stream(halo_ts)
         ch.join(stream)
 
     def step(s, last):
         if world == 1:
             ch.process_device(x, R, stream)     # on torch's current stream: the timing events live there
             return
-        works = ring.exchange_halo(tail_rows, halo_in, s)          # NCCL send/recv of the input halo
-        ring.wait_all(works)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(halo_ev[s % 2])                              # this step's halo has landed
         ch.seek_async(plan.abs_start(s) - halo, stream)
         if plan.front_after_own_tail:
-            # world >= 3: between two of its tails a rank has (world - 1) tail slots of idle time, more than one front
-            # takes, so the front does not need to run underneath the rank's own tail (where the two slow each other
-            # down by 20-50 %): the serial tail chain, which caps the whole job, then runs at its stand-alone speed
-            torch.cuda.current_stream().wait_stream(tail_ts)
-        ch.process_front_device(x, halo + R, stream)                # all ranks concurrently
+            # 2+ ranks: the front runs after the rank's own previous tail instead of underneath it (the two slow each
+            # other down by 20-50 %), so the serial tail chain, which caps the whole job, runs at its stand-alone speed
+            cur.wait_stream(tail_ts)
+        ch.process_front_device(xbuf[s % 2], halo + R, stream)        # all ranks concurrently
+        front_ev[s % 2] = torch.cuda.Event()
+        front_ev[s % 2].record(cur)
+        post_halo(s + 1)                                            # one exchange per step, one step ahead
         # The tails form ONE serial chain over all blocks of all ranks (block b's clock recovery starts from block
-        # b-1's final loop state), so they run on a side stream: this rank's main stream goes on to the next halo
-        # exchange and front while its tail waits for the left neighbour's state.
+        # b-1's final loop state), so they run on a side stream: this rank's main stream goes on to the next front
+        # while its tail waits for the left neighbour's state.
         with torch.cuda.stream(tail_ts):
             ts = tail_ts.cuda_stream
+            # the NCCL receive spins on an SM until the left neighbour's tail has finished: posted before the front is
+            # done it takes that SM away from the front's persistent one-CTA-per-SM FFT, which then needs a second wave
+            tail_ts.wait_event(front_ev[s % 2])
             if ring.recv_state(state, s):                           # loop state of block b-1 (ring)
                 ch.import_state(state, ts)
             ch.process_tail_device(ts)
             ch.export_state(state, ts)
             ring.send_state(state, s, last)
 
+    if world > 1:
+        post_halo(0)
     total_steps = args.warmup + args.steps
     for s in range(args.warmup):
         step(s, total_steps - 1)
