@@ -36,6 +36,8 @@ struct FftArgs {
   int threads_per_row;
   int row_stride;        // smem float2 per row (N + padding)
   int pad_div;           // phys(i) = i + i / pad_div  (0 = no padding)
+  int* counter;          // staged kernels: row groups are claimed from this counter (zeroed before the launch);
+                         // nullptr = static assignment g = blockIdx.x + k * gridDim.x
 };
 
 __device__ __forceinline__ int fft_phys(int i, int pad_div) { return pad_div ? i + i / pad_div : i; }
@@ -161,17 +163,41 @@ __device__ __forceinline__ void fft_fixed_body(const FftArgs& a) {
     mbar_expect_tx(full, bytes);
     bulk_g2s(base + work, a.in + r0 * (long)N, bytes, full);
   };
+  // Row groups are CLAIMED, not assigned (staged kernels): a CTA that shares its SM with a CTA of another kernel
+  // (the clock-recovery kernel of the previous block, an NCCL receive spinning on its peer) or that is not resident
+  // at all for a while simply takes fewer groups, instead of the whole launch waiting for it.  A CTA holds its
+  // current group and the next one (whose bulk load it issues as soon as the stage buffer is free) and claims the
+  // one after that at the top of an iteration, so that the atomic's latency hides under the butterflies.
+  __shared__ int s_claim[2];
+  int stat = blockIdx.x;  // static sequence when there is no counter
+  const int ng = (int)min(ngroups, 0x7fffffffL);
+  auto claim = [&]() -> int {
+    if (STAGED && a.counter) return atomicAdd(a.counter, 1);
+    const int v = stat;
+    stat += gridDim.x;
+    return v;
+  };
+  int g, gn;
   if (STAGED) {
     if (threadIdx.x == 0) {
       mbar_init(full, 1);
       mbar_init_fence();
-      if ((long)blockIdx.x < ngroups) issue(blockIdx.x);
+      const int g0 = claim();
+      if (g0 < ng) issue(g0);
+      s_claim[0] = g0;
+      s_claim[1] = claim();
     }
     __syncthreads();
+    g = s_claim[0];
+    gn = s_claim[1];
+  } else {
+    g = claim();
+    gn = claim();
   }
-  int it = 0;
-  for (long g = blockIdx.x; g < ngroups; g += gridDim.x, it++) {
-    const long row = g * a.rows_per_cta + lrow;
+  for (int it = 0; g < ng; it++) {
+    int gnn = 0;
+    if (!STAGED || threadIdx.x == 0) gnn = claim();
+    const long row = (long)g * a.rows_per_cta + lrow;
     const bool row_ok = lrow < a.rows_per_cta && row < a.nrows;
     const float2* st = nullptr;
     if (STAGED) {
@@ -182,11 +208,11 @@ __device__ __forceinline__ void fft_fixed_body(const FftArgs& a) {
       fft_pass<R0, DIR, true, true, PADDIV, STAGED>(a, N, 1, j, row_ok, row, srow, nullptr, st);
       if (STAGED) {
         __syncthreads();  // every thread has its inputs in registers: the stage can be refilled
-        if (threadIdx.x == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x);
+        if (threadIdx.x == 0 && gn < ng) issue(gn);
       }
     } else {
       fft_pass<R0, DIR, true, false, PADDIV, STAGED>(a, N, 1, j, row_ok, row, srow, nullptr, st);  // ends with a barrier
-      if (STAGED && threadIdx.x == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x);
+      if (STAGED && threadIdx.x == 0 && gn < ng) issue(gn);
       if (NP == 2) {
         fft_pass<R1, DIR, false, true, PADDIV>(a, N, R0, j, row_ok, row, srow, a.tw[1]);
       } else {
@@ -198,7 +224,16 @@ __device__ __forceinline__ void fft_fixed_body(const FftArgs& a) {
           fft_pass<R3, DIR, false, true, PADDIV>(a, N, R0 * R1 * R2, j, row_ok, row, srow, a.tw[3]);
         }
       }
-      __syncthreads();  // the next group's first pass overwrites the rows read above
+    }
+    if (STAGED) {
+      if (threadIdx.x == 0) { s_claim[0] = gn; s_claim[1] = gnn; }
+      __syncthreads();  // publishes the claims; also: the next group's first pass overwrites the rows read above
+      g = s_claim[0];
+      gn = s_claim[1];
+    } else {
+      if (NP != 1) __syncthreads();  // the next group's first pass overwrites the rows read above
+      g = gn;
+      gn = gnn;
     }
   }
 }

@@ -27,6 +27,9 @@ struct FftPlan {
   size_t smem = 0;
   int threads = 0;
   int max_ctas = 0;
+  static const int kCounters = 16;
+  int* d_counters = nullptr;  // row-group claim counters of the staged kernel, one per launch in flight
+  unsigned counter_turn = 0;
   std::string desc;
 };
 
@@ -179,6 +182,10 @@ FftPlan* fft_plan_create(int n, int dir, bool coresident) {
       p->kernel_staged = nullptr;
     } else {
       p->max_ctas_staged = ps * sm_count();
+      if (!getenv("GRCUDA_FFT_STATIC_ROWS") && cudaMalloc(&p->d_counters, FftPlan::kCounters * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        p->d_counters = nullptr;  // static row assignment
+      }
     }
   }
   char buf[256];
@@ -192,6 +199,7 @@ FftPlan* fft_plan_create(int n, int dir, bool coresident) {
 void fft_plan_destroy(FftPlan* p) {
   if (!p) return;
   if (p->d_tw) cudaFree(p->d_tw);
+  if (p->d_counters) cudaFree(p->d_counters);
   delete p;
 }
 
@@ -218,6 +226,10 @@ int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, con
                         !getenv("GRCUDA_FFT_NO_TMA");
     if (staged) {
       const int grid = (int)std::min<long>(ngroups, p->max_ctas_staged);
+      if (p->d_counters) {  // a fresh claim counter per launch (a small ring: launches of one plan may overlap)
+        a.counter = p->d_counters + (p->counter_turn++ % FftPlan::kCounters);
+        if (cudaMemsetAsync(a.counter, 0, sizeof(int), stream) != cudaSuccess) { cudaGetLastError(); a.counter = nullptr; }
+      }
       p->kernel_staged<<<grid, p->threads, p->smem_staged, stream>>>(a);
     } else {
       const int grid = (int)std::min<long>(ngroups, p->max_ctas);
