@@ -801,6 +801,111 @@ int grcuda_pfb_decimator_ccf_work(grcuda_pfb_decim* h, int noutput_items, const 
 }  // extern "C"
 
 // =============================================================================================
+// 8f rank 4: gr_fft_filter_ccc (complex taps, history 1, output in blocks of nsamples)
+// =============================================================================================
+// The reference convolves by overlap-add in the frequency domain (gri_fft_filter_ccc_generic.cc:120-165) because
+// that is the cheap way on a CPU; what it computes is y[n] = sum_k taps[k] x[n - k] (x[<0] = 0), decimated, and
+// its own QA checks it against gr_fir_filter_ccc (qa_fft_filter.py).  On the GPU the same block is the direct-form
+// decimating FIR with complex taps (fir_decim_kernel: shared-memory window, register-tiled outputs) plus what the
+// block interface requires: history 1 (the plan carries the last ntaps-1 input samples itself, as the reference
+// carries its overlap-add tail), output_multiple = nsamples = fftsize - ntaps + 1 with
+// fftsize = 2 * 2^ceil(log2 ntaps) (:103-118), set_taps deferred to the next work(), which returns 0 and clears the
+// carried state (:62-69).  Direct form costs ntaps MACs per input sample: filters beyond the kernel's shared-memory
+// tile (a few thousand taps) are refused with GRCUDA_EUNSUPPORTED rather than run slowly.
+struct grcuda_fft_filter : PlanBase {
+  int decim = 1, ntaps = 0, nsamples = 1;
+  bool updated = false;
+  std::vector<float> new_taps;  // interleaved re, im
+  FirCore core;
+  DevBuf d_buf, d_carry;        // [carry | new input] contiguous; the last ntaps-1 samples seen
+  static int nsamples_for(int nt) {
+    const int fftsize = (int)(2 * pow(2.0, ceil(log((double)nt) / log(2.0))));  // :106
+    return fftsize - nt + 1;
+  }
+  int build(const std::vector<float>& t_ri) {
+    cudaDeviceSynchronize();
+    ntaps = (int)t_ri.size() / 2;
+    nsamples = nsamples_for(ntaps);
+    std::vector<float> rev(t_ri.size());
+    for (int k = 0; k < ntaps; k++) { rev[2 * k] = t_ri[2 * (ntaps - 1 - k)]; rev[2 * k + 1] = t_ri[2 * (ntaps - 1 - k) + 1]; }
+    core.decim = decim;
+    int rc = core.upload(rev.data(), ntaps, true);
+    if (rc) return rc;
+    const size_t cb = (size_t)std::max(ntaps - 1, 1) * sizeof(float2);
+    if ((rc = d_carry.reserve(cb))) return rc;
+    GRB_CUDA(cudaMemset(d_carry.p, 0, cb));  // the tail is cleared by set_taps (:67-69)
+    return GRCUDA_OK;
+  }
+};
+
+extern "C" {
+
+grcuda_fft_filter* grcuda_fft_filter_ccc_create(int decimation, const grcuda_complex* taps, int ntaps) {
+  if (decimation < 1 || ntaps < 1 || !taps) { set_error(GRCUDA_EINVAL, "fft_filter_ccc: bad decimation / taps"); return nullptr; }
+  if (!device_ok()) return nullptr;
+  grcuda_fft_filter* h = new grcuda_fft_filter;
+  h->decim = decimation;
+  if (h->base_init() || h->build(std::vector<float>((const float*)taps, (const float*)taps + 2 * (size_t)ntaps))) { delete h; return nullptr; }
+  return h;
+}
+void grcuda_fft_filter_ccc_destroy(grcuda_fft_filter* h) { delete h; }
+int grcuda_fft_filter_ccc_set_taps(grcuda_fft_filter* h, const grcuda_complex* taps, int ntaps) {
+  if (ntaps < 1 || !taps) return set_error(GRCUDA_EINVAL, "fft_filter_ccc: no taps");
+  std::lock_guard<std::mutex> lk(h->mu);  // gr_fft_filter_ccc.cc:75-79: deferred to the next work()
+  h->new_taps.assign((const float*)taps, (const float*)taps + 2 * (size_t)ntaps);
+  h->updated = true;
+  return GRCUDA_OK;
+}
+int grcuda_fft_filter_ccc_output_multiple(grcuda_fft_filter* h) { return h->nsamples; }  // :66
+int grcuda_fft_filter_ccc_decimation(grcuda_fft_filter* h) { return h->decim; }
+unsigned grcuda_fft_filter_ccc_history(grcuda_fft_filter* h) { (void)h; return 1; }        // :58
+// d_in: noutput_items * decimation NEW items (history 1); noutput_items must be a multiple of output_multiple()
+int grcuda_fft_filter_ccc_work_device(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* d_in,
+                                      grcuda_complex* d_out, void* stream) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {  // :85-90: "output multiple may have changed"
+      h->updated = false;
+      int rc = h->build(h->new_taps);
+      return rc ? rc : 0;
+    }
+  }
+  if (noutput_items <= 0) return 0;
+  if (noutput_items % h->nsamples) return set_error(GRCUDA_EINVAL, "fft_filter_ccc: noutput_items %d is not a multiple of %d (:92)", noutput_items, h->nsamples);
+  cudaStream_t s = h->pick(stream);
+  const size_t nin = (size_t)noutput_items * h->decim, nc = (size_t)h->ntaps - 1;
+  int rc;
+  if ((rc = h->d_buf.reserve((nc + nin) * sizeof(float2)))) return rc;
+  float2* buf = h->d_buf.as<float2>();
+  if (nc) GRB_CUDA(cudaMemcpyAsync(buf, h->d_carry.p, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  GRB_CUDA(cudaMemcpyAsync(buf + nc, d_in, nin * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  if ((rc = h->core.launch(buf, (float2*)d_out, noutput_items, false, 0.0, 0, s))) return rc;
+  if (nc) GRB_CUDA(cudaMemcpyAsync(h->d_carry.p, buf + nin, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  return noutput_items;
+}
+int grcuda_fft_filter_ccc_work(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* in, grcuda_complex* out) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {
+      h->updated = false;
+      int rc = h->build(h->new_taps);
+      return rc ? rc : 0;
+    }
+  }
+  if (noutput_items <= 0) return 0;
+  const size_t nin = (size_t)noutput_items * h->decim;
+  int rc;
+  if ((rc = h->d_in.reserve(nin * sizeof(float2))) || (rc = h->d_out.reserve((size_t)noutput_items * sizeof(float2)))) return rc;
+  if ((rc = h->stager.h2d(h->d_in.p, in, nin * sizeof(float2), h->stream))) return rc;
+  const int r = grcuda_fft_filter_ccc_work_device(h, noutput_items, (const grcuda_complex*)h->d_in.p, (grcuda_complex*)h->d_out.p, h->stream);
+  if (r <= 0) return r;
+  if ((rc = h->stager.d2h(out, h->d_out.p, (size_t)r * sizeof(float2), h->stream))) return rc;
+  return r;
+}
+
+}  // extern "C"
+
+// =============================================================================================
 // a5 / a6: gr_fft_vcc
 // =============================================================================================
 struct grcuda_fft : PlanBase {

@@ -331,6 +331,53 @@ class pfb_decimator_ccf(_Block):
         return np.concatenate(out) if out else np.zeros(0, np.complex64)
 
 
+class fft_filter_ccc(_Block):
+    """gr_make_fft_filter_ccc(int decimation, const std::vector<gr_complex>& taps) (gr_fft_filter_ccc.cc:46-106)."""
+    _destroy = "grcuda_fft_filter_ccc_destroy"
+    in_dtype, out_dtype = np.complex64, np.complex64
+
+    def __init__(self, decimation, taps):
+        t = _c64(taps)
+        self.L = _l.load()
+        self.decim = int(decimation)
+        self.h = _l.check_handle(self.L.grcuda_fft_filter_ccc_create(self.decim, _p(t), len(t)))
+
+    def set_taps(self, taps):
+        t = _c64(taps)
+        _l.check(self.L.grcuda_fft_filter_ccc_set_taps(self.h, _p(t), len(t)))
+
+    def output_multiple(self):
+        return int(self.L.grcuda_fft_filter_ccc_output_multiple(self.h))
+
+    def history(self):
+        return 1
+
+    def decimation(self):
+        return self.decim
+
+    def work(self, noutput_items, in_items):
+        x = _c64(in_items)
+        out = np.empty(max(noutput_items, 0), np.complex64)
+        n = _l.check(self.L.grcuda_fft_filter_ccc_work(self.h, int(noutput_items), _p(x), _p(out)))
+        return out[:n]
+
+    def work_device(self, noutput_items, d_in, d_out):
+        return _l.check(self.L.grcuda_fft_filter_ccc_work_device(self.h, int(noutput_items), _dp(d_in), _dp(d_out),
+                                                                 _torch_stream()))
+
+    def run(self, x, blocks_per_call=None):
+        """vector_source -> block -> vector_sink: whole blocks of output_multiple() items, like the scheduler."""
+        x = _c64(x)
+        ns = self.output_multiple()
+        nblocks = (len(x) // self.decim) // ns
+        outs, done, step = [], 0, (blocks_per_call or max(nblocks, 1)) * ns
+        while done < nblocks * ns:
+            n = min(step, nblocks * ns - done)
+            outs.append(self.work(n, x[done * self.decim: (done + n) * self.decim]))
+            done += n
+        return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
 class fft_vcc(_Block):
     """gr_make_fft_vcc(int fft_size, bool forward, const std::vector<float>& window, bool shift=false)
     (gr_fft_vcc.cc:34-64, gr_fft_vcc_fftw.cc:51-103).  IndexError for fft_size <= 0."""

@@ -10,6 +10,7 @@
  *     gr_make_pfb_channelizer_ccf                            filter/gr_pfb_channelizer_ccf.h:31-34
  *     gr_make_pfb_arb_resampler_ccf                          filter/gr_pfb_arb_resampler_ccf.h:36-39
  *     gr_make_pfb_decimator_ccf                              filter/gr_pfb_decimator_ccf.h
+ *     gr_make_fft_filter_ccc                                 filter/gr_fft_filter_ccc.h
  *     gr_make_fft_vcc                                        general/gr_fft_vcc.h:32-33
  *     gr_make_quadrature_demod_cf                            general/gr_quadrature_demod_cf.h
  *     digital_make_clock_recovery_mm_ff                      gr-digital/include/digital_clock_recovery_mm_ff.h:37-40
@@ -213,6 +214,36 @@ class gr_pfb_channelizer_ccf : public gr_block {
 inline gr_pfb_channelizer_ccf_sptr gr_make_pfb_channelizer_ccf(unsigned int numchans, const std::vector<float>& taps,
                                                                float oversample_rate) {
   return GR_B200_INITIAL_SPTR(new gr_pfb_channelizer_ccf(numchans, taps, oversample_rate));
+}
+
+/* ---- gr_fft_filter_ccc (filter/gr_fft_filter_ccc.cc:46-106) ---------------------------------------------- */
+class gr_fft_filter_ccc;
+typedef GR_B200_SPTR(gr_fft_filter_ccc) gr_fft_filter_ccc_sptr;
+gr_fft_filter_ccc_sptr gr_make_fft_filter_ccc(int decimation, const std::vector<gr_complex>& taps);
+class gr_fft_filter_ccc : public gr_sync_decimator {
+  friend gr_fft_filter_ccc_sptr gr_make_fft_filter_ccc(int, const std::vector<gr_complex>&);
+  grcuda_fft_filter* d_plan;
+  gr_fft_filter_ccc(int decimation, const std::vector<gr_complex>& taps)
+      : gr_sync_decimator("fft_filter_ccc", gr_make_io_signature(1, 1, sizeof(gr_complex)),
+                          gr_make_io_signature(1, 1, sizeof(gr_complex)), decimation),
+        d_plan(grcuda_fft_filter_ccc_create(decimation, cin(taps.data()), (int)taps.size())) {
+    if (!d_plan) throw_last_error("gr_fft_filter_ccc");
+    set_history(1);                                                                          /* :58 */
+    set_output_multiple(grcuda_fft_filter_ccc_output_multiple(d_plan));                      /* :66 */
+  }
+ public:
+  ~gr_fft_filter_ccc() { grcuda_fft_filter_ccc_destroy(d_plan); }
+  void set_taps(const std::vector<gr_complex>& taps) {          /* :75-79: takes effect at the next work() */
+    check_rc(grcuda_fft_filter_ccc_set_taps(d_plan, cin(taps.data()), (int)taps.size()), "set_taps");
+  }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    int r = check_rc(grcuda_fft_filter_ccc_work(d_plan, noutput_items, cin(input_items[0]), cout_(output_items[0])), "work");
+    set_output_multiple(grcuda_fft_filter_ccc_output_multiple(d_plan));                      /* :88 */
+    return r;
+  }
+};
+inline gr_fft_filter_ccc_sptr gr_make_fft_filter_ccc(int decimation, const std::vector<gr_complex>& taps) {
+  return GR_B200_INITIAL_SPTR(new gr_fft_filter_ccc(decimation, taps));
 }
 
 /* ---- gr_pfb_decimator_ccf (filter/gr_pfb_decimator_ccf.cc:35-175) -------------------------------------- */

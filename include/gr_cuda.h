@@ -285,6 +285,24 @@ int grcuda_pfb_decimator_ccf_work_interleaved(grcuda_pfb_decim* h, int noutput_i
 int grcuda_pfb_decimator_ccf_work_device(grcuda_pfb_decim* h, long noutput_items, const grcuda_complex* d_in_rows,
                                          grcuda_complex* d_out, void* stream);
 
+/* ---- 8f rank 4  gr_fft_filter_ccc ---------------------------------------------------------------
+ * replaces gr_fft_filter_ccc::work and gri_fft_filter_ccc_generic (gr_fft_filter_ccc.cc:46-106,
+ * gri_fft_filter_ccc_generic.cc:62-165): y[n] = sum_k taps[k] x[n-k], decimated, complex taps.  Same
+ * block contract: history 1 (the plan carries the last ntaps-1 samples, as the reference carries its
+ * overlap-add tail), output_multiple = nsamples = fftsize - ntaps + 1, set_taps deferred to the next work()
+ * which returns 0 and clears the carried state.  Computed in direct form on the GPU (see gr_cuda.cu);
+ * within 1e-6 of the reference (bar 1e-4).  GRCUDA_EUNSUPPORTED for filters beyond the FIR tile. */
+typedef struct grcuda_fft_filter grcuda_fft_filter;
+grcuda_fft_filter* grcuda_fft_filter_ccc_create(int decimation, const grcuda_complex* taps, int ntaps);
+void grcuda_fft_filter_ccc_destroy(grcuda_fft_filter* h);
+int grcuda_fft_filter_ccc_set_taps(grcuda_fft_filter* h, const grcuda_complex* taps, int ntaps);
+int grcuda_fft_filter_ccc_output_multiple(grcuda_fft_filter* h);
+int grcuda_fft_filter_ccc_decimation(grcuda_fft_filter* h);
+unsigned grcuda_fft_filter_ccc_history(grcuda_fft_filter* h);
+int grcuda_fft_filter_ccc_work(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* in, grcuda_complex* out);
+int grcuda_fft_filter_ccc_work_device(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* d_in,
+                                      grcuda_complex* d_out, void* stream);
+
 /* ---- flagship pipeline: wideband -> PFB -> batched 4FSK demod -> sync search ---------------
  * One object that owns the HBM-resident intermediates and per-channel loop state and runs
  *   pfb_channelizer_ccf -> quadrature_demod_cf -> fir_filter_fff(RRC) -> clock_recovery_mm_ff

@@ -613,6 +613,69 @@ void orc_pfb_decimator_ccf(int decim, const float* taps, int ntaps, unsigned cha
   free(wr);
 }
 
+
+/* ---- gr_fft_filter_ccc ------------------------------------------------------------------------- */
+int orc_fftfilt_set_taps(orc_fftfilt_state* s, const orc_cpx* taps, int ntaps) { /* gri_fft_filter_ccc_generic.cc:62-118 */
+  s->ntaps = ntaps;
+  s->fftsize = (int)(2 * pow(2.0, ceil(log((double)ntaps) / log(2.0)))); /* :106 */
+  s->nsamples = s->fftsize - s->ntaps + 1;
+  free(s->xformed_taps);
+  free(s->tail);
+  s->xformed_taps = (orc_cpx*)malloc(sizeof(orc_cpx) * (size_t)s->fftsize);
+  s->tail = (orc_cpx*)calloc((size_t)(ntaps > 1 ? ntaps - 1 : 1), sizeof(orc_cpx)); /* :67-69: the tail is cleared */
+  orc_cpx* in = (orc_cpx*)calloc((size_t)s->fftsize, sizeof(orc_cpx));
+  const float scale = (float)(1.0 / s->fftsize); /* :74 `float scale = 1.0 / d_fftsize` */
+  for (int i = 0; i < ntaps; i++) { /* complex<float> * float */
+    in[i].re = taps[i].re * scale;
+    in[i].im = taps[i].im * scale;
+  }
+  orc_dft(in, s->xformed_taps, s->fftsize, 1);
+  free(in);
+  return s->nsamples;
+}
+int orc_fftfilt_init(orc_fftfilt_state* s, int decimation, const orc_cpx* taps, int ntaps) {
+  memset(s, 0, sizeof *s);
+  s->decimation = decimation;
+  return orc_fftfilt_set_taps(s, taps, ntaps);
+}
+void orc_fftfilt_free(orc_fftfilt_state* s) {
+  free(s->xformed_taps);
+  free(s->tail);
+  s->xformed_taps = s->tail = 0;
+}
+int orc_fftfilt_filter(orc_fftfilt_state* s, int nitems, const orc_cpx* input, orc_cpx* output) { /* :120-165 */
+  const int N = s->fftsize, ns = s->nsamples, tailsize = s->ntaps - 1;
+  orc_cpx* a = (orc_cpx*)malloc(sizeof(orc_cpx) * (size_t)N);
+  orc_cpx* b = (orc_cpx*)malloc(sizeof(orc_cpx) * (size_t)N);
+  int dec_ctr = 0;
+  const int ninput_items = nitems * s->decimation;
+  for (int i = 0; i < ninput_items; i += ns) {
+    memcpy(a, input + i, sizeof(orc_cpx) * (size_t)ns);
+    for (int j = ns; j < N; j++) a[j].re = a[j].im = 0;
+    orc_dft(a, b, N, 1);
+    for (int j = 0; j < N; j++) { /* complex<float> product as gcc expands it */
+      const orc_cpx x = b[j], t = s->xformed_taps[j];
+      a[j].re = x.re * t.re - x.im * t.im;
+      a[j].im = x.re * t.im + x.im * t.re;
+    }
+    orc_dft(a, b, N, 0);
+    for (int j = 0; j < tailsize; j++) {
+      b[j].re += s->tail[j].re;
+      b[j].im += s->tail[j].im;
+    }
+    int j = dec_ctr;
+    while (j < ns) {
+      *output++ = b[j];
+      j += s->decimation;
+    }
+    dec_ctr = j - ns;
+    memcpy(s->tail, b + ns, sizeof(orc_cpx) * (size_t)tailsize);
+  }
+  free(a);
+  free(b);
+  return nitems;
+}
+
 /* ---- gr_firdes ------------------------------------------------------------------------------ */
 static double izero(double x) { /* gr_firdes.cc:35-51 */
   double sum, u, halfx, temp;

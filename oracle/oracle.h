@@ -134,6 +134,20 @@ int orc_arb_schedule(orc_arb_state* s, int ninput, int noutput, int* count_of, u
 int orc_pfb_decimator_taps_per_filter(int decim, int ntaps);
 void orc_pfb_decimator_ccf(int decim, const float* taps, int ntaps, unsigned channel, const orc_cpx* const* ins,
                            long noutput, orc_cpx* out);
+/* gr_fft_filter_ccc / gri_fft_filter_ccc_generic (gr_fft_filter_ccc.cc:46-106, gri_fft_filter_ccc_generic.cc:62-165):
+ * overlap-add FFT filter with complex taps.  fftsize = 2 * 2^ceil(log2 ntaps), nsamples = fftsize - ntaps + 1
+ * (= the block's output_multiple), taps pre-scaled by 1/fftsize, tail of ntaps-1 carried between blocks.  The
+ * transforms are the float64 DFT of orc_dft (FFTW absent). */
+typedef struct {
+  int ntaps, fftsize, nsamples, decimation;
+  orc_cpx* xformed_taps; /* [fftsize] */
+  orc_cpx* tail;         /* [ntaps-1] */
+} orc_fftfilt_state;
+int orc_fftfilt_init(orc_fftfilt_state* s, int decimation, const orc_cpx* taps, int ntaps); /* returns nsamples */
+int orc_fftfilt_set_taps(orc_fftfilt_state* s, const orc_cpx* taps, int ntaps);             /* returns nsamples */
+void orc_fftfilt_free(orc_fftfilt_state* s);
+/* nitems outputs (multiple of nsamples) from nitems * decimation inputs; returns nitems */
+int orc_fftfilt_filter(orc_fftfilt_state* s, int nitems, const orc_cpx* in, orc_cpx* out);
 /* gr_firdes (gr_firdes.cc:57-147,601-655,720-782): tap / window design on the host. */
 int orc_firdes_window(int win_type, int ntaps, double beta, float* out);
 int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win_type, double beta, float* out, int cap);

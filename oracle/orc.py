@@ -34,6 +34,11 @@ class ArbState(C.Structure):
                 ("updated", C.c_int), ("taps", C.POINTER(C.c_float)), ("dtaps", C.POINTER(C.c_float))]
 
 
+class FftFiltState(C.Structure):
+    _fields_ = [("ntaps", C.c_int), ("fftsize", C.c_int), ("nsamples", C.c_int), ("decimation", C.c_int),
+                ("xformed_taps", C.c_void_p), ("tail", C.c_void_p)]
+
+
 class Rotator(C.Structure):
     _fields_ = [("phase", C.c_float * 2), ("incr", C.c_float * 2), ("counter", C.c_uint)]
 
@@ -386,3 +391,42 @@ def pfb_decimator_ccf(decim, taps, channel, x):
     out = np.zeros(max(n, 1), np.complex64)
     lib().orc_pfb_decimator_ccf(int(decim), _p(t), len(t), int(channel), ptrs, C.c_long(n), _p(out))
     return out[:n]
+
+
+# ---- gr_fft_filter_ccc ------------------------------------------------------------------------------
+class FftFilter:
+    """orc_fftfilt_*: overlap-add FFT filter with complex taps (gri_fft_filter_ccc_generic.cc)."""
+
+    def __init__(self, decim, taps):
+        t = np.ascontiguousarray(taps, np.complex64)
+        self.s = FftFiltState()
+        self.decim = int(decim)
+        self.nsamples = lib().orc_fftfilt_init(C.byref(self.s), self.decim, _p(t), len(t))
+
+    def __del__(self):
+        try:
+            lib().orc_fftfilt_free(C.byref(self.s))
+        except Exception:
+            pass
+
+    def set_taps(self, taps):
+        t = np.ascontiguousarray(taps, np.complex64)
+        self.nsamples = lib().orc_fftfilt_set_taps(C.byref(self.s), _p(t), len(t))
+
+    def filter(self, nitems, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        assert nitems % self.nsamples == 0 and len(x) >= nitems * self.decim
+        out = np.zeros(max(nitems, 1), np.complex64)
+        lib().orc_fftfilt_filter(C.byref(self.s), int(nitems), _p(x), _p(out))
+        return out[:nitems]
+
+    def run(self, x, blocks_per_call=None):
+        x = np.ascontiguousarray(x, np.complex64)
+        ns = self.nsamples
+        nblocks = (len(x) // self.decim) // ns
+        outs, done, step = [], 0, (blocks_per_call or max(nblocks, 1)) * ns
+        while done < nblocks * ns:
+            n = min(step, nblocks * ns - done)
+            outs.append(self.filter(n, x[done * self.decim:]))
+            done += n
+        return np.concatenate(outs) if outs else np.zeros(0, np.complex64)

@@ -16,6 +16,7 @@
 #include <gr_pfb_channelizer_ccf.h>
 #include <gr_pfb_arb_resampler_ccf.h>
 #include <gr_pfb_decimator_ccf.h>
+#include <gr_fft_filter_ccc.h>
 #include <gr_fft_vcc.h>
 #include <gr_quadrature_demod_cf.h>
 #include <gr_math.h>
@@ -94,6 +95,21 @@ grref_block* grref_make_pfb_arb_resampler_ccf(float rate, const float* taps, int
 }
 grref_block* grref_make_pfb_decimator_ccf(unsigned decim, const float* taps, int ntaps, unsigned channel) {
   return guarded([&] { return gr_block_sptr(gr_make_pfb_decimator_ccf(decim, std::vector<float>(taps, taps + ntaps), channel)); });
+}
+grref_block* grref_make_fft_filter_ccc(int decim, const float* taps_ri, int ntaps) {
+  return guarded([&] {
+    std::vector<gr_complex> t(ntaps);
+    for (int i = 0; i < ntaps; i++) t[i] = gr_complex(taps_ri[2 * i], taps_ri[2 * i + 1]);
+    return gr_block_sptr(gr_make_fft_filter_ccc(decim, t));
+  });
+}
+int grref_fft_filter_ccc_set_taps(grref_block* h, const float* taps_ri, int ntaps) {
+  gr_fft_filter_ccc* b = dynamic_cast<gr_fft_filter_ccc*>(h->blk.get());
+  if (!b) return -1;
+  std::vector<gr_complex> t(ntaps);
+  for (int i = 0; i < ntaps; i++) t[i] = gr_complex(taps_ri[2 * i], taps_ri[2 * i + 1]);
+  b->set_taps(t);
+  return 0;
 }
 grref_block* grref_make_fft_vcc(int fft_size, int forward, const float* window, int nwin, int shift) {
   return guarded([&] {

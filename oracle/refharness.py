@@ -44,7 +44,7 @@ def dir_makers():
         "grref_make_pfb_channelizer_ccf", "grref_make_fft_vcc", "grref_make_quadrature_demod_cf",
         "grref_make_clock_recovery_mm_ff", "grref_make_pager_slicer_fb", "grref_make_binary_slicer_fb",
         "grref_make_map_bb", "grref_make_unpack_k_bits_bb", "grref_make_correlate_access_code_bb",
-        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf",
+        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf", "grref_make_fft_filter_ccc",
     ]
 
 
@@ -204,6 +204,33 @@ def run_pfb_decimator(block, x, decim, chunk=None):
         assert r == m
         done += r
     return out[:n]
+
+
+def fft_filter_ccc(decim, taps):
+    t = np.ascontiguousarray(taps, np.complex64)
+    return RefBlock(lib().grref_make_fft_filter_ccc(int(decim), _fp(t.view(np.float32)), len(t)), np.complex64, np.complex64)
+
+
+def fft_filter_ccc_set_taps(block, taps):
+    t = np.ascontiguousarray(taps, np.complex64)
+    assert lib().grref_fft_filter_ccc_set_taps(block.h, _fp(t.view(np.float32)), len(t)) == 0
+
+
+def run_fft_filter(block, x, decim, blocks_per_call=None):
+    """gr_fft_filter_ccc over the new items x (history 1).  noutput is a multiple of output_multiple = nsamples
+    (gr_fft_filter_ccc.cc:66,92-100); the tail that does not fill a whole block is not asked for, like the scheduler."""
+    x = np.ascontiguousarray(x, np.complex64)
+    ns = block.output_multiple
+    raw, ptr, view = aligned_stream(x, 1, np.complex64)
+    nblocks = (len(x) // decim) // ns
+    out = np.zeros(max(nblocks * ns, 1), np.complex64)
+    done, step = 0, (blocks_per_call or max(nblocks, 1)) * ns
+    while done < nblocks * ns:
+        n = min(step, nblocks * ns - done)
+        r = block.general_work(n, [ptr + done * decim * 8], [n * decim], out[done:])
+        assert r == n, (r, n)
+        done += r
+    return out[:nblocks * ns]
 
 
 def fft_vcc(fft_size, forward, window, shift=False):

@@ -112,6 +112,12 @@ static int cmd_run(int argc, char** argv) {
       for (unsigned j = 0; j < M; j++)
         memcpy(streams[j].data() + m * sizeof(gr_complex), in.data() + (m * M + j) * sizeof(gr_complex), sizeof(gr_complex));
     out = run_block(*b, streams, max_noutput);
+  } else if (kind == "fftfilt") {
+    std::vector<float> t = floats(argv[4]);  // interleaved re, im
+    std::vector<gr_complex> tc(t.size() / 2);
+    for (size_t i = 0; i < tc.size(); i++) tc[i] = gr_complex(t[2 * i], t[2 * i + 1]);
+    auto b = gr_make_fft_filter_ccc(atoi(argv[3]), tc);
+    out = run_block(*b, streams, max_noutput);
   } else if (kind == "arb") {
     auto b = gr_make_pfb_arb_resampler_ccf((float)atof(argv[3]), floats(argv[4]), (unsigned)atoi(argv[5]));
     out = run_block(*b, streams, max_noutput);

@@ -198,6 +198,15 @@ def fixtures_next():
         fx["pfbdec_%s_taps" % tag], fx["pfbdec_%s_x" % tag] = taps, xin
         fx["pfbdec_%s_args" % tag] = np.array([M, ch])
         fx["pfbdec_%s_y" % tag] = R.run_pfb_decimator(R.pfb_decimator_ccf(M, taps, ch), xin, M, chunk=50)
+    # rank 4: gr_fft_filter_ccc (overlap-add, complex taps): decimation 1 and 3, tap counts on both sides of a power of two
+    xf = (rng.standard_normal(6000) + 1j * rng.standard_normal(6000)).astype(np.complex64)
+    fx["fftfilt_x"] = xf
+    for tag, dec, nt in (("d1_t33", 1, 33), ("d3_t64", 3, 64), ("d1_t200", 1, 200)):
+        tc = ((rng.standard_normal(nt) + 1j * rng.standard_normal(nt)) * 0.1).astype(np.complex64)
+        blk = R.fft_filter_ccc(dec, tc)
+        fx["fftfilt_%s_taps" % tag] = tc
+        fx["fftfilt_%s_args" % tag] = np.array([dec, blk.output_multiple])
+        fx["fftfilt_%s_y" % tag] = R.run_fft_filter(blk, xf, dec, blocks_per_call=2)
     return fx
 
 

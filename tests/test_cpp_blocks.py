@@ -127,6 +127,19 @@ def test_pfb_decimator_block(harness, tmp_path, orc):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_fft_filter_block(harness, tmp_path, orc):
+    """gr_make_fft_filter_ccc under the scheduler: history 1, output_multiple = nsamples, decimation 2."""
+    rng = np.random.default_rng(31)
+    x = (rng.standard_normal(20000) + 1j * rng.standard_normal(20000)).astype(np.complex64)
+    taps = ((rng.standard_normal(45) + 1j * rng.standard_normal(45)) * 0.1).astype(np.complex64)
+    y = run(harness, tmp_path, ["fftfilt", 2, taps.view(np.float32)], x, np.complex64, max_noutput=1000)
+    want = orc.FftFilter(2, taps).run(x)
+    assert len(want) - 2000 <= len(y) <= len(want) and len(y) % 84 == 0     # nsamples = 128 - 45 + 1
+    assert relerr(y, want[:len(y)]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
 def test_pfb_arb_resampler_block(harness, tmp_path, orc):
     """gr_make_pfb_arb_resampler_ccf under the scheduler: forecast = noutput + history - 1 (gr_block default),
     consume_each honoured, first general_work returns 0; bit identical to the generic-order reference."""
