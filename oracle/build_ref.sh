@@ -28,7 +28,7 @@ SRCS=(
   "$CORE/filter/gr_fir_fff_simd.cc" "$CORE/filter/gr_fir_fff_x86.cc"
   "$CORE/filter/gr_fir_ccc_simd.cc" "$CORE/filter/gr_fir_ccc_x86.cc"
   "$CORE/filter/gr_pfb_channelizer_ccf.cc" "$CORE/filter/gr_pfb_arb_resampler_ccf.cc" "$CORE/filter/gr_pfb_decimator_ccf.cc"
-  "$CORE/filter/gr_fft_filter_ccc.cc" "$CORE/filter/gri_fft_filter_ccc_generic.cc"
+  "$CORE/filter/gr_fft_filter_ccc.cc" "$CORE/filter/gri_fft_filter_ccc_generic.cc" "$CORE/general/gr_framer_sink_1.cc"
   "$CORE/filter/gri_mmse_fir_interpolator.cc"
   "$CORE/general/gr_reverse.cc" "$CORE/general/gr_fast_atan2f.cc" "$CORE/general/gr_count_bits.cc"
   "$CORE/general/gr_quadrature_demod_cf.cc" "$CORE/general/gr_fft_vcc.cc" "$CORE/general/gr_fft_vcc_fftw.cc"

@@ -676,6 +676,67 @@ int orc_fftfilt_filter(orc_fftfilt_state* s, int nitems, const orc_cpx* input, o
   return nitems;
 }
 
+
+/* ---- gr_framer_sink_1 -------------------------------------------------------------------------- */
+void orc_framer_init(orc_framer_state* s) { /* ctor -> enter_search (:86-90) */
+  memset(s, 0, sizeof *s);
+  s->state = 0;
+}
+void orc_framer_work(orc_framer_state* s, const unsigned char* in, long n, orc_framer_emit emit, void* ctx) { /* :93-196 */
+  long count = 0;
+  while (count < n) {
+    switch (s->state) {
+      case 0: /* STATE_SYNC_SEARCH (:107-119): the flagged byte itself is NOT consumed here */
+        while (count < n) {
+          if (in[count] & 0x2) {
+            s->state = 1; /* enter_have_sync (:46-55) */
+            s->header = 0;
+            s->headerbitlen_cnt = 0;
+            break;
+          }
+          count++;
+        }
+        break;
+      case 1: /* STATE_HAVE_SYNC (:121-159) */
+        while (count < n) {
+          s->header = (s->header << 1) | (in[count++] & 0x1);
+          if (++s->headerbitlen_cnt == 32) {
+            if (((s->header >> 16) ^ (s->header & 0xffff)) == 0) { /* header_ok (.h:88-92) */
+              s->packetlen = (int)((s->header >> 16) & 0x0fff); /* header_payload (.h:94-102) */
+              s->whitener_offset = (int)((s->header >> 28) & 0x000f);
+              s->state = 2; /* enter_have_header (:57-69) */
+              s->packetlen_cnt = 0;
+              s->packet_byte = 0;
+              s->byte_index = 0;
+              if (s->packetlen == 0) { /* zero-length payload (:139-149) */
+                emit(ctx, s->whitener_offset, s->packet, 0);
+                s->state = 0;
+              }
+            } else {
+              s->state = 0; /* bad header */
+            }
+            break;
+          }
+        }
+        break;
+      default: /* STATE_HAVE_HEADER (:161-187) */
+        while (count < n) {
+          s->packet_byte = (unsigned char)((s->packet_byte << 1) | (in[count++] & 0x1));
+          if (s->byte_index++ == 7) {
+            s->packet[s->packetlen_cnt++] = s->packet_byte;
+            s->byte_index = 0;
+            if (s->packetlen_cnt == s->packetlen) {
+              emit(ctx, s->whitener_offset, s->packet, s->packetlen_cnt);
+              s->state = 0;
+              break;
+            }
+          }
+        }
+        break;
+    }
+  }
+}
+
 /* ---- gr_firdes ------------------------------------------------------------------------------ */
 static double izero(double x) { /* gr_firdes.cc:35-51 */
   double sum, u, halfx, temp;

@@ -148,6 +148,20 @@ int orc_fftfilt_set_taps(orc_fftfilt_state* s, const orc_cpx* taps, int ntaps); 
 void orc_fftfilt_free(orc_fftfilt_state* s);
 /* nitems outputs (multiple of nsamples) from nitems * decimation inputs; returns nitems */
 int orc_fftfilt_filter(orc_fftfilt_state* s, int nitems, const orc_cpx* in, orc_cpx* out);
+/* gr_framer_sink_1::work (gr_framer_sink_1.cc:93-196; header checks gr_framer_sink_1.h:88-103): consumes the
+ * correlator's output bytes (bit 0 = data, bit 1 = "access code ended here"), reads a 32-bit header (two identical
+ * 16-bit halves: whitener offset << 12 | payload length), then payload_len bytes MSB first, and posts a message per
+ * packet.  emit(ctx, whitener_offset, payload, len) stands for d_target_queue->insert_tail(). */
+typedef struct {
+  int state; /* 0 sync search, 1 have sync, 2 have header */
+  unsigned header;
+  int headerbitlen_cnt, packetlen, whitener_offset, packetlen_cnt, byte_index;
+  unsigned char packet_byte;
+  unsigned char packet[4096];
+} orc_framer_state;
+typedef void (*orc_framer_emit)(void* ctx, int whitener_offset, const unsigned char* payload, int len);
+void orc_framer_init(orc_framer_state* s);
+void orc_framer_work(orc_framer_state* s, const unsigned char* in, long n, orc_framer_emit emit, void* ctx);
 /* gr_firdes (gr_firdes.cc:57-147,601-655,720-782): tap / window design on the host. */
 int orc_firdes_window(int win_type, int ntaps, double beta, float* out);
 int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win_type, double beta, float* out, int cap);

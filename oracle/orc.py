@@ -430,3 +430,50 @@ class FftFilter:
             outs.append(self.filter(n, x[done * self.decim:]))
             done += n
         return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
+# ---- gr_framer_sink_1 ---------------------------------------------------------------------------------
+class FramerState(C.Structure):
+    _fields_ = [("state", C.c_int), ("header", C.c_uint), ("headerbitlen_cnt", C.c_int), ("packetlen", C.c_int),
+                ("whitener_offset", C.c_int), ("packetlen_cnt", C.c_int), ("byte_index", C.c_int),
+                ("packet_byte", C.c_ubyte), ("packet", C.c_ubyte * 4096)]
+
+
+_EMIT = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_ubyte), C.c_int)
+
+
+class Framer:
+    """orc_framer_*: gr_framer_sink_1's state machine; work() returns the packets posted during the call as
+    [(whitener_offset, payload bytes)]."""
+
+    def __init__(self):
+        self.s = FramerState()
+        lib().orc_framer_init(C.byref(self.s))
+
+    def work(self, in_bytes):
+        x = np.ascontiguousarray(in_bytes, np.uint8)
+        got = []
+
+        def emit(ctx, off, payload, n):
+            got.append((int(off), bytes(bytearray(payload[i] for i in range(n)))))
+        cb = _EMIT(emit)
+        lib().orc_framer_work(C.byref(self.s), _p(x), C.c_long(len(x)), cb, None)
+        return got
+
+
+def framer_make_stream(rng, packets, gap=(5, 200), corrupt_header_every=0):
+    """Correlator-style byte stream (bit 0 data, bit 1 flag) carrying `packets` = [(whitener_offset, payload bytes)]:
+    random data bits, then for each packet one byte with the flag set (the first header bit rides on it), 32 header bits
+    and the payload MSB first.  corrupt_header_every = k flips one header bit of every k-th packet."""
+    out = []
+    for i, (off, payload) in enumerate(packets):
+        out.append(rng.integers(0, 2, int(rng.integers(gap[0], gap[1]))).astype(np.uint8))
+        h16 = ((off & 0xf) << 12) | (len(payload) & 0xfff)
+        hdr = [(((h16 << 16) | h16) >> (31 - b)) & 1 for b in range(32)]
+        if corrupt_header_every and (i + 1) % corrupt_header_every == 0:
+            hdr[int(rng.integers(0, 32))] ^= 1
+        bits = np.array(hdr + [(byte >> (7 - b)) & 1 for byte in payload for b in range(8)], np.uint8)
+        bits[0] |= 2
+        out.append(bits)
+    out.append(rng.integers(0, 2, 50).astype(np.uint8))
+    return np.concatenate(out)

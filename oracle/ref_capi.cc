@@ -17,6 +17,7 @@
 #include <gr_pfb_arb_resampler_ccf.h>
 #include <gr_pfb_decimator_ccf.h>
 #include <gr_fft_filter_ccc.h>
+#include <gr_framer_sink_1.h>
 #include <gr_fft_vcc.h>
 #include <gr_quadrature_demod_cf.h>
 #include <gr_math.h>
@@ -110,6 +111,36 @@ int grref_fft_filter_ccc_set_taps(grref_block* h, const float* taps_ri, int ntap
   for (int i = 0; i < ntaps; i++) t[i] = gr_complex(taps_ri[2 * i], taps_ri[2 * i + 1]);
   b->set_taps(t);
   return 0;
+}
+// gr_framer_sink_1: the block and the queue it posts to live together; messages are drained through the C API
+struct grref_framer_ctx { gr_msg_queue_sptr q; };
+static std::vector<std::pair<grref_block*, gr_msg_queue_sptr> > g_framer_queues;
+grref_block* grref_make_framer_sink_1() {
+  gr_msg_queue_sptr q = gr_make_msg_queue();
+  grref_block* b = guarded([&] { return gr_block_sptr(gr_make_framer_sink_1(q)); });
+  if (b) g_framer_queues.push_back(std::make_pair(b, q));
+  return b;
+}
+static gr_msg_queue_sptr framer_queue(grref_block* h) {
+  for (size_t i = 0; i < g_framer_queues.size(); i++)
+    if (g_framer_queues[i].first == h) return g_framer_queues[i].second;
+  return gr_msg_queue_sptr();
+}
+int grref_framer_count(grref_block* h) { gr_msg_queue_sptr q = framer_queue(h); return q ? (int)q->count() : -1; }
+// pops one message: returns its length (>= 0) or -1 if the queue is empty; *arg1 = whitener offset
+int grref_framer_pop(grref_block* h, unsigned char* out, int cap, double* arg1) {
+  gr_msg_queue_sptr q = framer_queue(h);
+  if (!q) return -1;
+  gr_message_sptr m = q->delete_head_nowait();
+  if (!m) return -1;
+  if (arg1) *arg1 = m->arg1();
+  const int n = (int)m->length();
+  memcpy(out, m->msg(), (size_t)(n < cap ? n : cap));
+  return n;
+}
+void grref_framer_forget(grref_block* h) {
+  for (size_t i = 0; i < g_framer_queues.size(); i++)
+    if (g_framer_queues[i].first == h) { g_framer_queues.erase(g_framer_queues.begin() + i); return; }
 }
 grref_block* grref_make_fft_vcc(int fft_size, int forward, const float* window, int nwin, int shift) {
   return guarded([&] {

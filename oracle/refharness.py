@@ -44,7 +44,7 @@ def dir_makers():
         "grref_make_pfb_channelizer_ccf", "grref_make_fft_vcc", "grref_make_quadrature_demod_cf",
         "grref_make_clock_recovery_mm_ff", "grref_make_pager_slicer_fb", "grref_make_binary_slicer_fb",
         "grref_make_map_bb", "grref_make_unpack_k_bits_bb", "grref_make_correlate_access_code_bb",
-        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf", "grref_make_fft_filter_ccc",
+        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf", "grref_make_fft_filter_ccc", "grref_make_framer_sink_1",
     ]
 
 
@@ -231,6 +231,34 @@ def run_fft_filter(block, x, decim, blocks_per_call=None):
         assert r == n, (r, n)
         done += r
     return out[:nblocks * ns]
+
+
+class FramerSink:
+    """gr_framer_sink_1 + the gr_msg_queue it posts to."""
+
+    def __init__(self):
+        self.blk = RefBlock(lib().grref_make_framer_sink_1(), np.uint8, np.uint8)
+
+    def __del__(self):
+        try:
+            lib().grref_framer_forget(self.blk.h)
+        except Exception:
+            pass
+
+    def work(self, in_bytes):
+        x = np.ascontiguousarray(in_bytes, np.uint8)
+        if len(x):
+            ip = (C.c_void_p * 1)(x.ctypes.data)
+            ni = (C.c_int * 1)(len(x))
+            r = lib().grref_block_general_work(self.blk.h, len(x), ni, 1, ip, None, 0)
+            assert r == len(x), r
+        got, buf, a1 = [], np.zeros(4096, np.uint8), C.c_double(0)
+        while True:
+            n = lib().grref_framer_pop(self.blk.h, buf.ctypes.data_as(C.c_void_p), 4096, C.byref(a1))
+            if n < 0:
+                break
+            got.append((int(a1.value), bytes(buf[:n])))
+        return got
 
 
 def fft_vcc(fft_size, forward, window, shift=False):

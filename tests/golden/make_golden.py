@@ -207,6 +207,19 @@ def fixtures_next():
         fx["fftfilt_%s_taps" % tag] = tc
         fx["fftfilt_%s_args" % tag] = np.array([dec, blk.output_multiple])
         fx["fftfilt_%s_y" % tag] = R.run_fft_filter(blk, xf, dec, blocks_per_call=2)
+    # rank 4: gr_framer_sink_1 on a correlator-style stream: good packets (incl. zero length and the 4095-byte maximum),
+    # every third header corrupted; packets recorded as [whitener offset, length, payload...] rows
+    import orc
+    pk = [(int(rng.integers(0, 16)), bytes(rng.integers(0, 256, int(n)).astype(np.uint8))) for n in (5, 0, 17, 1, 300, 4095, 2, 64)]
+    stream = orc.framer_make_stream(rng, pk, corrupt_header_every=3)
+    f = R.FramerSink()
+    got = []
+    for chunk in np.array_split(stream, 23):
+        got += f.work(chunk)
+    fx["framer_stream"] = stream
+    fx["framer_offsets"] = np.array([g[0] for g in got], np.int32)
+    fx["framer_lengths"] = np.array([len(g[1]) for g in got], np.int32)
+    fx["framer_payloads"] = np.frombuffer(b"".join(g[1] for g in got), np.uint8)
     return fx
 
 
