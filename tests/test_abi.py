@@ -61,6 +61,27 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.grcuda_last_error_code() == -2
 
 
+def test_argument_errors_of_the_8f_blocks(lib):
+    """gr_pfb_arb_resampler_ccf / gr_pfb_decimator_ccf / gr_fft_filter_ccc: bad constructor arguments are refused with
+    GRCUDA_EINVAL before any device is touched."""
+    f = ctypes.c_float
+    taps = (ctypes.c_float * 8)(*([0.125] * 8))
+    for name in ("grcuda_pfb_arb_resampler_ccf_create", "grcuda_pfb_decimator_ccf_create", "grcuda_fft_filter_ccc_create"):
+        getattr(lib, name).restype = ctypes.c_void_p
+    assert not lib.grcuda_pfb_arb_resampler_ccf_create(f(1.5), taps, 1, 32, 1)      # create_diff_taps needs 2 taps
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_pfb_arb_resampler_ccf_create(f(0.0), taps, 8, 32, 1)      # rate must be > 0
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_pfb_arb_resampler_ccf_create(f(1.5), taps, 8, 0, 1)       # no filters
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_pfb_decimator_ccf_create(0, taps, 8, 0)
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_fft_filter_ccc_create(0, taps, 4)
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_fft_filter_ccc_create(1, taps, 0)
+    assert lib.grcuda_last_error_code() == -1
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200")
     for dp, _, files in os.walk(pkg):
