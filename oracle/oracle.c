@@ -737,6 +737,56 @@ void orc_framer_work(orc_framer_state* s, const unsigned char* in, long n, orc_f
   }
 }
 
+
+/* ---- digital_clock_recovery_mm_cc -------------------------------------------------------------- */
+int orc_mmcc_init(orc_mmcc_state* s, float omega, float gain_omega, float mu, float gain_mu, float lim) { /* :53-75 */
+  memset(s, 0, sizeof *s);
+  if (omega <= 0.0) return -1;                  /* :65-66 std::out_of_range */
+  if (gain_mu < 0 || gain_omega < 0) return -1; /* :67-68 */
+  s->mu = mu; s->gain_omega = gain_omega; s->gain_mu = gain_mu; s->omega_relative_limit = lim;
+  s->omega = omega; /* set_omega (.h:75-80): double expressions stored to float */
+  const float mn = (float)(omega * (1.0 - lim)), mx = (float)(omega * (1.0 + lim));
+  s->omega_mid = (float)(0.5 * (mn + mx));
+  return 0;
+}
+int orc_mmcc_forecast(const orc_mmcc_state* s, int noutput) { /* :84-91: ntaps 8, FUDGE 16 */
+  return (int)ceil((noutput * s->omega) + 8) + 16;
+}
+int orc_mmcc_general_work(orc_mmcc_state* s, const orc_cpx* in, int ninput, orc_cpx* out, float* err, int noutput,
+                          int* consumed) { /* :123-218 */
+  int ii = 0, oo = 0;
+  const int ni = ninput - 8 - 16;
+  const float lim = err ? 4.0f : 1.0f;
+  const float* table = orc_mmse_table();
+  while (oo < noutput && ii < ni) {
+    s->p_2T = s->p_1T;
+    s->p_1T = s->p_0T;
+    const int imu = (int)rint(s->mu * 128); /* gri_mmse_fir_interpolator_cc.cc:65 */
+    s->p_0T = arb_filter(table + (size_t)imu * 8, 8, in + ii);
+    s->c_2T = s->c_1T;
+    s->c_1T = s->c_0T;
+    s->c_0T.re = s->p_0T.re > 0 ? 1.0f : 0.0f; /* slicer_0deg (:93-103) */
+    s->c_0T.im = s->p_0T.im > 0 ? 1.0f : 0.0f;
+    /* x = (c_0T - c_2T) * conj(p_1T); y = (p_0T - p_2T) * conj(c_1T); mm_val = (y - x).real() (:137-140) */
+    const float ar = s->c_0T.re - s->c_2T.re, ai = s->c_0T.im - s->c_2T.im;
+    const float xr = ar * s->p_1T.re - ai * (-s->p_1T.im);
+    const float br = s->p_0T.re - s->p_2T.re, bi = s->p_0T.im - s->p_2T.im;
+    const float yr = br * s->c_1T.re - bi * (-s->c_1T.im);
+    float mm_val = yr - xr;
+    out[oo++] = s->p_0T;
+    mm_val = branchless_clip(mm_val, lim);
+    s->omega = s->omega + s->gain_omega * mm_val;
+    s->omega = s->omega_mid + branchless_clip(s->omega - s->omega_mid, s->omega_relative_limit);
+    s->mu = s->mu + s->omega + s->gain_mu * mm_val;
+    ii += (int)floor(s->mu);
+    s->mu -= floor(s->mu);
+    if (err) err[oo - 1] = mm_val;
+    if (ii < 0) ii = 0;
+  }
+  if (consumed) *consumed = ii > 0 ? ii : 0; /* :207-214: consume_each only when ii > 0 */
+  return oo;
+}
+
 /* ---- gr_firdes ------------------------------------------------------------------------------ */
 static double izero(double x) { /* gr_firdes.cc:35-51 */
   double sum, u, halfx, temp;

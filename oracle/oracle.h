@@ -162,6 +162,18 @@ typedef struct {
 typedef void (*orc_framer_emit)(void* ctx, int whitener_offset, const unsigned char* payload, int len);
 void orc_framer_init(orc_framer_state* s);
 void orc_framer_work(orc_framer_state* s, const unsigned char* in, long n, orc_framer_emit emit, void* ctx);
+/* digital_clock_recovery_mm_cc (gr-digital/lib/digital_clock_recovery_mm_cc.cc:53-75 ctor, :123-218 general_work;
+ * set_omega gr-digital/include/digital_clock_recovery_mm_cc.h:75-80) with gri_mmse_fir_interpolator_cc
+ * (filter/gri_mmse_fir_interpolator_cc.cc:62-71: gr_fir_ccf on the 8-tap MMSE rows; generic order here).
+ * err may be NULL: the reference then clips the timing error to +-1 instead of +-4 (:146 vs :181). */
+typedef struct {
+  float mu, omega, gain_omega, gain_mu, omega_mid, omega_relative_limit;
+  orc_cpx p_2T, p_1T, p_0T, c_2T, c_1T, c_0T;
+} orc_mmcc_state;
+int orc_mmcc_init(orc_mmcc_state* s, float omega, float gain_omega, float mu, float gain_mu, float omega_relative_limit);
+int orc_mmcc_forecast(const orc_mmcc_state* s, int noutput);
+int orc_mmcc_general_work(orc_mmcc_state* s, const orc_cpx* in, int ninput, orc_cpx* out, float* err, int noutput,
+                          int* consumed);
 /* gr_firdes (gr_firdes.cc:57-147,601-655,720-782): tap / window design on the host. */
 int orc_firdes_window(int win_type, int ntaps, double beta, float* out);
 int orc_firdes_low_pass(double gain, double fs, double fc, double tw, int win_type, double beta, float* out, int cap);

@@ -477,3 +477,29 @@ def framer_make_stream(rng, packets, gap=(5, 200), corrupt_header_every=0):
         out.append(bits)
     out.append(rng.integers(0, 2, 50).astype(np.uint8))
     return np.concatenate(out)
+
+
+# ---- digital_clock_recovery_mm_cc ---------------------------------------------------------------------
+class MMCCState(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("mu", "omega", "gain_omega", "gain_mu", "omega_mid", "omega_relative_limit")] + \
+               [(n, C.c_float * 2) for n in ("p_2T", "p_1T", "p_0T", "c_2T", "c_1T", "c_0T")]
+
+
+def mmcc_new(omega, gain_omega, mu, gain_mu, omega_relative_limit=0.001):
+    s = MMCCState()
+    if lib().orc_mmcc_init(C.byref(s), C.c_float(omega), C.c_float(gain_omega), C.c_float(mu), C.c_float(gain_mu),
+                           C.c_float(omega_relative_limit)) != 0:
+        raise IndexError("out_of_range")
+    return s
+
+
+def mmcc_work(state, x, noutput=None, with_error=False):
+    """Returns (symbols, error signal or None, consumed)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    nout = len(x) if noutput is None else noutput
+    out = np.zeros(max(nout, 1), np.complex64)
+    err = np.zeros(max(nout, 1), np.float32) if with_error else None
+    consumed = C.c_int(0)
+    r = lib().orc_mmcc_general_work(C.byref(state), _p(x), len(x), _p(out), _p(err) if with_error else None, int(nout),
+                                    C.byref(consumed))
+    return out[:r], (err[:r] if with_error else None), consumed.value

@@ -28,6 +28,7 @@
 #include <gr_unpack_k_bits_bb.h>
 #include <gri_mmse_fir_interpolator.h>
 #include <digital_clock_recovery_mm_ff.h>
+#include <digital_clock_recovery_mm_cc.h>
 #include <digital_correlate_access_code_bb.h>
 #include <digital_binary_slicer_fb.h>
 #include <pager_slicer_fb.h>
@@ -154,6 +155,12 @@ grref_block* grref_make_clock_recovery_mm_ff(float omega, float gain_omega, floa
                                              float omega_relative_limit) {
   return guarded([&] {
     return gr_block_sptr(digital_make_clock_recovery_mm_ff(omega, gain_omega, mu, gain_mu, omega_relative_limit));
+  });
+}
+grref_block* grref_make_clock_recovery_mm_cc(float omega, float gain_omega, float mu, float gain_mu,
+                                             float omega_relative_limit) {
+  return guarded([&] {
+    return gr_block_sptr(digital_make_clock_recovery_mm_cc(omega, gain_omega, mu, gain_mu, omega_relative_limit));
   });
 }
 grref_block* grref_make_pager_slicer_fb(float alpha) {

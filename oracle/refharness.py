@@ -44,7 +44,7 @@ def dir_makers():
         "grref_make_pfb_channelizer_ccf", "grref_make_fft_vcc", "grref_make_quadrature_demod_cf",
         "grref_make_clock_recovery_mm_ff", "grref_make_pager_slicer_fb", "grref_make_binary_slicer_fb",
         "grref_make_map_bb", "grref_make_unpack_k_bits_bb", "grref_make_correlate_access_code_bb",
-        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf", "grref_make_fft_filter_ccc", "grref_make_framer_sink_1",
+        "grref_make_pfb_arb_resampler_ccf", "grref_make_pfb_decimator_ccf", "grref_make_fft_filter_ccc", "grref_make_framer_sink_1", "grref_make_clock_recovery_mm_cc",
     ]
 
 
@@ -275,6 +275,31 @@ def clock_recovery_mm_ff(omega, gain_omega, mu, gain_mu, omega_relative_limit=0.
     return RefBlock(lib().grref_make_clock_recovery_mm_ff(C.c_float(omega), C.c_float(gain_omega), C.c_float(mu),
                                                           C.c_float(gain_mu), C.c_float(omega_relative_limit)),
                     np.float32, np.float32)
+
+
+def clock_recovery_mm_cc(omega, gain_omega, mu, gain_mu, omega_relative_limit=0.001):
+    return RefBlock(lib().grref_make_clock_recovery_mm_cc(C.c_float(omega), C.c_float(gain_omega), C.c_float(mu),
+                                                          C.c_float(gain_mu), C.c_float(omega_relative_limit)),
+                    np.complex64, np.complex64)
+
+
+def run_mm_cc(block, x, noutput=None, with_error=False):
+    """digital_clock_recovery_mm_cc.general_work on the complex stream x (one or two outputs).
+    Returns (symbols, error signal or None, consumed)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    raw, ptr, view = aligned_stream(x, 1, np.complex64)
+    nout = noutput if noutput is not None else len(x)
+    out = np.zeros(max(nout, 1), np.complex64)
+    err = np.zeros(max(nout, 1), np.float32)
+    ip = (C.c_void_p * 1)(ptr)
+    ni = (C.c_int * 1)(len(x))
+    if with_error:
+        op = (C.c_void_p * 2)(out.ctypes.data, err.ctypes.data)
+        r = lib().grref_block_general_work(block.h, int(nout), ni, 1, ip, op, 2)
+    else:
+        op = (C.c_void_p * 1)(out.ctypes.data)
+        r = lib().grref_block_general_work(block.h, int(nout), ni, 1, ip, op, 1)
+    return out[:r], (err[:r] if with_error else None), block.consumed
 
 
 def pager_slicer_fb(alpha):

@@ -16,3 +16,7 @@ typedef std::shared_ptr<gr_io_signature> gr_io_signature_sptr;
 inline gr_io_signature_sptr gr_make_io_signature(int mn, int mx, int sz) {
   return gr_io_signature_sptr(new gr_io_signature(mn, mx, sz));
 }
+// two differently sized streams (runtime/gr_io_signature.h gr_make_io_signature2): the shim keeps the first size
+inline gr_io_signature_sptr gr_make_io_signature2(int mn, int mx, int sz1, int) {
+  return gr_io_signature_sptr(new gr_io_signature(mn, mx, sz1));
+}

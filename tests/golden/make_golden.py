@@ -220,6 +220,19 @@ def fixtures_next():
     fx["framer_offsets"] = np.array([g[0] for g in got], np.int32)
     fx["framer_lengths"] = np.array([len(g[1]) for g in got], np.int32)
     fx["framer_payloads"] = np.frombuffer(b"".join(g[1] for g in got), np.uint8)
+    # rank 4: digital_clock_recovery_mm_cc on noisy QPSK at 4 samples/symbol, with and without the error output
+    # (generic-order interpolator filters: the restatement's order)
+    nq = 6000
+    symq = (rng.integers(0, 2, nq // 4 + 1) * 2 - 1) + 1j * (rng.integers(0, 2, nq // 4 + 1) * 2 - 1)
+    xq = (np.repeat(symq, 4)[:nq] + 0.1 * (rng.standard_normal(nq) + 1j * rng.standard_normal(nq))).astype(np.complex64)
+    fx["mmcc_x"], fx["mmcc_args"] = xq, np.array([4.0, 0.25 * 0.1 * 0.1, 0.5, 0.1, 0.005])
+    R.set_fir_impl(0)
+    for we, nm in ((False, "plain"), (True, "err")):
+        y, e, c = R.run_mm_cc(R.clock_recovery_mm_cc(*[float(v) for v in fx["mmcc_args"]]), xq, with_error=we)
+        fx["mmcc_y_" + nm], fx["mmcc_consumed_" + nm] = y, np.int64(c)
+        if we:
+            fx["mmcc_err"] = e
+    R.set_fir_impl(1)
     return fx
 
 
