@@ -56,7 +56,7 @@ namespace grb {
                               // from finite data; a colliding input NaN is re-encoded as 0x7fc00000)
 #define MMW_CH 64             // channels per CTA
 #define MMW_THREADS 192
-#define MMW_TABREP 1          // copies of the interpolator table in shared memory, one per bank group (below)
+#define MMW_TABREP 1          // copies of the interpolator table in shared memory (1 = the plain table; see below)
 #define MMW_TABROW (2 * MMW_TABREP * 16)  // bytes per interpolator row: [2 halves][MMW_TABREP copies][4 floats]
 #define MMW_MAGIC 12582912.0f // 1.5 * 2^23: adding it leaves round(x) / floor(x) in the low mantissa bits
 #define MMW_MAGIC_BITS 0x4b400000
@@ -88,11 +88,12 @@ static inline size_t mm_ws_smem_bytes(int ring) {
 template <int RING, int ORDER>
 __global__ void __maxnreg__(MMW_REGS) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
-  // Interpolator table, [129 rows][2 halves][MMW_TABREP copies][4 floats]: a lane's LDS.128 of its row (every lane
-  // has its own mu) goes to the copy lane % MMW_TABREP, so that the eight lanes of a quarter warp spread over
-  // MMW_TABREP disjoint bank groups whatever their rows are (the plain [129][8] table cost 13.6 wavefronts per load
-  // instead of 4; 8 copies would make it exactly 4 but cost 33 KB: the kernel must stay under 48 KB to co-reside
-  // with the 128 KB tiles of the branch filter)
+  // Interpolator table, [129 rows][2 halves][MMW_TABREP copies][4 floats].  With MMW_TABREP = 1 this is the plain
+  // [129][8] table: every lane has its own mu, so a lane's two LDS.128 of its row cost 13.6 shared-memory wavefronts
+  // each instead of 4.  MMW_TABREP > 1 sends lane l to copy l % MMW_TABREP, i.e. spreads the eight lanes of a quarter
+  // warp over disjoint bank groups (8 copies: exactly 4 wavefronts), but the extra 16-33 KB push the kernel past the
+  // 48 KB at which it co-resides with the 128 KB tiles of the branch filter, and the kernel time did not move
+  // (profiles/README.md): 1 is what ships.
   float* tab = mmw_smem;
   float* ring = tab + 129 * (MMW_TABROW / 4);        // [RING + 8][64]; rows RING..RING+7 mirror rows 0..7
   unsigned* q = reinterpret_cast<unsigned*>(ring + (RING + 8) * MMW_CH);    // [MMW_Q][64]
