@@ -171,7 +171,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        # Keep stdout to the one JSON line.  With NCCL_DEBUG=VERSION NCCL prints its banner ("NCCL version ...") to
+        # stdout and ignores NCCL_DEBUG_FILE (the file is only honoured above that level): drop that level; any more
+        # verbose level the caller asked for is kept and sent to stderr.
+        if os.environ.get("NCCL_DEBUG", "").strip().upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
