@@ -170,7 +170,13 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = None
     if world > 1:
+        # Whatever a library writes to file descriptor 1 from here on (NCCL banners, ...) goes to stderr; the JSON line
+        # is written to the original stdout at the end.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         # Keep stdout to the one JSON line.  With NCCL_DEBUG=VERSION NCCL prints its banner ("NCCL version ...") to
         # stdout and ignores NCCL_DEBUG_FILE (the file is only honoured above that level): drop that level; any more
         # verbose level the caller asked for is kept and sent to stderr.
@@ -395,7 +401,10 @@ def run_ours(args):
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "sync_hits_last_step": hit_counts,
     }
-    print(json.dumps(line))
+    if json_fd is not None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
