@@ -84,7 +84,9 @@ static inline size_t mm_ws_smem_bytes(int ring) {
 
 // 6 warps x 64 registers leave room on the SM for the big-tile front kernels this kernel runs next to; at 48 the
 // core loop's ten shared-memory loads per symbol were issued one at a time, each just before its use
+#ifndef MMW_REGS
 #define MMW_REGS 48
+#endif
 template <int RING, int ORDER>
 __global__ void __maxnreg__(MMW_REGS) mm_ws_kernel(const MMArgs a) {
   extern __shared__ __align__(16) float mmw_smem[];
