@@ -129,3 +129,18 @@ def test_plan_indexing():
     assert p.left == 2 and p.right == 4 and p.has_left_state(0)
     p0 = sharding.TimeShardPlan(8, 0, 12500, 126)
     assert p0.left == 7 and not p0.has_left_state(0) and p0.has_left_state(1)
+
+
+def test_stream_policy_by_world_size():
+    """One rank overlaps its front with its own previous tail; from two ranks on the front is ordered after it
+    (stream policy)."""
+    from grb200 import sharding
+    assert not sharding.TimeShardPlan(1, 0, 100, 0).front_after_own_tail
+    for world in (2, 3, 4, 8):
+        for rank in range(world):
+            p = sharding.TimeShardPlan(world, rank, 100, 10)
+            assert p.front_after_own_tail
+            assert p.block_index(3) == 3 * world + rank and p.abs_start(3) == (3 * world + rank) * 100
+            assert p.left == (rank - 1) % world and p.right == (rank + 1) % world
+    assert not sharding.TimeShardPlan(4, 0, 100, 10).has_left_state(0)
+    assert sharding.TimeShardPlan(4, 1, 100, 10).has_left_state(0)
