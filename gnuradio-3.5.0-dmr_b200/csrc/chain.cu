@@ -398,6 +398,9 @@ int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d
   return grcuda_dmr_chain_process_tail_device(h, h->pipeline ? (void*)h->tail_stream : stream_);
 }
 
+int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant) {
+  return grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, variant);
+}
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on) {
   h->prof.on = on != 0;
   return grcuda_pfb_channelizer_ccf_set_profiling(h->pfb, on);

@@ -1037,6 +1037,7 @@ struct grcuda_mm : PlanBase {
   float min_omega = 0, max_omega = 0, omega_mid = 0;
   int slicer_levels = 0;
   float slicer_alpha = 0, slicer_beta = 1;
+  int variant = 0;  // which build of mm_ws_kernel runs (grcuda_clock_recovery_mm_ff_set_kernel_variant)
   DeviceTables tabs;
   DevBuf d_state, d_counts, d_slice;
   void calc_omega(float omega) {  // set_omega (digital_clock_recovery_mm_ff.h:75-80)
@@ -1067,16 +1068,48 @@ struct grcuda_mm : PlanBase {
       a.p.gain_omega = gain_omega; a.p.gain_mu = gain_mu; a.p.omega_mid = omega_mid; a.p.omega_relative_limit = limit;
       a.slicer_levels = slicer_levels; a.slicer_alpha = slicer_alpha; a.slicer_beta = slicer_beta;
     }
-    a.order = order; a.mmse_eff = tabs.mmse_eff;
+    a.order = order; a.mmse_eff = tabs.mmse_eff; a.one = 1.0f;
     // look-ahead ring depth in rows: ~120 rows is >= 24 symbols up to 5 samples/symbol (several HBM round
     // trips at the loop's pace); slower symbol rates (the 10 samples/symbol single-channel config) go deeper
     const int grid = (nchan + MMW_CH - 1) / MMW_CH;
-    // 47 KB with the 128-row ring (co-resides with the front kernels), 143 KB with the 512-row one
     typedef void (*mm_kernel_t)(const MMArgs);
     const bool deep = max_omega > 5.0f;
-    const mm_kernel_t k = deep ? (order == GRCUDA_ORDER_SSE ? mm_ws_kernel<512, GR_ORDER_SSE> : mm_ws_kernel<512, GR_ORDER_GENERIC>)
-                               : (order == GRCUDA_ORDER_SSE ? mm_ws_kernel<128, GR_ORDER_SSE> : mm_ws_kernel<128, GR_ORDER_GENERIC>);
-    const size_t smem = mm_ws_smem_bytes(deep ? 512 : 128);
+    const bool sse = order == GRCUDA_ORDER_SSE;
+    mm_kernel_t k = nullptr;
+    int tabrep = 1;
+    const int ringrows = deep ? 512 : 128;
+#define MMK(RINGV, NREG, TRV, COREV, LDV) \
+  (tabrep = TRV, sse ? mm_ws_kernel<RINGV, GR_ORDER_SSE, NREG, TRV, COREV, LDV> : mm_ws_kernel<RINGV, GR_ORDER_GENERIC, NREG, TRV, COREV, LDV>)
+    // the bulk-copy loader moves 16-byte multiples from 16-byte aligned addresses
+    const bool tma_ok = nchan % 4 == 0 && ((uintptr_t)d_in & 15) == 0;
+    int v = variant;
+    if (v >= 16 && !tma_ok) v = 13;
+    if (deep) k = v == 0 ? MMK(512, 48, 1, 1, 0) : MMK(512, 64, 1, 3, 0);
+    else switch (v) {
+      case 0: k = MMK(128, 48, 1, 1, 0); break;   // round-1 kernel, co-resident with the front kernels (47 KB)
+      case 1: k = MMK(128, 64, 1, 1, 0); break;
+      case 2: k = MMK(128, 64, 8, 1, 0); break;
+      case 3: k = MMK(128, 48, 1, 2, 0); break;
+      case 4: k = MMK(128, 64, 1, 2, 0); break;
+      case 5: k = MMK(128, 64, 8, 2, 0); break;
+      case 6: k = MMK(128, 80, 8, 2, 0); break;
+      case 7: k = MMK(128, 96, 8, 2, 0); break;
+      case 8: k = MMK(128, 128, 8, 2, 0); break;
+      case 9: k = MMK(128, 80, 1, 2, 0); break;
+      case 10: k = MMK(128, 48, 1, 3, 0); break;
+      case 11: k = MMK(128, 64, 1, 3, 0); break;
+      case 12: k = MMK(128, 64, 8, 3, 0); break;
+      case 13: k = MMK(128, 80, 8, 3, 0); break;
+      case 14: k = MMK(128, 96, 8, 3, 0); break;
+      case 15: k = MMK(128, 128, 8, 3, 0); break;
+      case 16: k = MMK(128, 80, 8, 3, 1); break;
+      case 17: k = MMK(128, 64, 8, 3, 1); break;
+      case 18: k = MMK(128, 64, 1, 3, 1); break;
+      case 19: k = MMK(128, 48, 1, 3, 1); break;
+      default: return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
+    }
+#undef MMK
+    const size_t smem = mm_ws_smem_bytes(ringrows, tabrep);
     GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
     k<<<grid, MMW_THREADS, smem, s>>>(a);
     GRB_LAUNCH_CHECK();
@@ -1134,6 +1167,22 @@ int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha
   h->slicer_levels = levels;
   h->slicer_alpha = alpha;
   h->slicer_beta = (float)(1.0 - alpha);  // pager_slicer_fb.cc:40
+  return GRCUDA_OK;
+}
+#ifdef MMW_STATS
+// lab build only (not declared in gr_cuda.h): reads and clears the core-warp counters of kernel_mm.cuh
+__attribute__((visibility("default"))) int grcuda_lab_mm_stats(unsigned long long* out12) {
+  GRB_CUDA(cudaDeviceSynchronize());
+  GRB_CUDA(cudaMemcpyFromSymbol(out12, grb::mmw_stats, 12 * sizeof(unsigned long long)));
+  unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  GRB_CUDA(cudaMemcpyToSymbol(grb::mmw_stats, z, sizeof z));
+  return GRCUDA_OK;
+}
+#endif
+int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant) {
+  if (variant < 0 || variant >= GRCUDA_MM_VARIANTS) return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->variant = variant;
   return GRCUDA_OK;
 }
 int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long abs_row0, const float* d_in,

@@ -105,6 +105,8 @@ struct MMArgs {
   int slicer_levels;     // 0, 2 or 4
   float slicer_alpha, slicer_beta;
   const float* mmse_eff; // [129][8] coefficients applied to in[ii+0..7]
+  float one;             // 1.0f, opaque to the compiler: acc + p is issued as fma(p, 1, acc) so that ptxas cannot
+                         // contract a packed multiply into the addition (kernel_demod_front.cuh)
 };
 
 // stand-alone slicer (single stream; the recurrence on d_avg is sequential when alpha != 0)

@@ -486,6 +486,9 @@ class clock_recovery_mm_ff(_Block):
     def set_gain_omega(self, g):
         _l.check(self.L.grcuda_clock_recovery_mm_ff_set_gain_omega(self.h, C.c_float(g)))
 
+    def set_kernel_variant(self, variant):
+        _l.check(self.L.grcuda_clock_recovery_mm_ff_set_kernel_variant(self.h, int(variant)))
+
     def set_slicer(self, levels, alpha=0.0):
         _l.check(self.L.grcuda_clock_recovery_mm_ff_set_slicer(self.h, int(levels), C.c_float(alpha)))
 

@@ -128,6 +128,10 @@ class DmrChain:
 
     STAGES = ("pfb_fir", "pfb_fft", "quad_demod", "rrc_fir", "mm_slicer", "map_unpack_corr", "carry_copies")
 
+    def set_tail_variant(self, variant):
+        """Which build of the clock-recovery kernel the tail runs (0 = sized to co-reside with the front kernels)."""
+        _l.check(self.L.grcuda_dmr_chain_set_tail_variant(self.h, int(variant)))
+
     def set_profiling(self, on):
         _l.check(self.L.grcuda_dmr_chain_set_profiling(self.h, int(bool(on))))
 

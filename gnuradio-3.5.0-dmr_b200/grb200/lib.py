@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libgr_cuda.so")
+# GRCUDA_LIB: another build of the SAME library (instrumented lab builds of tools/, see csrc/Makefile); never a fallback
+LIB_PATH = os.environ.get("GRCUDA_LIB") or os.path.join(_PKG, "libgr_cuda.so")
 
 OK, EINVAL, ERANGE, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 ORDER_GENERIC, ORDER_SSE = 0, 1

@@ -207,6 +207,12 @@ int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long
 /* slicer fused into the M&M epilogue: mode 0 none, 2 = gr_binary_slicer (gr_math.h:82-88),
  * 4 = pager_slicer_fb::slice with DC-tracking alpha (pager_slicer_fb.cc:47-69). */
 int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha);
+/* Which build of the clock-recovery kernel runs (all produce identical bits; tests/test_gpu_blocks.py checks every
+ * one against the oracle).  0 = 48 registers / 47 KB of shared memory, sized to co-reside with the front kernels
+ * of a single-GPU chain; the others trade that for a shorter per-symbol dependency chain when the kernel has the
+ * SMs to itself (time shards, stand-alone block).  GRCUDA_EINVAL for an unknown number. */
+int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant);
+#define GRCUDA_MM_VARIANTS 20
 
 /* stand-alone slicer blocks (host pointers) */
 typedef struct grcuda_slicer grcuda_slicer;
@@ -392,6 +398,8 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
 #define GRCUDA_NSTAGES 7
 int grcuda_pfb_channelizer_ccf_set_profiling(grcuda_pfb* h, int on);
 int grcuda_pfb_channelizer_ccf_profile_read(grcuda_pfb* h, float ms[2], int launches[2]);
+/* which build of the clock-recovery kernel the tail stage runs (grcuda_clock_recovery_mm_ff_set_kernel_variant) */
+int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant);
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on);
 int grcuda_dmr_chain_profile_read(grcuda_dmr_chain* h, float ms[GRCUDA_NSTAGES], int launches[GRCUDA_NSTAGES]);
 
