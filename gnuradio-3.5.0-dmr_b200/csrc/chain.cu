@@ -51,6 +51,7 @@ struct grcuda_dmr_chain {
   bool B_pending[2] = {false, false};
   int fcur = 0;           // F buffer of the block whose front ran last
   bool pipeline = true;   // tail on its own stream (overlaps the next block's front)
+  bool split_corr = true; // correlator as its own time-parallel kernel behind the clock-recovery kernel
   cudaStream_t tail_stream = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
   bool tail_pending[2] = {false, false};
@@ -375,11 +376,17 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
   //      over F rows [abs_row-KEEP, abs_row+R)
   if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
   h->prof.begin(4, s);
-  if ((rc = mm_corr_launch(h->mm, h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, F, KEEP + R,
-                           (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(), h->max_sym,
-                           h->counts.as<int>(), h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr,
-                           (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s)))
-    return rc;
+  rc = GRCUDA_EUNSUPPORTED;
+  if (h->split_corr && !h->keep_bytes)
+    rc = mm_then_corr_launch(h->mm, h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, F, KEEP + R,
+                             (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(), h->max_sym,
+                             h->counts.as<int>(), (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s);
+  if (rc == GRCUDA_EUNSUPPORTED)
+    rc = mm_corr_launch(h->mm, h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, F, KEEP + R,
+                        (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(), h->max_sym,
+                        h->counts.as<int>(), h->keep_bytes ? h->bytes.as<unsigned char>() : nullptr,
+                        (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s);
+  if (rc) return rc;
   h->prof.end(s);
   GRB_CUDA(cudaEventRecord(h->ev_tail[cur], s));
   h->tail_pending[cur] = true;
@@ -400,6 +407,10 @@ int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d
 
 int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant) {
   return grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, variant);
+}
+int grcuda_dmr_chain_set_split_correlator(grcuda_dmr_chain* h, int on) {
+  h->split_corr = on != 0;
+  return GRCUDA_OK;
 }
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on) {
   h->prof.on = on != 0;

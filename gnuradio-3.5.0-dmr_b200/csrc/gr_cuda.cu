@@ -12,6 +12,7 @@
 #include "internal.h"
 #include "kernels_demod.cuh"
 #include "kernel_mm.cuh"
+#include "kernel_mm_quad.cuh"
 #include "kernels_fir.cuh"
 
 using namespace grb;
@@ -1083,7 +1084,14 @@ struct grcuda_mm : PlanBase {
     // the bulk-copy loader moves 16-byte multiples from 16-byte aligned addresses
     const bool tma_ok = nchan % 4 == 0 && ((uintptr_t)d_in & 15) == 0;
     int v = variant;
-    if (v >= 16 && !tma_ok) v = 13;
+    if (v >= 16 && !tma_ok) v = 11;
+    size_t smem = 0;
+    if (v >= 20 && !deep) {  // quad ring + TMA staging (kernel_mm_quad.cuh)
+      k = v == 20 ? (sse ? mm_quad_kernel<GR_ORDER_SSE, 80> : mm_quad_kernel<GR_ORDER_GENERIC, 80>)
+        : v == 21 ? (sse ? mm_quad_kernel<GR_ORDER_SSE, 64> : mm_quad_kernel<GR_ORDER_GENERIC, 64>)
+                  : (sse ? mm_quad_kernel<GR_ORDER_SSE, 96> : mm_quad_kernel<GR_ORDER_GENERIC, 96>);
+      smem = mm_quad_smem_bytes();
+    } else
     if (deep) k = v == 0 ? MMK(512, 48, 1, 1, 0) : MMK(512, 64, 1, 3, 0);
     else switch (v) {
       case 0: k = MMK(128, 48, 1, 1, 0); break;   // round-1 kernel, co-resident with the front kernels (47 KB)
@@ -1109,7 +1117,7 @@ struct grcuda_mm : PlanBase {
       default: return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
     }
 #undef MMK
-    const size_t smem = mm_ws_smem_bytes(ringrows, tabrep);
+    if (!smem) smem = mm_ws_smem_bytes(ringrows, tabrep);
     GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
     k<<<grid, MMW_THREADS, smem, s>>>(a);
     GRB_LAUNCH_CHECK();
@@ -1292,6 +1300,30 @@ struct grcuda_corr : PlanBase {
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
   }
+  // time-parallel form (kernels_demod.cuh: corr_par_kernel): 2 bits per symbol, code length >= 16, no byte output
+  bool par_ok(int k, const unsigned char* d_out) {
+    std::lock_guard<std::mutex> lk(mu);
+    const int len = p.flag_bit ? 64 - (__builtin_ffsll((long long)p.flag_bit) - 1) : 0;
+    return k == 2 && d_out == nullptr && len >= 16;
+  }
+  int launch_par(const unsigned char* d_sym, const int* d_counts, int sym_rows, const int* map, int nmap, CorrHit* d_hits_,
+                 int max_hits, int* d_nhits_, cudaStream_t s) {
+    int rc;
+    if ((rc = d_state_next.reserve((size_t)nchan * sizeof(CorrChanState)))) return rc;
+    CorrParArgs a;
+    a.symbols = d_sym; a.counts = d_counts; a.nchan = nchan;
+    for (int i = 0; i < 256; i++) a.map[i] = (unsigned char)i;
+    for (int i = 0; i < std::min(nmap, 256); i++) a.map[i] = (unsigned char)map[i];
+    a.state_in = d_state.as<CorrChanState>(); a.state_out = d_state_next.as<CorrChanState>();
+    { std::lock_guard<std::mutex> lk(mu); a.p = p; }
+    a.hits = d_hits_; a.max_hits = max_hits; a.nhits = d_nhits_;
+    const dim3 grid((nchan + 127) / 128, std::max(1, (sym_rows + CORR_CHUNK - 1) / CORR_CHUNK));
+    corr_par_kernel<<<grid, 128, 0, s>>>(a);
+    GRB_LAUNCH_CHECK();
+    GRB_CUDA(cudaMemcpyAsync(d_state.p, d_state_next.p, (size_t)nchan * sizeof(CorrChanState), cudaMemcpyDeviceToDevice, s));
+    return GRCUDA_OK;
+  }
+  DevBuf d_state_next;
 };
 
 extern "C" {
@@ -1359,6 +1391,19 @@ int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, i
   f.max_hits = max_hits;
   f.nhits = d_nhits;
   return mm->launch(d_in, ninput, abs_row0, d_soft, d_sym, max_out, d_counts, s, &f);
+}
+// the same stage as two kernels: clock recovery + slicer (soft symbols and decisions to HBM), then the correlator
+// parallel over channels AND time.  The correlator leaves the kernel whose per-symbol latency bounds the tail (its
+// post warps were the bottleneck of the fused form: 0.73 ms against 0.56 ms without it) and the serial chain of a
+// time-sharded run.  Returns GRCUDA_EUNSUPPORTED when the parallel correlator does not apply.
+int mm_then_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const float* d_in,
+                        long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out, int* d_counts,
+                        grcuda_hit* d_hits, int max_hits, int* d_nhits, cudaStream_t s) {
+  if (mm->nchan != corr->nchan) return set_error(GRCUDA_EINVAL, "mm/corr channel counts differ");
+  if (!corr->par_ok(bits_per_symbol, nullptr) || !d_sym) return GRCUDA_EUNSUPPORTED;
+  int rc = mm->launch(d_in, ninput, abs_row0, d_soft, d_sym, max_out, d_counts, s, nullptr);
+  if (rc) return rc;
+  return corr->launch_par(d_sym, d_counts, max_out, map, nmap, (CorrHit*)d_hits, max_hits, d_nhits, s);
 }
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
   if (ntaps) *ntaps = h->ntaps;

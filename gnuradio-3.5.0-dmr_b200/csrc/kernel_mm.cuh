@@ -107,6 +107,7 @@ __device__ __forceinline__ bool mmw_mbar_test(uint64_t* bar, unsigned parity) {
 
 // ---- POST warp: takes soft symbols from the shared-memory queue, eight at a time: soft symbol -> HBM, slicer, dibit
 // map, bit unpack, access-code correlation, sync-hit list (shared by both clock-recovery kernels)
+template <int QD>
 __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState& st, const bool valid, const int c, const int cl,
                                               const unsigned q_lane, int* pub_done, const unsigned char* smap) {
   const size_t nchan = (size_t)a.nchan;
@@ -161,16 +162,20 @@ __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState
   };
 
   while (true) {
+    bool got = false;
     if (!finished) {
       unsigned slot[MMW_PB], w[MMW_PB];
 #pragma unroll
-      for (int i = 0; i < MMW_PB; i++) slot[i] = q_lane + (unsigned)((consumed + i) & (MMW_Q - 1)) * RP;
-#pragma unroll
-      for (int i = 0; i < MMW_PB; i++) w[i] = mmw_ldq(slot[i]);
-      bool full = true;
-#pragma unroll
-      for (int i = 0; i < MMW_PB; i++) full = full && (w[i] != MMW_EMPTY);
+      for (int i = 0; i < MMW_PB; i++) slot[i] = q_lane + (unsigned)((consumed + i) & (QD - 1)) * RP;
+      // The core fills the slots in order (in-order shared-memory stores of one warp), so the LAST slot of a batch
+      // being full means the whole batch is: ONE load per poll.  (Eight loads per poll from two post warps that had
+      // caught up with the core took ~40 % of the shared-memory pipe away from the loop they were waiting for.)
+      w[MMW_PB - 1] = mmw_ldq(slot[MMW_PB - 1]);
+      const bool full = w[MMW_PB - 1] != MMW_EMPTY;
       if (full) {
+        got = true;
+#pragma unroll
+        for (int i = 0; i < MMW_PB - 1; i++) w[i] = mmw_ldq(slot[i]);
 #pragma unroll
         for (int i = 0; i < MMW_PB; i++) mmw_stq(slot[i], MMW_EMPTY);
         if (windowed || !corr_on) {
@@ -196,7 +201,7 @@ __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState
           }
           op += MMW_PB * nchan;
           if (sp) sp += MMW_PB * nchan;
-          if (!corr_on) { consumed += MMW_PB; continue; }  // stand-alone block: soft symbols + slicer only
+          if (corr_on) {  // (the stand-alone block stops here: soft symbols + slicer only)
           const unsigned dhi = (unsigned)(cs.data_reg >> 32), dlo = (unsigned)cs.data_reg;
           const unsigned inb = bits16 << 16;
           // two stages: the mismatches of the upper word alone already exceed the threshold at almost every
@@ -222,6 +227,7 @@ __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState
           cs.data_reg = (cs.data_reg << 16) | bits16;
           cs.flag_reg = (cs.flag_reg << 16) | ((unsigned long long)mm << flag_shift);
           ob += 16;
+          }
         } else {
 #pragma unroll 1
           for (int i = 0; i < MMW_PB; i++) emit(__uint_as_float(w[i]));
@@ -233,18 +239,18 @@ __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState
         if (dn != 0) {
           const unsigned w0 = mmw_ldq(slot[0]);
           if (w0 != MMW_EMPTY) {
+            got = true;
             mmw_stq(slot[0], MMW_EMPTY);
             emit(__uint_as_float(w0));
             consumed++;
           } else if (consumed == dn - 1) {
             finished = true;
           }
-        } else {
-          __nanosleep(20);
         }
       }
     }
     if (__all_sync(0xffffffffu, finished)) break;
+    if (!__any_sync(0xffffffffu, got)) __nanosleep(200);  // a trip of the core takes ~600 ns, the queue holds 4 to 8
   }
   if (valid) {
     a.state[c].slicer_avg = avg;
@@ -966,7 +972,7 @@ __global__ void __maxnreg__(NREG) mm_ws_kernel(const MMArgs a) {
   }
 
   // ------------------------------------------------------------------------------ POST
-  mmw_post_warp(a, st, valid, c, cl, q_lane, pub_done, smap);
+  mmw_post_warp<MMW_Q>(a, st, valid, c, cl, q_lane, pub_done, smap);
 }
 
 }  // namespace grb

@@ -177,4 +177,94 @@ __global__ void __launch_bounds__(128) corr_kernel(const CorrArgs a) {
   a.state[c] = st;
 }
 
+// ---- gr_map_bb -> gr_unpack_k_bits_bb(2) -> digital_correlate_access_code_bb, parallel in TIME as well ----------
+// (digital_correlate_access_code_bb.cc:87-133.)  The block's output at bit i is a pure function of the 64 bits before
+// it: data_reg = bits [i-64, i-1]; a match at bit i (popcount((data_reg ^ code) & mask) <= threshold) raises the
+// flag that reaches bit 63 of flag_reg, i.e. the output, exactly `len` bits later.  So a thread that starts 64
+// symbols (128 bits >= 64 + len) before its chunk with zeroed registers has the sequential registers bit for bit by
+// the time its chunk begins, and chunks are independent: thread = (channel, chunk of CORR_CHUNK symbols).  Chunk 0
+// starts from the carried registers instead.  The chunk holding a channel's last symbol writes the registers to
+// state_out (a separate array: every chunk reads the old bit count); hits go to the shared list in any order.
+// Requirements (else the caller uses the sequential kernel): k = 2 bits per symbol, code length >= 16, no byte output.
+#define CORR_CHUNK 128
+struct CorrParArgs {
+  const unsigned char* symbols;  // [sym_rows][nchan] slicer decisions
+  const int* counts;             // [nchan]
+  int nchan;
+  unsigned char map[256];
+  const CorrChanState* state_in;
+  CorrChanState* state_out;
+  CorrParams p;
+  CorrHit* hits;
+  int max_hits;
+  int* nhits;
+};
+
+__global__ void __launch_bounds__(128) corr_par_kernel(const CorrParArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.nchan) return;
+  const int n = a.counts[c];
+  const int k = blockIdx.y;
+  const int s0 = k * CORR_CHUNK;
+  if (k > 0 && s0 >= n) return;
+  const int s1 = min(n, s0 + CORR_CHUNK);
+  const CorrChanState old = a.state_in[c];
+  unsigned long long data_reg = 0, flag_reg = 0;
+  int s = 0;
+  if (k == 0) { data_reg = old.data_reg; flag_reg = old.flag_reg; }
+  else s = s0 - 64;
+  const CorrParams cp = a.p;
+  const int code_len = cp.flag_bit ? 64 - (__ffsll((long long)cp.flag_bit) - 1) : 0;
+  const int flag_shift = 64 - code_len;
+  const unsigned code_hi = (unsigned)(cp.access_code >> 32), code_lo = (unsigned)cp.access_code;
+  const unsigned mask_hi = (unsigned)(cp.mask >> 32), mask_lo = (unsigned)cp.mask;
+  const size_t nchan = (size_t)a.nchan;
+  const unsigned char* sp = a.symbols + (size_t)s * nchan + c;
+  const long long first_bit = 2ll * s0;  // hits at bit positions >= this one are this chunk's to report
+  auto hit = [&](long long bit) {
+    if (bit < first_bit) return;
+    const int h = atomicAdd(a.nhits, 1);
+    if (h < a.max_hits) { a.hits[h].channel = c; a.hits[h].pad = 0; a.hits[h].bit_index = old.nbits + bit; }
+  };
+  // eight symbols = 16 bits at a time (same window form as the fused epilogue of the clock-recovery kernel)
+  for (; s + 8 <= s1; s += 8) {
+    unsigned bits16 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) bits16 |= ((unsigned)a.map[sp[(size_t)i * nchan]] & 3u) << (14 - 2 * i);
+    sp += 8 * nchan;
+    const unsigned dhi = (unsigned)(data_reg >> 32), dlo = (unsigned)data_reg;
+    const unsigned inb = bits16 << 16;
+    unsigned mm = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const unsigned shi = __funnelshift_l(dlo, dhi, j);
+      if (__popc((shi ^ code_hi) & mask_hi) <= cp.threshold) {
+        const unsigned slo = __funnelshift_l(inb, dlo, j);
+        const unsigned nwrong = __popc((shi ^ code_hi) & mask_hi) + __popc((slo ^ code_lo) & mask_lo);
+        mm |= (nwrong <= cp.threshold ? 1u : 0u) << (15 - j);
+      }
+    }
+    const unsigned hits16 = (unsigned)(flag_reg >> 48);
+    if (hits16) {
+      for (int j = 0; j < 16; j++)
+        if (hits16 & (0x8000u >> j)) hit(2ll * s + j);
+    }
+    data_reg = (data_reg << 16) | bits16;
+    flag_reg = (flag_reg << 16) | ((unsigned long long)mm << flag_shift);
+  }
+  for (; s < s1; s++) {  // fewer than eight symbols left: bit serial
+    const unsigned dib = a.map[*sp];
+    sp += nchan;
+    for (int b = 1; b >= 0; b--) {
+      const unsigned char t = corr_step(data_reg, flag_reg, cp, (dib >> b) & 1u);
+      if (t & 2) hit(2ll * s + (1 - b));
+    }
+  }
+  if (s1 == n && (k == 0 ? n <= CORR_CHUNK : true)) {  // this chunk holds the channel's last symbol (or there is none)
+    CorrChanState o;
+    o.data_reg = data_reg; o.flag_reg = flag_reg; o.nbits = old.nbits + 2ll * n;
+    a.state_out[c] = o;
+  }
+}
+
 }  // namespace grb

@@ -132,6 +132,9 @@ class DmrChain:
         """Which build of the clock-recovery kernel the tail runs (0 = sized to co-reside with the front kernels)."""
         _l.check(self.L.grcuda_dmr_chain_set_tail_variant(self.h, int(variant)))
 
+    def set_split_correlator(self, on):
+        _l.check(self.L.grcuda_dmr_chain_set_split_correlator(self.h, int(bool(on))))
+
     def set_profiling(self, on):
         _l.check(self.L.grcuda_dmr_chain_set_profiling(self.h, int(bool(on))))
 

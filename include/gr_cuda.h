@@ -212,7 +212,7 @@ int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha
  * of a single-GPU chain; the others trade that for a shorter per-symbol dependency chain when the kernel has the
  * SMs to itself (time shards, stand-alone block).  GRCUDA_EINVAL for an unknown number. */
 int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant);
-#define GRCUDA_MM_VARIANTS 20
+#define GRCUDA_MM_VARIANTS 23
 
 /* stand-alone slicer blocks (host pointers) */
 typedef struct grcuda_slicer grcuda_slicer;
@@ -400,6 +400,9 @@ int grcuda_pfb_channelizer_ccf_set_profiling(grcuda_pfb* h, int on);
 int grcuda_pfb_channelizer_ccf_profile_read(grcuda_pfb* h, float ms[2], int launches[2]);
 /* which build of the clock-recovery kernel the tail stage runs (grcuda_clock_recovery_mm_ff_set_kernel_variant) */
 int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant);
+/* 1 (default): the tail is two kernels, clock recovery + slicer, then the access-code correlator parallel over channels
+ * and time; 0: one fused kernel (always used when the correlator's byte stream is kept).  Identical results. */
+int grcuda_dmr_chain_set_split_correlator(grcuda_dmr_chain* h, int on);
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on);
 int grcuda_dmr_chain_profile_read(grcuda_dmr_chain* h, float ms[GRCUDA_NSTAGES], int launches[GRCUDA_NSTAGES]);
 

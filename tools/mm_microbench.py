@@ -112,7 +112,8 @@ def main():
                 "other_trips_per_warp": stats[3] / w, "cycles_per_other_trip": stats[2] / max(stats[3], 1),
                 "single_sections_per_warp": stats[5] / w, "cycles_per_single_section": stats[4] / max(stats[5], 1),
                 "core_cycles_per_warp": stats[6] / w, "lane_trips_blocked_by_queue_per_warp": stats[8] / w,
-                "lane_trips_blocked_by_input_per_warp": stats[9] / w, "lane_trips_stopped_half_way_per_warp": stats[10] / w}
+                "lane_trips_blocked_by_input_per_warp": stats[9] / w, "lane_trips_stopped_half_way_per_warp": stats[10] / w,
+                "raw": stats}
         results.append(r)
         print(json.dumps(r), flush=True)
         del out, sl, cnt
@@ -135,7 +136,8 @@ def chain_mode(args, torch, np, bench, lib, synth_torch, dev):
     results = []
     for v in [int(t) for t in args.variants.split(",")]:
         ch = chain.DmrChain(bench.chain_config(R))
-        ch.set_tail_variant(v)
+        ch.set_tail_variant(v % 100)
+        ch.set_split_correlator(v >= 100)    # variant + 100: correlator as its own kernel
         Th = ch.history_rows()
         x, _ = synth_torch.wideband_block(M, R, Th, args.active, 1234, dev)
         stream = torch.cuda.current_stream().cuda_stream
@@ -179,7 +181,8 @@ def chain_mode(args, torch, np, bench, lib, synth_torch, dev):
                 "other_trips_per_warp": stats[3] / w, "cycles_per_other_trip": stats[2] / max(stats[3], 1),
                 "single_sections_per_warp": stats[5] / w, "cycles_per_single_section": stats[4] / max(stats[5], 1),
                 "core_cycles_per_warp": stats[6] / w, "lane_trips_blocked_by_queue_per_warp": stats[8] / w,
-                "lane_trips_blocked_by_input_per_warp": stats[9] / w, "lane_trips_stopped_half_way_per_warp": stats[10] / w}
+                "lane_trips_blocked_by_input_per_warp": stats[9] / w, "lane_trips_stopped_half_way_per_warp": stats[10] / w,
+                "raw": stats}
         results.append(r)
         print(json.dumps(r), flush=True)
         del ch, x
