@@ -158,7 +158,18 @@ def run_reference(args):
     return 0
 
 
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write("[bench rank %s %.1f] %s\n" % (os.environ.get("RANK", "0"), time.time() % 1000, msg))
+        sys.stderr.flush()
+
+
 def run_ours(args):
+    # A time shard keeps ~12 streams busy (front, clock-recovery chain, correlator chain, halo, the chain object's own,
+    # one per NCCL communicator), several of them with kernels that spin until a peer arrives.  With the default 8
+    # hardware work queues, streams share queues, and a kernel can sit behind a spinning one of another stream: a
+    # cross-rank deadlock.  32 is the maximum.  (Must be set before the CUDA context exists.)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -189,111 +200,149 @@ def run_ours(args):
     cfg0 = chain_config(R)
     probe = chain.DmrChain(chain_config(512))
     halo = probe.warmup_rows() if world > 1 else 0   # extra input rows re-processed by each shard
+    if world > 1:
+        # Load every kernel of the sharded schedule before the first NCCL operation: the first launch of a kernel loads
+        # its module, which synchronises the device -- for ever, if a receive kernel is spinning on it for a peer that
+        # is itself waiting to load a kernel.
+        xp = torch.zeros((probe.history_rows() + 512, M), dtype=torch.complex64, device=dev)
+        s0 = torch.cuda.current_stream().cuda_stream
+        probe.process_front_device(xp, 512, s0)
+        probe.process_tail_mm_device(None, None, s0)
+        probe.process_tail_corr_device(None, None, s0)
+        torch.cuda.synchronize()
+        del xp
     del probe
     cfg = chain_config(R + halo)
     ch = chain.DmrChain(cfg)
+    if args.tail_variant is not None:
+        ch.set_tail_variant(args.tail_variant)
+    if args.fused_correlator:
+        ch.set_split_correlator(False)
     Th = ch.history_rows()
-    x, active = synth_torch.wideband_block(M, R, Th + halo, args.active, 1234 + rank, dev)   # [(Th+halo) + R][M]
+    # ONE stream for the whole job: the same periodic block on every rank (it tiles seamlessly in time), rank r takes
+    # blocks r, r + world, ...  The loop state, and therefore every symbol and sync hit, evolves from block to block.
+    x, active = synth_torch.wideband_block(M, R, Th + halo, args.active, 1234, dev)   # [(Th+halo) + R][M]
     plan = sharding.TimeShardPlan(world, rank, R, halo)
-    ring = sharding.RingExchanger(plan)
-    state = torch.zeros(ch.state_bytes(), dtype=torch.uint8, device=dev)
-    # Two copies of the input block, used alternately: the NCCL halo exchange of step s+1 writes the head of one
-    # while the front of step s still reads the other.  The exchange only depends on INPUT rows, so it is posted one
-    # step ahead on its own stream: the rendezvous of the two neighbours (which are one tail slot apart in time by
-    # construction) then never stalls a front, and its kernels do not sit on SMs next to the persistent FFT CTAs.
-    xbuf = [x, x.clone()] if world > 1 else [x]
     stream = torch.cuda.current_stream().cuda_stream
-    tail_ts = torch.cuda.Stream() if world > 1 else None
-    halo_ts = torch.cuda.Stream() if world > 1 else None
-    halo_ev, front_ev = [None, None], [None, None]
+    if world > 1:
+        from grb200 import shardrun
+        # Two copies of the input block, used alternately: the NCCL halo exchange of step s+1 writes the head of one
+        # while the front of step s still reads the other.
+        xbuf = [x, x.clone()]
+        sc = shardrun.ShardedChain(ch, plan, dev, R, halo, Th)
+        sc.post_halo(0, xbuf)
 
-    def post_halo(s):
-        """NCCL send/recv of the input halo of step s into xbuf[s % 2] (tap history + warm-up rows of the left block)."""
-        buf = xbuf[s % 2]
-        with torch.cuda.stream(halo_ts):
-            if front_ev[s % 2] is not None:
-                halo_ts.wait_event(front_ev[s % 2])                # the front of step s-2 has read this copy's head
-            works = ring.exchange_halo(buf[buf.shape[0] - (Th + halo):], buf[: Th + halo], s)
-            ring.wait_all(works)
-            halo_ev[s % 2] = torch.cuda.Event()
-            halo_ev[s % 2].record(halo_ts)
+        def step(s):
+            sc.step(s, xbuf, total_steps - 1)   # (total_steps: set below, before the first step)
 
-    def drain():
-        if world > 1:
-            with torch.cuda.stream(tail_ts):
-                ring.finish()
-            torch.cuda.current_stream().wait_stream(tail_ts)
-            torch.cuda.current_stream().wait_stream(halo_ts)
-        ch.join(stream)
+        def drain():
+            sc.drain()
+    else:
+        ch.set_accumulate_hits(True)
+        ch.clear_hits(stream)
 
-    def step(s, last):
-        if world == 1:
+        def step(s):
             ch.process_device(x, R, stream)     # on torch's current stream: the timing events live there
-            return
-        cur = torch.cuda.current_stream()
-        cur.wait_event(halo_ev[s % 2])                              # this step's halo has landed
-        ch.seek_async(plan.abs_start(s) - halo, stream)
-        if plan.front_after_own_tail:
-            # 2+ ranks: the front runs after the rank's own previous tail instead of underneath it (the two slow each
-            # other down by 20-50 %), so the serial tail chain, which caps the whole job, runs at its stand-alone speed
-            cur.wait_stream(tail_ts)
-        ch.process_front_device(xbuf[s % 2], halo + R, stream)        # all ranks concurrently
-        front_ev[s % 2] = torch.cuda.Event()
-        front_ev[s % 2].record(cur)
-        post_halo(s + 1)                                            # one exchange per step, one step ahead
-        # The tails form ONE serial chain over all blocks of all ranks (block b's clock recovery starts from block
-        # b-1's final loop state), so they run on a side stream: this rank's main stream goes on to the next front
-        # while its tail waits for the left neighbour's state.
-        with torch.cuda.stream(tail_ts):
-            ts = tail_ts.cuda_stream
-            # the NCCL receive spins on an SM until the left neighbour's tail has finished: posted before the front is
-            # done it takes that SM away from the front's persistent one-CTA-per-SM FFT, which then needs a second wave
-            tail_ts.wait_event(front_ev[s % 2])
-            if ring.recv_state(state, s):                           # loop state of block b-1 (ring)
-                ch.import_state(state, ts)
-            ch.process_tail_device(ts)
-            ch.export_state(state, ts)
-            ring.send_state(state, s, last)
 
-    if world > 1:
-        post_halo(0)
-    total_steps = args.warmup + args.steps
-    for s in range(args.warmup):
-        step(s, total_steps - 1)
-    if world > 1:
-        with torch.cuda.stream(tail_ts):
-            ring.prepost_recv(state, args.warmup)   # lets the neighbour's last warm-up send complete before the sync
-    drain()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+        def drain():
+            ch.join(stream)
+
+    # Regions: W warm-up steps | K timed steps (the contract's number) | S more steps, >= --sustain-seconds of back-to-back
+    # work, timed separately so that the clock sampler sees the steady state (same stream, same chain, continuing).
+    def region(first, count, timed):
+        _dbg("region %d +%d" % (first, count))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for s in range(first, first + count):
+            step(s)
+        if world > 1 and first + count < total_steps:
+            sc.prepost(first + count)
+        drain()          # the tails run on side streams: a region ends when the last one has
+        e1.record()
+        _dbg("region %d: all launched" % first)
+        if world > 1:
+            sc.report(4.0)
+        torch.cuda.synchronize()
+        _dbg("region %d: synchronized" % first)
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # the sustained region's step count must be known before the first step (the very last block sends no state on)
+    n_sustain = 0
+    if args.sustain_seconds > 0:
+        est_ms = {1: 1.9, 2: 2.2, 4: 2.8, 8: 5.2}.get(world, 5.2) * R / 12500.0
+        n_sustain = int(min(4000, max(8, args.sustain_seconds * 1e3 / est_ms)))
+    main_steps = args.warmup + args.steps
+    total_steps = main_steps + n_sustain
+    region(0, args.warmup, False)
     ch.set_profiling(True)
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = lib.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for s in range(args.warmup, total_steps):
-        step(s, total_steps - 1)
-    drain()              # the tails run on a side stream: the timed region ends when the last one has
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+    ms_max = region(args.warmup, args.steps, True)
     launches = lib.launches() - n0
     clocks = sampler.stop() if sampler else None
     prof = ch.profile_read()
     ch.set_profiling(False)
-    hits, nhits = ch.read_hits(16)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms = ms_max
+
+    # ---- final result gather + parity of the whole job against ONE chain running the same stream ----------------------
+    # (every sync hit of every block of every rank, as (channel, absolute bit index); outside the timed region)
+    parity = None
+    _dbg("gathering hits")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    hit_counts = sharding.gather_counts(nhits, world, dev)            # final result gather
+        allhits = sc.gather_hits()
+    else:
+        hh, nh_all = ch.read_hits_array(ch.max_hits())
+        allhits = torch.stack([torch.from_numpy(hh["channel"].astype("int64")), torch.from_numpy(hh["bit_index"].astype("int64"))], 1).to(dev)
+    if rank == 0:
+        from grb200 import shardrun as _sr
+        csum, cnt = _sr.hit_checksum(allhits)
+        parity = {"blocks": world * main_steps, "sync_hits": cnt, "checksum": csum}
+        if world > 1 and not args.no_verify:
+            ref = chain.DmrChain(cfg)
+            ref.set_accumulate_hits(False)
+            parts = []
+            for b in range(world * main_steps):
+                if b == 0:
+                    ref.seek_async(-halo, stream)
+                    ref.process_front_device(x, halo + R, stream)
+                else:
+                    ref.process_front_device(x[halo:], R, stream)
+                ref.process_tail_device(stream)
+                hb, nb = ref.read_hits_array(ref.max_hits())
+                parts.append(torch.stack([torch.from_numpy(hb["channel"].astype("int64")),
+                                          torch.from_numpy(hb["bit_index"].astype("int64"))], 1))
+            refhits = torch.cat(parts).to(dev)
+            rsum, rcnt = _sr.hit_checksum(refhits)
+
+            def canon(tt):
+                key = tt[:, 1] * 65536 + tt[:, 0]
+                return torch.sort(key).values
+            same = rcnt == cnt and bool(torch.equal(canon(refhits), canon(allhits)))
+            parity.update({"single_chain_sync_hits": rcnt, "single_chain_checksum": rsum, "identical_to_single_chain": same})
+            del ref
+            assert same, "sharded run differs from the single chain: %r" % (parity,)
+    _dbg("parity %r" % (parity,))
+    # ---- sustained region (clocks under load) -------------------------------------------------------------------------
+    sustained = None
+    if n_sustain > 0:
+        ch.set_accumulate_hits(False)
+        sampler2 = ClockSampler(local) if rank == 0 else None
+        ms_sus = region(main_steps, n_sustain, True)
+        clocks2 = sampler2.stop() if sampler2 else None
+        sustained = {"value": world * n_sustain * R * M / (ms_sus * 1e-3) / 1e6, "unit": "MS/s", "steps": n_sustain,
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sustain, "clocks": clocks2}
     samples_per_step = R * M
     value = world * args.steps * samples_per_step / (ms_max * 1e-3) / 1e6
 
+    _dbg("e2e")
     # ---- end to end through the host-pointer C ABI (pinned host input, H2D + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     host = torch.empty((Th + R, M), dtype=torch.complex64, pin_memory=True)
@@ -399,7 +448,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": (Th + R) * M * 8, "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps, "api": "grcuda_dmr_chain_process_host + grcuda_dmr_chain_read_hits (pinned host input)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "sync_hits_last_step": hit_counts,
+        "parity": parity, "sustained": sustained,
     }
     if json_fd is not None:
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -434,6 +483,10 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of one pass of the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work to time for the baseline beside the GPU number")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra, separately timed steady-state region (0: none)")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the comparison of all sync hits with a single chain")
+    ap.add_argument("--tail-variant", type=int, default=None, help="build of the clock-recovery kernel (default: the chain's choice)")
+    ap.add_argument("--fused-correlator", action="store_true", help="correlator inside the clock-recovery kernel (round-1 form)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # the reference arm's steps are bounded samples (--cpu-rows) so that K steps finish within minutes

@@ -52,9 +52,13 @@ struct grcuda_dmr_chain {
   int fcur = 0;           // F buffer of the block whose front ran last
   bool pipeline = true;   // tail on its own stream (overlaps the next block's front)
   bool split_corr = true; // correlator as its own time-parallel kernel behind the clock-recovery kernel
+  int tail_variant = -1;  // user's choice of clock-recovery kernel; -1: by mode (see process_tail_device)
+  bool split_user = false, under_front = false;
   cudaStream_t tail_stream = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
   bool tail_pending[2] = {false, false};
+  cudaEvent_t ev_mm = nullptr, ev_corr = nullptr;  // two-kernel tail of a time shard: clock recovery done / correlator done
+  bool corr_pending = false, mm_pending = false;
   cudaEvent_t ev_state = nullptr;  // export/import_state copies (they touch what the tail kernel reads and writes)
   bool state_pending = false;
   int prev_rows = 0;      // rows of the previous block (where its F tail sits)
@@ -84,6 +88,8 @@ struct grcuda_dmr_chain {
       if (ev_B[i]) cudaEventDestroy(ev_B[i]);
     }
     if (ev_state) cudaEventDestroy(ev_state);
+    if (ev_mm) cudaEventDestroy(ev_mm);
+    if (ev_corr) cudaEventDestroy(ev_corr);
     for (int i = 0; i < 2; i++) {
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -163,7 +169,9 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
       cudaEventCreateWithFlags(&h->ev_front[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_mm, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_corr, cudaEventDisableTiming) != cudaSuccess) {
     set_error(GRCUDA_ECUDA, "dmr_chain: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
     return nullptr;
@@ -224,6 +232,7 @@ int grcuda_dmr_chain_join(grcuda_dmr_chain* h, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
   for (int i = 0; i < 2; i++)
     if (h->tail_pending[i]) GRB_CUDA(cudaStreamWaitEvent(s, h->ev_tail[i], 0));
+  if (h->corr_pending) GRB_CUDA(cudaStreamWaitEvent(s, h->ev_corr, 0));
   return GRCUDA_OK;
 }
 int grcuda_dmr_chain_export_state(grcuda_dmr_chain* h, void* d_state, void* stream_) {
@@ -375,9 +384,16 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
   // 4+5. clock recovery + slicer + (dibit map -> bits -> sync correlation fused in the same kernel)
   //      over F rows [abs_row-KEEP, abs_row+R)
   if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  // Which kernels: a tail that runs UNDERNEATH the next block's front (single-GPU pipeline) is the 48-register /
+  // 47 KB build with the correlator fused, which co-resides with the front kernels (measured: 1.85 ms per block
+  // against 2.05 ms with the stand-alone build, whose 198 KB of shared memory keep the front off its 125 SMs); a tail
+  // that has the device to itself is the quad-ring kernel followed by the time-parallel correlator (0.59 ms against
+  // 0.74 ms).  Explicit choices (set_tail_variant / set_split_correlator) win.
+  const bool split = h->split_user ? h->split_corr : !h->under_front;
+  if (h->tail_variant < 0) grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, h->under_front ? 10 : -1);
   h->prof.begin(4, s);
   rc = GRCUDA_EUNSUPPORTED;
-  if (h->split_corr && !h->keep_bytes)
+  if (split && !h->keep_bytes)
     rc = mm_then_corr_launch(h->mm, h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, F, KEEP + R,
                              (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(), h->max_sym,
                              h->counts.as<int>(), (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), s);
@@ -397,19 +413,88 @@ int grcuda_dmr_chain_process_tail_device(grcuda_dmr_chain* h, void* stream_) {
   return GRCUDA_OK;
 }
 
+// The tail as its two kernels on two streams, for a time shard: the clock-recovery kernel is the serial
+// chain over all blocks of all ranks, so nothing else sits on it -- it reads the loop state where the left neighbour's
+// send landed (d_mm_state_in, nullptr: the chain's own) and writes its final state to d_mm_state_out as well (what
+// the send to the right neighbour starts from); the correlator follows on its own stream with its own (small) state
+// ring.  GRCUDA_EUNSUPPORTED when the time-parallel correlator does not apply (then use process_tail_device).
+int grcuda_dmr_chain_process_tail_mm_device(grcuda_dmr_chain* h, const void* d_mm_state_in, void* d_mm_state_out, void* stream_) {
+  if (h->front_rows <= 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_tail_mm without a pending process_front");
+  if (h->keep_bytes) return GRCUDA_EUNSUPPORTED;
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  const long R = h->front_rows;
+  const int cur = h->fcur;
+  int rc;
+  float* F = h->Fb[cur].as<float>();
+  GRB_CUDA(cudaStreamWaitEvent(s, h->ev_front[cur], 0));
+  if (h->state_pending) { GRB_CUDA(cudaStreamWaitEvent(s, h->ev_state, 0)); h->state_pending = false; }
+  // the symbol buffers are single: the previous block's correlator must have read them
+  if (h->corr_pending) GRB_CUDA(cudaStreamWaitEvent(s, h->ev_corr, 0));
+  if (h->tail_variant < 0) grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, -1);
+  h->prof.begin(4, s);
+  if ((rc = mm_only_launch(h->mm, F, KEEP + R, (long)(h->abs_row - KEEP), h->soft.as<float>(), h->sym.as<unsigned char>(),
+                           h->max_sym, h->counts.as<int>(), d_mm_state_in, d_mm_state_out, s)))
+    return rc;
+  h->prof.end(s);
+  GRB_CUDA(cudaEventRecord(h->ev_mm, s));
+  GRB_CUDA(cudaEventRecord(h->ev_tail[cur], s));  // F is only read by this kernel
+  h->tail_pending[cur] = true;
+  h->mm_pending = true;
+  h->abs_row += R;
+  h->last_rows = (int)R;
+  h->prev_rows = (int)R;
+  h->front_rows = 0;
+  h->last_stream = s;
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_process_tail_corr_device(grcuda_dmr_chain* h, const void* d_corr_state_in, void* d_corr_state_out, void* stream_) {
+  if (!h->mm_pending) return set_error(GRCUDA_EINVAL, "dmr_chain: process_tail_corr without a pending process_tail_mm");
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  GRB_CUDA(cudaStreamWaitEvent(s, h->ev_mm, 0));
+  if (!h->accumulate_hits) GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  h->prof.begin(5, s);
+  int rc = corr_par_launch(h->corr, h->symbol_map.data(), (int)h->symbol_map.size(), 2, h->sym.as<unsigned char>(), h->counts.as<int>(),
+                           h->max_sym, (grcuda_hit*)h->hits.p, h->max_hits, h->nhits.as<int>(), d_corr_state_in, d_corr_state_out, s);
+  if (rc) return rc;
+  h->prof.end(s);
+  GRB_CUDA(cudaEventRecord(h->ev_corr, s));
+  h->corr_pending = true;
+  h->mm_pending = false;
+  h->last_stream = s;
+  return GRCUDA_OK;
+}
+size_t grcuda_dmr_chain_mm_state_bytes(grcuda_dmr_chain* h) { return mm_state_bytes(h->mm); }
+size_t grcuda_dmr_chain_corr_state_bytes(grcuda_dmr_chain* h) { return corr_state_bytes(h->corr); }
+
 int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
   int rc = front_impl(h, d_in, nrows, s, (h->pipeline && h->three_stage) ? h->mid_stream : s);
   if (rc) return rc;
   // the tail goes to the chain's own stream: it overlaps the front of the next block
-  return grcuda_dmr_chain_process_tail_device(h, h->pipeline ? (void*)h->tail_stream : stream_);
+  h->under_front = h->pipeline;
+  rc = grcuda_dmr_chain_process_tail_device(h, h->pipeline ? (void*)h->tail_stream : stream_);
+  h->under_front = false;
+  return rc;
 }
 
 int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant) {
-  return grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, variant);
+  int rc = grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, variant);
+  if (!rc) h->tail_variant = variant;
+  return rc;
 }
+int grcuda_dmr_chain_set_accumulate_hits(grcuda_dmr_chain* h, int on) {
+  h->accumulate_hits = on != 0;
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_clear_hits(grcuda_dmr_chain* h, void* stream_) {
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
+  GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), s));
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_max_hits(grcuda_dmr_chain* h) { return h->max_hits; }
 int grcuda_dmr_chain_set_split_correlator(grcuda_dmr_chain* h, int on) {
   h->split_corr = on != 0;
+  h->split_user = true;
   return GRCUDA_OK;
 }
 int grcuda_dmr_chain_set_profiling(grcuda_dmr_chain* h, int on) {
@@ -447,7 +532,8 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
   const size_t buf_bytes = (size_t)(h->T + sub) * M * sizeof(float2);
   for (int i = 0; i < 2; i++)
     if ((rc = h->d_stage[i].reserve(buf_bytes))) return rc;
-  {
+  const bool user_accumulates = h->accumulate_hits;
+  if (!user_accumulates) {
     cudaStream_t ts = h->pipeline ? h->tail_stream : h->stream;  // where the tails of the sub-blocks run
     GRB_CUDA(cudaMemsetAsync(h->nhits.p, 0, sizeof(int), ts));
   }
@@ -457,19 +543,19 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
     int n = std::min(sub, nrows - done);
     if (nrows - (done + n) > 0 && nrows - (done + n) < minr) n = nrows - done;  // fold a short tail
     const int b = i & 1;
-    if (n > sub && (rc = h->d_stage[b].reserve((size_t)(h->T + n) * M * sizeof(float2)))) { h->accumulate_hits = false; return rc; }
+    if (n > sub && (rc = h->d_stage[b].reserve((size_t)(h->T + n) * M * sizeof(float2)))) { h->accumulate_hits = user_accumulates; return rc; }
     if (i >= 2) GRB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));  // buffer b free again
     // host rows [done, done + T + n) : T history rows + n new rows of this sub-block
     if ((rc = h->stager.h2d(h->d_stage[b].p, (const char*)in + (size_t)done * M * sizeof(float2),
-                            (size_t)(h->T + n) * M * sizeof(float2), h->copy_stream))) { h->accumulate_hits = false; return rc; }
+                            (size_t)(h->T + n) * M * sizeof(float2), h->copy_stream))) { h->accumulate_hits = user_accumulates; return rc; }
     GRB_CUDA(cudaEventRecord(h->ev_copied[b], h->copy_stream));
     GRB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
-    if ((rc = grcuda_dmr_chain_process_device(h, (const grcuda_complex*)h->d_stage[b].p, n, h->stream))) { h->accumulate_hits = false; return rc; }
+    if ((rc = grcuda_dmr_chain_process_device(h, (const grcuda_complex*)h->d_stage[b].p, n, h->stream))) { h->accumulate_hits = user_accumulates; return rc; }
     GRB_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
     done += n;
     i++;
   }
-  h->accumulate_hits = false;
+  h->accumulate_hits = user_accumulates;
   GRB_CUDA(cudaStreamSynchronize(h->stream));
   if (h->last_stream) GRB_CUDA(cudaStreamSynchronize(h->last_stream));
   return GRCUDA_OK;

@@ -1038,7 +1038,7 @@ struct grcuda_mm : PlanBase {
   float min_omega = 0, max_omega = 0, omega_mid = 0;
   int slicer_levels = 0;
   float slicer_alpha = 0, slicer_beta = 1;
-  int variant = 0;  // which build of mm_ws_kernel runs (grcuda_clock_recovery_mm_ff_set_kernel_variant)
+  int variant = -1;  // which build of the kernel runs (grcuda_clock_recovery_mm_ff_set_kernel_variant); -1 = automatic
   DeviceTables tabs;
   DevBuf d_state, d_counts, d_slice;
   void calc_omega(float omega) {  // set_omega (digital_clock_recovery_mm_ff.h:75-80)
@@ -1058,12 +1058,13 @@ struct grcuda_mm : PlanBase {
     return GRCUDA_OK;
   }
   int launch(const float* d_in, long ninput, long abs_row0, float* d_out, unsigned char* d_sl, int max_out, int* d_cnt,
-             cudaStream_t s, const MMCorrFuse* fuse = nullptr) {
+             cudaStream_t s, const MMCorrFuse* fuse = nullptr, const void* d_state_in = nullptr, void* d_state_out2 = nullptr) {
     MMArgs a;
     memset(&a.corr, 0, sizeof a.corr);
     if (fuse) a.corr = *fuse;
     a.in = d_in; a.ninput = ninput; a.abs_row0 = abs_row0; a.nchan = nchan; a.out = d_out; a.sliced = d_sl;
     a.max_out = max_out; a.counts = d_cnt; a.state = d_state.as<MMChanState>();
+    a.state_in = (const MMChanState*)d_state_in; a.state_out2 = (MMChanState*)d_state_out2;
     {
       std::lock_guard<std::mutex> lk(mu);
       a.p.gain_omega = gain_omega; a.p.gain_mu = gain_mu; a.p.omega_mid = omega_mid; a.p.omega_relative_limit = limit;
@@ -1084,6 +1085,8 @@ struct grcuda_mm : PlanBase {
     // the bulk-copy loader moves 16-byte multiples from 16-byte aligned addresses
     const bool tma_ok = nchan % 4 == 0 && ((uintptr_t)d_in & 15) == 0;
     int v = variant;
+    // automatic: the quad-ring kernel when its 16-byte staging copies apply, else the per-lane loader with the same core
+    if (v < 0) v = tma_ok ? 21 : 11;
     if (v >= 16 && !tma_ok) v = 11;
     size_t smem = 0;
     if (v >= 20 && !deep) {  // quad ring + TMA staging (kernel_mm_quad.cuh)
@@ -1188,7 +1191,7 @@ __attribute__((visibility("default"))) int grcuda_lab_mm_stats(unsigned long lon
 }
 #endif
 int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant) {
-  if (variant < 0 || variant >= GRCUDA_MM_VARIANTS) return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
+  if (variant < -1 || variant >= GRCUDA_MM_VARIANTS) return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
   std::lock_guard<std::mutex> lk(h->mu);
   h->variant = variant;
   return GRCUDA_OK;
@@ -1307,9 +1310,10 @@ struct grcuda_corr : PlanBase {
     return k == 2 && d_out == nullptr && len >= 16;
   }
   int launch_par(const unsigned char* d_sym, const int* d_counts, int sym_rows, const int* map, int nmap, CorrHit* d_hits_,
-                 int max_hits, int* d_nhits_, cudaStream_t s) {
+                 int max_hits, int* d_nhits_, cudaStream_t s, const void* ext_in = nullptr, void* ext_out = nullptr) {
     int rc;
     if ((rc = d_state_next.reserve((size_t)nchan * sizeof(CorrChanState)))) return rc;
+    if (ext_in) GRB_CUDA(cudaMemcpyAsync(d_state.p, ext_in, (size_t)nchan * sizeof(CorrChanState), cudaMemcpyDeviceToDevice, s));
     CorrParArgs a;
     a.symbols = d_sym; a.counts = d_counts; a.nchan = nchan;
     for (int i = 0; i < 256; i++) a.map[i] = (unsigned char)i;
@@ -1321,6 +1325,7 @@ struct grcuda_corr : PlanBase {
     corr_par_kernel<<<grid, 128, 0, s>>>(a);
     GRB_LAUNCH_CHECK();
     GRB_CUDA(cudaMemcpyAsync(d_state.p, d_state_next.p, (size_t)nchan * sizeof(CorrChanState), cudaMemcpyDeviceToDevice, s));
+    if (ext_out) GRB_CUDA(cudaMemcpyAsync(ext_out, d_state_next.p, (size_t)nchan * sizeof(CorrChanState), cudaMemcpyDeviceToDevice, s));
     return GRCUDA_OK;
   }
   DevBuf d_state_next;
@@ -1404,6 +1409,18 @@ int mm_then_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nm
   int rc = mm->launch(d_in, ninput, abs_row0, d_soft, d_sym, max_out, d_counts, s, nullptr);
   if (rc) return rc;
   return corr->launch_par(d_sym, d_counts, max_out, map, nmap, (CorrHit*)d_hits, max_hits, d_nhits, s);
+}
+// the two halves separately, for a time shard: the clock-recovery kernel reads the loop state where the left
+// neighbour's was received and writes its final state where the right neighbour's send starts from
+int mm_only_launch(grcuda_mm* mm, const float* d_in, long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out,
+                   int* d_counts, const void* d_state_in, void* d_state_out, cudaStream_t s) {
+  return mm->launch(d_in, ninput, abs_row0, d_soft, d_sym, max_out, d_counts, s, nullptr, d_state_in, d_state_out);
+}
+int corr_par_launch(grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const unsigned char* d_sym, const int* d_counts,
+                    int max_out, grcuda_hit* d_hits, int max_hits, int* d_nhits, const void* d_state_in, void* d_state_out,
+                    cudaStream_t s) {
+  if (!corr->par_ok(bits_per_symbol, nullptr)) return GRCUDA_EUNSUPPORTED;
+  return corr->launch_par(d_sym, d_counts, max_out, map, nmap, (CorrHit*)d_hits, max_hits, d_nhits, s, d_state_in, d_state_out);
 }
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order) {
   if (ntaps) *ntaps = h->ntaps;

@@ -16,6 +16,11 @@ int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, i
 int mm_then_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const float* d_in,
                         long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out, int* d_counts,
                         grcuda_hit* d_hits, int max_hits, int* d_nhits, cudaStream_t s);
+int mm_only_launch(grcuda_mm* mm, const float* d_in, long ninput, long abs_row0, float* d_soft, unsigned char* d_sym, int max_out,
+                   int* d_counts, const void* d_state_in, void* d_state_out, cudaStream_t s);
+int corr_par_launch(grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const unsigned char* d_sym, const int* d_counts,
+                    int max_out, grcuda_hit* d_hits, int max_hits, int* d_nhits, const void* d_state_in, void* d_state_out,
+                    cudaStream_t s);
 // fused quadrature_demod_cf + fir_filter_fff (SSE order) on [time][channel] data (demod_front.cu)
 int demod_front_max_taps();
 int demod_front_history(int ntaps);

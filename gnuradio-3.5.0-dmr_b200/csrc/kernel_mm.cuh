@@ -254,6 +254,7 @@ __device__ __forceinline__ void mmw_post_warp(const MMArgs& a, const MMChanState
   }
   if (valid) {
     a.state[c].slicer_avg = avg;
+    if (a.state_out2) a.state_out2[c].slicer_avg = avg;
     if (corr_on) { cs.nbits += ob; a.corr.state[c] = cs; }
   }
 }
@@ -304,7 +305,7 @@ __global__ void __maxnreg__(NREG) mm_ws_kernel(const MMArgs a) {
   const int ni = ninput - 8;  // :112
   MMChanState st;
   st.mu = 0.f; st.omega = 0.f; st.last_sample = 0.f; st.slicer_avg = 0.f; st.next_abs = a.abs_row0; st.clamped = 0; st.overflow = 0;
-  if (valid) st = a.state[c];
+  if (valid) st = (a.state_in ? a.state_in : a.state)[c];
   // floor(mu) can be negative when gain_mu*mm_val < -omega (unnormalised input): the reference then
   // re-reads older items of its circular buffer.  The caller keeps a carry of older rows in front of
   // each block for that; stepping even further back is clamped (and counted) instead of reading
@@ -553,6 +554,11 @@ __global__ void __maxnreg__(NREG) mm_ws_kernel(const MMArgs a) {
       sp->next_abs = a.abs_row0 + ii;
       sp->clamped = st.clamped + clamped;
       sp->overflow = st.overflow + (ii < ni ? 1 : 0);
+      if (a.state_out2) {  // the same state where the right-hand time shard reads it (no copy on the serial chain)
+        MMChanState* s2 = a.state_out2 + c;
+        s2->mu = mu; s2->omega = omega; s2->last_sample = last;
+        s2->next_abs = sp->next_abs; s2->clamped = sp->clamped; s2->overflow = sp->overflow;
+      }
       a.counts[c] = oo;
     }
     return;
@@ -722,6 +728,11 @@ __global__ void __maxnreg__(NREG) mm_ws_kernel(const MMArgs a) {
       sp->next_abs = a.abs_row0 + ii;
       sp->clamped = st.clamped + clamped;
       sp->overflow = st.overflow + (ii < ni ? 1 : 0);
+      if (a.state_out2) {  // the same state where the right-hand time shard reads it (no copy on the serial chain)
+        MMChanState* s2 = a.state_out2 + c;
+        s2->mu = mu; s2->omega = omega; s2->last_sample = last;
+        s2->next_abs = sp->next_abs; s2->clamped = sp->clamped; s2->overflow = sp->overflow;
+      }
       a.counts[c] = oo;
     }
     return;
@@ -966,6 +977,11 @@ __global__ void __maxnreg__(NREG) mm_ws_kernel(const MMArgs a) {
       sp->next_abs = a.abs_row0 + ii;
       sp->clamped = st.clamped + clamped;
       sp->overflow = st.overflow + (ii < ni ? 1 : 0);
+      if (a.state_out2) {  // the same state where the right-hand time shard reads it (no copy on the serial chain)
+        MMChanState* s2 = a.state_out2 + c;
+        s2->mu = mu; s2->omega = omega; s2->last_sample = last;
+        s2->next_abs = sp->next_abs; s2->clamped = sp->clamped; s2->overflow = sp->overflow;
+      }
       a.counts[c] = oo;
     }
     return;

@@ -88,7 +88,7 @@ __global__ void __maxnreg__(NREG) mm_quad_kernel(const MMArgs a) {
   const int ni = ninput - 8;  // :112
   MMChanState st;
   st.mu = 0.f; st.omega = 0.f; st.last_sample = 0.f; st.slicer_avg = 0.f; st.next_abs = a.abs_row0; st.clamped = 0; st.overflow = 0;
-  if (valid) st = a.state[c];
+  if (valid) st = (a.state_in ? a.state_in : a.state)[c];
   int ii0 = (int)(st.next_abs - a.abs_row0);  // may be > 0: samples already consumed
   const bool clamp0 = ii0 < 0;                // (see mm_ws_kernel: a step before the first buffered row is clamped and counted)
   if (clamp0) ii0 = 0;
@@ -142,7 +142,7 @@ __global__ void __maxnreg__(NREG) mm_quad_kernel(const MMArgs a) {
     while (g < last_g) {
       // ---- issue whatever the staging ring has room for (both converters must be done with the slot) ----------
       if (w == 0) {
-        const int done_g = min(g, mmw_ldv(misc + 1));
+        const int done_g = max(first_g, min(g, mmw_ldv(misc + 1)));  // (misc starts at 0, the groups at first_g)
         while (next_g < last_g && next_g - done_g < NB) {
           // 16-byte asynchronous copies (LDGSTS.128): a warp instruction moves two 256-byte row segments, a group
           // of G rows is G/2 instructions; every lane then makes the group's mbarrier track its copies
@@ -435,6 +435,11 @@ __global__ void __maxnreg__(NREG) mm_quad_kernel(const MMArgs a) {
       sp->next_abs = a.abs_row0 + ii;
       sp->clamped = st.clamped + clamped;
       sp->overflow = st.overflow + (ii < ni ? 1 : 0);
+      if (a.state_out2) {  // the same state where the right-hand time shard reads it (no copy on the serial chain)
+        MMChanState* s2 = a.state_out2 + c;
+        s2->mu = mu; s2->omega = omega; s2->last_sample = last;
+        s2->next_abs = sp->next_abs; s2->clamped = sp->clamped; s2->overflow = sp->overflow;
+      }
       a.counts[c] = oo;
     }
     return;

@@ -100,6 +100,9 @@ struct MMArgs {
   int max_out;
   int* counts;           // [nchan]
   MMChanState* state;    // [nchan]
+  const MMChanState* state_in;  // nullptr, or where the initial state is read instead (a time shard: the buffer
+                                // the left neighbour's final state was received into)
+  MMChanState* state_out2;      // nullptr, or a second place the final state is written to (the send buffer)
   MMParams p;
   int order;
   int slicer_levels;     // 0, 2 or 4

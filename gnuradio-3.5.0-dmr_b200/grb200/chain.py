@@ -126,11 +126,37 @@ class DmrChain:
     def process_tail_device(self, stream=None):
         _l.check(self.L.grcuda_dmr_chain_process_tail_device(self.h, _sp(stream)))
 
+    def process_tail_mm_device(self, state_in=None, state_out=None, stream=None):
+        """Clock recovery + slicer only; state_in / state_out: uint8 CUDA tensors (or None) of mm_state_bytes()."""
+        _l.check(self.L.grcuda_dmr_chain_process_tail_mm_device(
+            self.h, C.c_void_p(state_in.data_ptr() if state_in is not None else None),
+            C.c_void_p(state_out.data_ptr() if state_out is not None else None), _sp(stream)))
+
+    def process_tail_corr_device(self, state_in=None, state_out=None, stream=None):
+        _l.check(self.L.grcuda_dmr_chain_process_tail_corr_device(
+            self.h, C.c_void_p(state_in.data_ptr() if state_in is not None else None),
+            C.c_void_p(state_out.data_ptr() if state_out is not None else None), _sp(stream)))
+
+    def mm_state_bytes(self):
+        return int(self.L.grcuda_dmr_chain_mm_state_bytes(self.h))
+
+    def corr_state_bytes(self):
+        return int(self.L.grcuda_dmr_chain_corr_state_bytes(self.h))
+
     STAGES = ("pfb_fir", "pfb_fft", "quad_demod", "rrc_fir", "mm_slicer", "map_unpack_corr", "carry_copies")
 
     def set_tail_variant(self, variant):
         """Which build of the clock-recovery kernel the tail runs (0 = sized to co-reside with the front kernels)."""
         _l.check(self.L.grcuda_dmr_chain_set_tail_variant(self.h, int(variant)))
+
+    def set_accumulate_hits(self, on):
+        _l.check(self.L.grcuda_dmr_chain_set_accumulate_hits(self.h, int(bool(on))))
+
+    def clear_hits(self, stream=None):
+        _l.check(self.L.grcuda_dmr_chain_clear_hits(self.h, _sp(stream)))
+
+    def max_hits(self):
+        return int(self.L.grcuda_dmr_chain_max_hits(self.h))
 
     def set_split_correlator(self, on):
         _l.check(self.L.grcuda_dmr_chain_set_split_correlator(self.h, int(bool(on))))

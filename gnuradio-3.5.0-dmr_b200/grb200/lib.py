@@ -72,6 +72,8 @@ def load():
     L.grcuda_quadrature_demod_cf_gain.restype = C.c_float
     L.grcuda_pager_slicer_fb_dc_offset.restype = C.c_float
     L.grcuda_dmr_chain_state_bytes.restype = C.c_size_t
+    L.grcuda_dmr_chain_mm_state_bytes.restype = C.c_size_t
+    L.grcuda_dmr_chain_corr_state_bytes.restype = C.c_size_t
     L.grcuda_dmr_chain_tell.restype = C.c_longlong
     L.grcuda_fir_filter_ccf_history.restype = C.c_uint
     L.grcuda_fir_filter_fff_history.restype = C.c_uint

@@ -207,10 +207,12 @@ int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long
 /* slicer fused into the M&M epilogue: mode 0 none, 2 = gr_binary_slicer (gr_math.h:82-88),
  * 4 = pager_slicer_fb::slice with DC-tracking alpha (pager_slicer_fb.cc:47-69). */
 int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha);
-/* Which build of the clock-recovery kernel runs (all produce identical bits; tests/test_gpu_blocks.py checks every
- * one against the oracle).  0 = 48 registers / 47 KB of shared memory, sized to co-reside with the front kernels
- * of a single-GPU chain; the others trade that for a shorter per-symbol dependency chain when the kernel has the
- * SMs to itself (time shards, stand-alone block).  GRCUDA_EINVAL for an unknown number. */
+/* Which build of the clock-recovery kernel runs (all produce identical bits; tests/test_gpu_blocks.py checks them
+ * against the oracle).  -1 (default) = automatic: the quad-ring kernel (kernel_mm_quad.cuh, 198 KB of shared memory,
+ * one CTA per SM) when the channel count is a multiple of 4 and the input 16-byte aligned, else the per-lane loader.
+ * 0 = the round-1 kernel, 10 = its successor at the same 48 registers / 47 KB, sized to co-reside with the front
+ * kernels of a single-GPU chain; 11 = 64 registers; 20-22 = quad ring at 80 / 64 / 96 registers; the rest are the
+ * steps in between (profiles/README.md).  GRCUDA_EINVAL for an unknown number. */
 int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant);
 #define GRCUDA_MM_VARIANTS 23
 
@@ -399,6 +401,20 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
 int grcuda_pfb_channelizer_ccf_set_profiling(grcuda_pfb* h, int on);
 int grcuda_pfb_channelizer_ccf_profile_read(grcuda_pfb* h, float ms[2], int launches[2]);
 /* which build of the clock-recovery kernel the tail stage runs (grcuda_clock_recovery_mm_ff_set_kernel_variant) */
+/* The tail stage as its two kernels, for a time shard (the clock-recovery kernel is the one serial chain over all blocks
+ * of all ranks: nothing else sits on it).  process_tail_mm reads the loop state at d_mm_state_in (NULL: the chain's own)
+ * and ALSO writes its final state to d_mm_state_out (NULL: nowhere else) -- the receive and send buffers of the state
+ * ring, no copies; process_tail_corr runs the time-parallel correlator behind it (any stream), state likewise.
+ * GRCUDA_EUNSUPPORTED when that correlator does not apply (keep_bytes, code shorter than 16): use process_tail_device. */
+int grcuda_dmr_chain_process_tail_mm_device(grcuda_dmr_chain* h, const void* d_mm_state_in, void* d_mm_state_out, void* stream);
+int grcuda_dmr_chain_process_tail_corr_device(grcuda_dmr_chain* h, const void* d_corr_state_in, void* d_corr_state_out, void* stream);
+size_t grcuda_dmr_chain_mm_state_bytes(grcuda_dmr_chain* h);
+size_t grcuda_dmr_chain_corr_state_bytes(grcuda_dmr_chain* h);
+/* 1: the sync-hit list is NOT cleared at the start of a block: hits of successive blocks accumulate (up to max_hits;
+ * bit indices are absolute, so the list still says where each hit is) until grcuda_dmr_chain_clear_hits. */
+int grcuda_dmr_chain_set_accumulate_hits(grcuda_dmr_chain* h, int on);
+int grcuda_dmr_chain_clear_hits(grcuda_dmr_chain* h, void* stream);
+int grcuda_dmr_chain_max_hits(grcuda_dmr_chain* h);
 int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant);
 /* 1 (default): the tail is two kernels, clock recovery + slicer, then the access-code correlator parallel over channels
  * and time; 0: one fused kernel (always used when the correlator's byte stream is kept).  Identical results. */
