@@ -42,13 +42,7 @@ struct grcuda_dmr_chain {
   grcuda_mm* mm = nullptr;
   grcuda_corr* corr = nullptr;
   std::vector<int> symbol_map;
-  DevBuf Yb[2], D, Fb[2], soft, sym, counts, bytes, hits, nhits, d_in_host;
-  int ycur = 0;            // Y buffer holding the last block's channelizer output
-  bool three_stage = false;  // channelizer | discriminator+matched filter | tail on three streams (two Y buffers)
-  bool last_split = false;
-  cudaStream_t mid_stream = nullptr;
-  cudaEvent_t ev_A[2] = {nullptr, nullptr}, ev_B[2] = {nullptr, nullptr};
-  bool B_pending[2] = {false, false};
+  DevBuf Yb, D, Fb[2], soft, sym, counts, bytes, hits, nhits, d_in_host;
   int fcur = 0;           // F buffer of the block whose front ran last
   bool pipeline = true;   // tail on its own stream (overlaps the next block's front)
   bool split_corr = true; // correlator as its own time-parallel kernel behind the clock-recovery kernel
@@ -79,13 +73,10 @@ struct grcuda_dmr_chain {
     if (corr) grcuda_correlate_access_code_bb_destroy(corr);
     if (stream) cudaStreamDestroy(stream);
     if (tail_stream) cudaStreamDestroy(tail_stream);
-    if (mid_stream) cudaStreamDestroy(mid_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int i = 0; i < 2; i++) {
       if (ev_front[i]) cudaEventDestroy(ev_front[i]);
       if (ev_tail[i]) cudaEventDestroy(ev_tail[i]);
-      if (ev_A[i]) cudaEventDestroy(ev_A[i]);
-      if (ev_B[i]) cudaEventDestroy(ev_B[i]);
     }
     if (ev_state) cudaEventDestroy(ev_state);
     if (ev_mm) cudaEventDestroy(ev_mm);
@@ -132,16 +123,22 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   h->symbol_map.assign(p->symbol_map, p->symbol_map + p->symbol_map_len);
   h->T = grcuda_pfb_channelizer_ccf_taps_per_filter(h->pfb);
   // The fused discriminator + matched-filter kernel restates the SSE summation order only
-  h->fused = p->order == GRCUDA_ORDER_SSE && h->nrrc <= demod_front_max_taps() && !getenv("GRCUDA_CHAIN_UNFUSED");
+  h->fused = p->order == GRCUDA_ORDER_SSE && h->nrrc <= demod_front_max_taps();
   h->YH = h->fused ? demod_front_history(h->nrrc) : 1;
   const size_t M = h->M, R = h->max_rows;
-  h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)p->omega * 1.25) + 64;
+  // symbol capacity per block: the loop advances omega rows per symbol on average and omega never leaves
+  // omega_mid +- omega_relative_limit (an ABSOLUTE band: digital_clock_recovery_mm_ff.cc:124), so a block yields at
+  // most rows / (omega - limit) symbols (+ the interpolator's jitter); a configuration the buffer cannot cover is refused
+  if (!(p->omega - p->omega_relative_limit >= 1.0f)) {
+    set_error(GRCUDA_EINVAL, "dmr_chain: omega - omega_relative_limit = %g < 1 sample per symbol", (double)(p->omega - p->omega_relative_limit));
+    delete h;
+    return nullptr;
+  }
+  h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)(p->omega - p->omega_relative_limit) * 1.25) + 64;  // x 1.25: gain_mu * mean(mm) also moves the pace
   h->max_hits = std::max<int>(4096, (int)(M * (size_t)h->max_sym / 32));
   int rc = 0;
   rc = rc ? rc : pfb_reserve_rows(h->pfb, (long)R);  // no allocation (= device-wide sync) once blocks are flowing
-  h->three_stage = getenv("GRCUDA_CHAIN_3STAGE") != nullptr && getenv("GRCUDA_CHAIN_NO_OVERLAP") == nullptr;
-  rc = rc ? rc : h->Yb[0].reserve((h->YH + R) * M * sizeof(float2));
-  if (h->three_stage) rc = rc ? rc : h->Yb[1].reserve((h->YH + R) * M * sizeof(float2));
+  rc = rc ? rc : h->Yb.reserve((h->YH + R) * M * sizeof(float2));
   if (!h->fused) rc = rc ? rc : h->D.reserve((h->nrrc - 1 + R) * M * sizeof(float));
   rc = rc ? rc : h->Fb[0].reserve((KEEP + R) * M * sizeof(float));
   rc = rc ? rc : h->Fb[1].reserve((KEEP + R) * M * sizeof(float));
@@ -153,12 +150,7 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   if (!rc && h->keep_bytes) rc = h->bytes.reserve((size_t)2 * h->max_sym * M);
   if (rc) { delete h; return nullptr; }
   // stream start: all histories are the zeros the reference runtime pre-loads (gr_buffer.cc:201-214)
-  if (cudaMemset(h->Yb[0].p, 0, (size_t)h->YH * M * sizeof(float2)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->mid_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_A[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_A[1], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_B[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_B[1], cudaEventDisableTiming) != cudaSuccess ||
+  if (cudaMemset(h->Yb.p, 0, (size_t)h->YH * M * sizeof(float2)) != cudaSuccess ||
       (!h->fused && cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4) != cudaSuccess) ||
       cudaMemset(h->Fb[0].p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
       cudaMemset(h->Fb[1].p, 0, (size_t)KEEP * M * sizeof(float)) != cudaSuccess ||
@@ -178,6 +170,12 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
   }
   h->pipeline = getenv("GRCUDA_CHAIN_NO_OVERLAP") == nullptr;
   if (h->pipeline && pfb_prefer_coresident_fft(h->pfb) != GRCUDA_OK) { delete h; return nullptr; }
+  // the initialisation above went through the legacy stream; every stream the work runs on is non-blocking
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error(GRCUDA_ECUDA, "dmr_chain: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return nullptr;
+  }
   return h;
 }
 
@@ -194,8 +192,7 @@ int grcuda_dmr_chain_warmup_rows(grcuda_dmr_chain* h) {
 int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
   const size_t M = h->M;
   GRB_CUDA(cudaDeviceSynchronize());
-  GRB_CUDA(cudaMemset(h->Yb[h->ycur].p, 0, (size_t)h->YH * M * sizeof(float2)));
-  h->last_split = false;
+  GRB_CUDA(cudaMemset(h->Yb.p, 0, (size_t)h->YH * M * sizeof(float2)));
   if (!h->fused) GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
   h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
@@ -205,10 +202,7 @@ int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
 int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
   const size_t M = h->M;
-  for (int i = 0; i < 2; i++)  // a pending reader of the Y buffers must finish before their history is cleared
-    if (h->B_pending[i]) { GRB_CUDA(cudaStreamWaitEvent(s, h->ev_B[i], 0)); h->B_pending[i] = false; }
-  GRB_CUDA(cudaMemsetAsync(h->Yb[h->ycur].p, 0, (size_t)h->YH * M * sizeof(float2), s));
-  h->last_split = false;
+  GRB_CUDA(cudaMemsetAsync(h->Yb.p, 0, (size_t)h->YH * M * sizeof(float2), s));
   if (!h->fused) GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
   h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
@@ -254,72 +248,40 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
   return state_copy_end(h, s);
 }
 
-// front stage: channelizer (A, on sA) -> discriminator -> matched filter (B, on sB).  Finite-memory stages: a
-// time shard can run this on its block + halo without waiting for anybody.  sA == sB: one stream, one Y
-// buffer, history carried in place.  sA != sB (three-stage pipeline): A of block b+1 runs concurrently
-// with B of block b (A is HBM bound, B is FP32-issue bound), Y is double buffered and the history rows of a
-// block are copied from the other buffer's tail.
-static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, cudaStream_t sA, cudaStream_t sB) {
+// front stage: channelizer -> discriminator -> matched filter.  Finite-memory stages: a time shard can run this on
+// its block + halo without waiting for anybody.  One stream, one Y buffer, history carried in place.
+static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, cudaStream_t sA) {
   if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
     return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
   if (h->front_rows > 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_front twice without process_tail");
-  const bool split = sA != sB && h->three_stage;
-  if (!split) sB = sA;
+  cudaStream_t sB = sA;
   const size_t M = h->M;
   const long R = nrows;
   const size_t YH = h->YH;
   int rc;
   const int cur = h->fcur ^ 1;  // this block's F buffer; the other one holds the previous block
-  const int yc = split ? (h->ycur ^ 1) : h->ycur;
-  float2* Y = h->Yb[yc].as<float2>();
+  float2* Y = h->Yb.as<float2>();
   float* D = h->D.as<float>();
   float* F = h->Fb[cur].as<float>();
   const float* Fprev = h->Fb[cur ^ 1].as<float>();
-  // ---- A: channelizer ------------------------------------------------------------------------------
-  if (split) {
-    if (h->B_pending[yc]) {  // Y[yc] was last read by the B stage of the block before the previous one
-      GRB_CUDA(cudaStreamWaitEvent(sA, h->ev_B[yc], 0));
-      h->B_pending[yc] = false;
-    }
-    const float2* Yprev = h->Yb[yc ^ 1].as<float2>();
-    h->prof.begin(6, sA);
-    if (h->prev_rows > 0)
-      GRB_CUDA(cudaMemcpyAsync(Y, Yprev + (YH + (size_t)h->prev_rows - YH) * M, YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, sA));
-    else
-      GRB_CUDA(cudaMemsetAsync(Y, 0, YH * M * sizeof(float2), sA));
-    h->prof.end(sA, 0);
-  } else if (h->last_split && h->prev_rows > 0) {
-    // the previous block went through the split path, which does not carry the history in place
-    GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)h->prev_rows * M, YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, sA));
+  // F[cur] was last read by the tail of the block before the previous one.  (Before the channelizer: the small
+  // copy below then gives the tail kernel of the previous block, which becomes runnable at the same moment, the
+  // few microseconds it needs to get all its CTAs onto empty SMs; measured: with the channelizer launched first
+  // the tail kernel runs in two waves, 1.05 -> 2.15 ms.)
+  if (h->tail_pending[cur]) {
+    GRB_CUDA(cudaStreamWaitEvent(sB, h->ev_tail[cur], 0));
+    h->tail_pending[cur] = false;
   }
-  // F[cur] was last read by the tail of the block before the previous one.  (Before the channelizer in the
-  // one-stream case: the small copy below then gives the tail kernel of the previous block, which becomes
-  // runnable at the same moment, the few microseconds it needs to get all its CTAs onto empty SMs;
-  // measured: with the channelizer launched first the tail kernel runs in two waves, 1.05 -> 2.15 ms.)
-  auto f_carry = [&]() -> int {
-    if (h->tail_pending[cur]) {
-      GRB_CUDA(cudaStreamWaitEvent(sB, h->ev_tail[cur], 0));
-      h->tail_pending[cur] = false;
-    }
-    // M&M look-back carry: the last KEEP matched-filter rows of the previous block (written by its
-    // B stage on this same stream order; its tail only reads them)
-    h->prof.begin(6, sB);
-    if (h->prev_rows > 0)
-      GRB_CUDA(cudaMemcpyAsync(F, Fprev + (size_t)h->prev_rows * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, sB));
-    else
-      GRB_CUDA(cudaMemsetAsync(F, 0, (size_t)KEEP * M * sizeof(float), sB));
-    h->prof.end(sB, 0);
-    return GRCUDA_OK;
-  };
-  if (!split && (rc = f_carry())) return rc;
+  // M&M look-back carry: the last KEEP matched-filter rows of the previous block (written by its front on this
+  // same stream order; its tail only reads them)
+  h->prof.begin(6, sB);
+  if (h->prev_rows > 0)
+    GRB_CUDA(cudaMemcpyAsync(F, Fprev + (size_t)h->prev_rows * M, (size_t)KEEP * M * sizeof(float), cudaMemcpyDeviceToDevice, sB));
+  else
+    GRB_CUDA(cudaMemsetAsync(F, 0, (size_t)KEEP * M * sizeof(float), sB));
+  h->prof.end(sB, 0);
   // 1. channelizer: [T + R][M] -> Y rows YH..YH+R
   if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + YH * M), sA))) return rc;
-  if (split) {
-    GRB_CUDA(cudaEventRecord(h->ev_A[yc], sA));
-    GRB_CUDA(cudaStreamWaitEvent(sB, h->ev_A[yc], 0));
-  }
-  // ---- B: discriminator + matched filter -------------------------------------------------------------
-  if (split && (rc = f_carry())) return rc;
   if (h->fused) {
     // 2+3. discriminator + matched filter in one pass: Y (8 B/sample) -> F (4 B/sample); the
     //      discriminator output only ever lives in shared memory
@@ -345,16 +307,10 @@ static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows
   // carries of the front stages for the next block (small device-to-device copies, stream ordered;
   // nrows >= min_rows guarantees that source and destination never overlap)
   h->prof.begin(6, sB);
-  if (!split) GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, sB));
+  GRB_CUDA(cudaMemcpyAsync(Y, Y + (size_t)R * M, YH * M * sizeof(float2), cudaMemcpyDeviceToDevice, sB));
   if (!h->fused && h->nrrc > 1)
     GRB_CUDA(cudaMemcpyAsync(D, D + (size_t)R * M, (size_t)(h->nrrc - 1) * M * sizeof(float), cudaMemcpyDeviceToDevice, sB));
   h->prof.end(sB, 0);
-  if (split) {
-    GRB_CUDA(cudaEventRecord(h->ev_B[yc], sB));
-    h->B_pending[yc] = true;
-  }
-  h->ycur = yc;
-  h->last_split = split;
   GRB_CUDA(cudaEventRecord(h->ev_front[cur], sB));
   h->fcur = cur;
   h->front_rows = nrows;
@@ -363,7 +319,7 @@ static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows
 
 int grcuda_dmr_chain_process_front_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
-  return front_impl(h, d_in, nrows, s, s);
+  return front_impl(h, d_in, nrows, s);
 }
 
 // tail stage: the loops with infinite memory (M&M + DC-tracking slicer + correlator registers); a
@@ -468,7 +424,7 @@ size_t grcuda_dmr_chain_corr_state_bytes(grcuda_dmr_chain* h) { return corr_stat
 
 int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
-  int rc = front_impl(h, d_in, nrows, s, (h->pipeline && h->three_stage) ? h->mid_stream : s);
+  int rc = front_impl(h, d_in, nrows, s);
   if (rc) return rc;
   // the tail goes to the chain's own stream: it overlaps the front of the next block
   h->under_front = h->pipeline;
@@ -481,6 +437,16 @@ int grcuda_dmr_chain_set_tail_variant(grcuda_dmr_chain* h, int variant) {
   int rc = grcuda_clock_recovery_mm_ff_set_kernel_variant(h->mm, variant);
   if (!rc) h->tail_variant = variant;
   return rc;
+}
+// what would otherwise be silent: loop steps clamped at the first buffered row, blocks that hit the symbol capacity,
+// and sync hits beyond the hit list's capacity (all zero for in-contract input); synchronises the device
+int grcuda_dmr_chain_counters(grcuda_dmr_chain* h, long long* clamped, long long* overflow, long long* hits_dropped) {
+  int rc = mm_counters(h->mm, clamped, overflow);
+  if (rc) return rc;
+  int n = 0;
+  GRB_CUDA(cudaMemcpy(&n, h->nhits.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (hits_dropped) *hits_dropped = n > h->max_hits ? n - h->max_hits : 0;
+  return GRCUDA_OK;
 }
 int grcuda_dmr_chain_set_accumulate_hits(grcuda_dmr_chain* h, int on) {
   h->accumulate_hits = on != 0;
@@ -562,7 +528,7 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
 }
 
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r) {
-  r->d_channels = (const grcuda_complex*)(h->Yb[h->ycur].as<float2>() + (size_t)h->YH * h->M);
+  r->d_channels = (const grcuda_complex*)(h->Yb.as<float2>() + (size_t)h->YH * h->M);
   r->d_soft = h->soft.as<float>();
   r->d_symbols = h->sym.as<unsigned char>();
   r->d_sym_counts = h->counts.as<int>();

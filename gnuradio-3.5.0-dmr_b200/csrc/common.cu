@@ -1,6 +1,8 @@
 #include "common.cuh"
 
 #include <map>
+#include <mutex>
+#include <utility>
 
 #include "gr_tables.h"  // build/generated (tools/gen_tables.py)
 
@@ -36,6 +38,20 @@ int get_tables(DeviceTables* out) {
   }
   *out = it->second;
   return GRCUDA_OK;
+}
+
+cudaError_t raise_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> cur;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = cur[std::make_pair(dev, kernel)];
+  if (bytes <= have) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 
 int sm_count() {

@@ -54,6 +54,10 @@ struct DeviceTables {
 };
 int get_tables(DeviceTables* out);  // for the current device
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the KERNEL (per device), not to a plan: plans that share a
+// kernel (every FIR block, every generic FFT) must only ever RAISE it, or a plan created later with a smaller tile
+// makes the launches of an earlier one fail.  Thread safe.
+cudaError_t raise_dynamic_smem(const void* kernel, size_t bytes);
 
 // growable device buffer
 struct DevBuf {

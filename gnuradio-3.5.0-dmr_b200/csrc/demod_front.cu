@@ -56,7 +56,7 @@ int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int 
   }
   const int J = a.q + 1 + (rho > 0 ? 1 : 0);
   const size_t smem = ((size_t)4 * DF_MAXB * 4 + 260 + (size_t)(DF_RT + 4 * (J - 1)) * 32) * sizeof(float);
-  if (smem > 48 * 1024) GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) GRB_CUDA(raise_dynamic_smem((const void*)k, (size_t)smem));
   const long A0 = (abs_row0 >> 2) << 2;
   const long ntiles = (abs_row0 + nrows - A0 + DF_RT - 1) / DF_RT;
   dim3 grid((M + 31) / 32, (unsigned)ntiles);

@@ -160,7 +160,7 @@ FftPlan* fft_plan_create(int n, int dir, bool coresident) {
   }
   if (build_twiddles(p) != GRCUDA_OK) { delete p; return nullptr; }
   if (p->smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    cudaError_t e = raise_dynamic_smem((const void*)p->kernel, (size_t)p->smem);
     if (e != cudaSuccess) {
       set_error(GRCUDA_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", p->smem, cudaGetErrorString(e));
       cudaFree(p->d_tw);
@@ -176,7 +176,7 @@ FftPlan* fft_plan_create(int n, int dir, bool coresident) {
   p->max_ctas = per_sm * sm_count();
   if (p->kernel_staged) {
     int ps = 0;
-    if (cudaFuncSetAttribute((const void*)p->kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_staged) != cudaSuccess ||
+    if (raise_dynamic_smem((const void*)p->kernel_staged, (size_t)p->smem_staged) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, (const void*)p->kernel_staged, p->threads, p->smem_staged) != cudaSuccess || ps < 1) {
       cudaGetLastError();
       p->kernel_staged = nullptr;

@@ -109,22 +109,6 @@ int grcuda_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
 }
 int grcuda_stream_synchronize(void* stream) { GRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return GRCUDA_OK; }
 unsigned long long grcuda_kernel_launch_count(void) { return g_launches.load(); }
-int grcuda_ipc_export(void* dptr, unsigned char handle[64]) {
-  cudaIpcMemHandle_t h;
-  GRB_CUDA(cudaIpcGetMemHandle(&h, dptr));
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  memcpy(handle, &h, 64);
-  return GRCUDA_OK;
-}
-void* grcuda_ipc_open(const unsigned char handle[64]) {
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, 64);
-  void* p = nullptr;
-  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-  if (e != cudaSuccess) { set_error(GRCUDA_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return nullptr; }
-  return p;
-}
-int grcuda_ipc_close(void* dptr) { GRB_CUDA(cudaIpcCloseMemHandle(dptr)); return GRCUDA_OK; }
 
 }  // extern "C"
 
@@ -166,7 +150,7 @@ struct FirCore {
     if (smem > 200 * 1024)
       return set_error(GRCUDA_EUNSUPPORTED, "FIR with %d taps x decimation %d exceeds the shared-memory tile", n, D);
     const void* k = complex_taps ? (const void*)fir_decim_kernel<true> : (const void*)fir_decim_kernel<false>;
-    GRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRB_CUDA(raise_dynamic_smem(k, smem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
     max_ctas = std::max(1, per_sm) * sm_count();
@@ -228,6 +212,14 @@ unsigned grcuda_fir_filter_ccf_history(grcuda_fir_ccf* h) { return h->history; }
 int grcuda_fir_filter_ccf_decimation(grcuda_fir_ccf* h) { return h->core.decim; }
 int grcuda_fir_filter_ccf_work_device(grcuda_fir_ccf* h, long nout, const grcuda_complex* d_in, grcuda_complex* d_out,
                                       void* stream) {
+  {  // a pending set_taps takes effect here too (set_now synchronises the device before it replaces the tap store)
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {
+      h->updated = false;
+      int rc = h->set_now(h->new_taps);
+      if (rc) return rc;
+    }
+  }
   return h->core.launch((const float2*)d_in, (float2*)d_out, nout, false, 0.0, 0, h->pick(stream));
 }
 int grcuda_fir_filter_ccf_work(grcuda_fir_ccf* h, int nout, const grcuda_complex* in, grcuda_complex* out) {
@@ -308,6 +300,14 @@ int grcuda_freq_xlating_fir_filter_ccf_set_center_freq(grcuda_fxlat* h, double f
 unsigned grcuda_freq_xlating_fir_filter_ccf_history(grcuda_fxlat* h) { return h->history; }
 int grcuda_freq_xlating_fir_filter_ccf_work_device(grcuda_fxlat* h, long nout, const grcuda_complex* d_in,
                                                    grcuda_complex* d_out, void* stream) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {  // pending set_taps / set_center_freq
+      h->updated = false;
+      int rc0 = h->build();
+      if (rc0) return rc0;
+    }
+  }
   int rc = h->core.launch((const float2*)d_in, (float2*)d_out, nout, true, h->theta, h->out_count, h->pick(stream));
   if (rc == GRCUDA_OK) h->out_count += nout;
   return rc;
@@ -377,8 +377,8 @@ struct grcuda_fir_fff : PlanBase {
       has_front_tp = true;
     }
     if ((size_t)ntaps * sizeof(float) > 48 * 1024) {
-      GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      GRB_CUDA(cudaFuncSetAttribute((const void*)fir_fff_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      GRB_CUDA(raise_dynamic_smem((const void*)fir_fff_kernel, 96 * 1024));
+      GRB_CUDA(raise_dynamic_smem((const void*)fir_fff_stream_kernel, 96 * 1024));
     }
     return GRCUDA_OK;
   }
@@ -425,6 +425,14 @@ int grcuda_fir_filter_fff_set_taps(grcuda_fir_fff* h, const float* taps, int nta
 unsigned grcuda_fir_filter_fff_history(grcuda_fir_fff* h) { return h->history; }
 int grcuda_fir_filter_fff_work_device(grcuda_fir_fff* h, long nout, int nchan, const float* d_in, float* d_out,
                                       long abs_index0, void* stream) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->updated) {
+      h->updated = false;
+      int rc = h->set_now(h->new_taps);
+      if (rc) return rc;
+    }
+  }
   return h->launch(d_in, d_out, nout, nchan, abs_index0, h->pick(stream));
 }
 int grcuda_fir_filter_fff_work(grcuda_fir_fff* h, int nout, const float* in, float* out, long abs_index0) {
@@ -507,11 +515,11 @@ struct grcuda_pfb : PlanBase {
     if (nout <= 0) return GRCUDA_OK;
     const bool fast = (rr == (int)M) && TT;
     // bulk copies need 16-byte aligned row segments: even M (8-byte samples), 16-byte aligned base
-    const bool tma_ok = fast && TT <= 16 && (M % 2 == 0) && (((uintptr_t)d_rows_in & 15) == 0) && !getenv("GRCUDA_PFB_NO_TMA");
+    const bool tma_ok = fast && TT <= 16 && (M % 2 == 0) && (((uintptr_t)d_rows_in & 15) == 0);
     if (tma_ok) {
-      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
-      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
-      GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_fir_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_fir_tma_smem()));
+      GRB_CUDA(raise_dynamic_smem((const void*)pfb_fir_tma_kernel<4>, (size_t)pfb_fir_tma_smem()));
+      GRB_CUDA(raise_dynamic_smem((const void*)pfb_fir_tma_kernel<8>, (size_t)pfb_fir_tma_smem()));
+      GRB_CUDA(raise_dynamic_smem((const void*)pfb_fir_tma_kernel<16>, (size_t)pfb_fir_tma_smem()));
     }
     // The branch-filter output u is only an intermediate: process in row chunks small enough
     // to stay resident in the 126 MB L2 between the FIR kernel and the FFT kernel.
@@ -1048,6 +1056,9 @@ struct grcuda_mm : PlanBase {
   }
   int reset_state(bool only_mu, bool only_omega, float v) {
     std::vector<MMChanState> st(nchan);
+    // every plan / chain stream is non-blocking: a read-modify-write of the loop state through the legacy stream is
+    // only ordered against a running clock-recovery kernel by a device-wide synchronisation
+    GRB_CUDA(cudaDeviceSynchronize());
     if (only_mu || only_omega) {
       GRB_CUDA(cudaMemcpy(st.data(), d_state.p, st.size() * sizeof(MMChanState), cudaMemcpyDeviceToHost));
       for (auto& s : st) { if (only_mu) s.mu = v; else s.omega = v; }
@@ -1121,7 +1132,7 @@ struct grcuda_mm : PlanBase {
     }
 #undef MMK
     if (!smem) smem = mm_ws_smem_bytes(ringrows, tabrep);
-    GRB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+    GRB_CUDA(raise_dynamic_smem((const void*)k, (size_t)smem));  // per device
     k<<<grid, MMW_THREADS, smem, s>>>(a);
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
@@ -1190,6 +1201,9 @@ __attribute__((visibility("default"))) int grcuda_lab_mm_stats(unsigned long lon
   return GRCUDA_OK;
 }
 #endif
+int grcuda_clock_recovery_mm_ff_counters(grcuda_mm* h, long long* clamped, long long* overflow) {
+  return mm_counters(h, clamped, overflow);
+}
 int grcuda_clock_recovery_mm_ff_set_kernel_variant(grcuda_mm* h, int variant) {
   if (variant < -1 || variant >= GRCUDA_MM_VARIANTS) return set_error(GRCUDA_EINVAL, "clock_recovery_mm_ff: unknown kernel variant %d", variant);
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1441,6 +1455,18 @@ int pfb_reserve_rows(grcuda_pfb* h, long rows) { return h->d_u.reserve((size_t)r
 const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }
 float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }
 void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }
+// sums over channels of the two per-channel counters of the loop: steps clamped at the first buffered row, and calls
+// that stopped at the output capacity before the input ran out (both are where the output leaves the reference's)
+int mm_counters(grcuda_mm* h, long long* clamped, long long* overflow) {
+  std::vector<MMChanState> st(h->nchan);
+  GRB_CUDA(cudaDeviceSynchronize());
+  GRB_CUDA(cudaMemcpy(st.data(), h->d_state.p, st.size() * sizeof(MMChanState), cudaMemcpyDeviceToHost));
+  long long c = 0, o = 0;
+  for (auto& s : st) { c += s.clamped; o += s.overflow; }
+  if (clamped) *clamped = c;
+  if (overflow) *overflow = o;
+  return GRCUDA_OK;
+}
 size_t mm_state_bytes(grcuda_mm* h) { return (size_t)h->nchan * sizeof(MMChanState); }
 void* corr_state_ptr(grcuda_corr* h) { return h->d_state.p; }
 size_t corr_state_bytes(grcuda_corr* h) { return (size_t)h->nchan * sizeof(CorrChanState); }

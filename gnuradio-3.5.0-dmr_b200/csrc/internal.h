@@ -8,6 +8,7 @@
 namespace grb {
 void* mm_state_ptr(grcuda_mm* h);
 size_t mm_state_bytes(grcuda_mm* h);
+int mm_counters(grcuda_mm* h, long long* clamped, long long* overflow);
 void* corr_state_ptr(grcuda_corr* h);
 size_t corr_state_bytes(grcuda_corr* h);
 int mm_corr_launch(grcuda_mm* mm, grcuda_corr* corr, const int* map, int nmap, int bits_per_symbol, const float* d_in,

@@ -381,7 +381,7 @@ int grcuda_pfb_arb_resampler_ccf_work_device(grcuda_pfb_arb* h, int noutput_item
     const int fit = (int)std::floor((ARB_MAXROWS - (int)h->T - 2) / std::max(rows_per_out, 1e-9));
     ta.chunk = std::max(4, std::min(128, fit));
     const size_t smem = (size_t)ARB_MAXROWS * ARB_CH * sizeof(arb_u64) + tap_bytes;
-    GRB_CUDA(cudaFuncSetAttribute((const void*)pfb_arb_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRB_CUDA(raise_dynamic_smem((const void*)pfb_arb_tile_kernel, (size_t)smem));
     dim3 grid((h->nchan + ARB_CH - 1) / ARB_CH, (produced + ta.chunk - 1) / ta.chunk);
     pfb_arb_tile_kernel<<<grid, ARB_THREADS, smem, s>>>(ta);
   } else {

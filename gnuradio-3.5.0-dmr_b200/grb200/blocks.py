@@ -486,6 +486,11 @@ class clock_recovery_mm_ff(_Block):
     def set_gain_omega(self, g):
         _l.check(self.L.grcuda_clock_recovery_mm_ff_set_gain_omega(self.h, C.c_float(g)))
 
+    def counters(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        _l.check(self.L.grcuda_clock_recovery_mm_ff_counters(self.h, C.byref(a), C.byref(b)))
+        return {"clamped": a.value, "overflow": b.value}
+
     def set_kernel_variant(self, variant):
         _l.check(self.L.grcuda_clock_recovery_mm_ff_set_kernel_variant(self.h, int(variant)))
 

@@ -149,6 +149,12 @@ class DmrChain:
         """Which build of the clock-recovery kernel the tail runs (0 = sized to co-reside with the front kernels)."""
         _l.check(self.L.grcuda_dmr_chain_set_tail_variant(self.h, int(variant)))
 
+    def counters(self):
+        """dict(clamped, overflow, hits_dropped): all zero unless the output has left the reference's (gr_cuda.h)."""
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        _l.check(self.L.grcuda_dmr_chain_counters(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"clamped": a.value, "overflow": b.value, "hits_dropped": c.value}
+
     def set_accumulate_hits(self, on):
         _l.check(self.L.grcuda_dmr_chain_set_accumulate_hits(self.h, int(bool(on))))
 

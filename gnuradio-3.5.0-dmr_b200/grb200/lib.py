@@ -50,7 +50,7 @@ _PTR_RETURNING = [
     "grcuda_clock_recovery_mm_ff_create", "grcuda_pager_slicer_fb_create", "grcuda_binary_slicer_fb_create",
     "grcuda_correlate_access_code_bb_create", "grcuda_dmr_chain_create", "grcuda_malloc_device",
     "grcuda_pfb_arb_resampler_ccf_create", "grcuda_pfb_decimator_ccf_create", "grcuda_fft_filter_ccc_create",
-    "grcuda_malloc_pinned", "grcuda_ipc_open",
+    "grcuda_malloc_pinned",
 ]
 
 

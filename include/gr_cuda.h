@@ -15,6 +15,11 @@
  *    Setters are thread safe and take effect at the next work() boundary; the first work()
  *    after set_taps returns 0 exactly like the reference ("history requirements may have
  *    changed", gr_fir_filter_XXX.cc.t:74-79, gr_pfb_channelizer_ccf.cc:164-167).
+ *  - *_work_device returns GRCUDA_OK (0) or a negative GRCUDA_E* code; it always produces exactly
+ *    noutput_items (the caller owns the buffers and their sizes).  A pending setter is applied at
+ *    the start of the call (after a device synchronisation), the call then proceeds: the "return 0
+ *    once" of the scheduler-facing work() has no meaning for a caller that sizes its own buffers,
+ *    but history() may have changed -- re-read it after a set_taps.
  *  - *_create returns NULL on error; grcuda_last_error() / grcuda_last_error_code() tell why.
  *    GRCUDA_EINVAL maps to std::invalid_argument, GRCUDA_ERANGE to std::out_of_range,
  *    GRCUDA_ECUDA to std::runtime_error in the C++ block wrappers (blocks/gr_b200_blocks.h).
@@ -64,11 +69,6 @@ int grcuda_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 int grcuda_stream_synchronize(void* stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long grcuda_kernel_launch_count(void);
-/* CUDA IPC: export / open a device allocation in another process of the same node (multi-GPU
- * shards exchange halos and results through peer memory). handle = 64 bytes. */
-int grcuda_ipc_export(void* dptr, unsigned char handle[64]);
-void* grcuda_ipc_open(const unsigned char handle[64]);
-int grcuda_ipc_close(void* dptr);
 
 /* ---- a1  gr_fir_filter_ccf -----------------------------------------------------------------
  * replaces gr_fir_filter_ccf / gr_fir_ccf{,_simd,_x86} + fcomplex_dotprod_sse64.S
@@ -207,6 +207,11 @@ int grcuda_clock_recovery_mm_ff_work_device(grcuda_mm* h, long ninput_rows, long
 /* slicer fused into the M&M epilogue: mode 0 none, 2 = gr_binary_slicer (gr_math.h:82-88),
  * 4 = pager_slicer_fb::slice with DC-tracking alpha (pager_slicer_fb.cc:47-69). */
 int grcuda_clock_recovery_mm_ff_set_slicer(grcuda_mm* h, int levels, float alpha);
+/* Sums over channels of the loop's two error counters (synchronises the device): `clamped` = steps that wanted to go
+ * back before the first row the caller buffered (the reference would re-read older items of its circular buffer),
+ * `overflow` = work calls that stopped at max_out before the input ran out.  Either one non-zero means the output has
+ * left the reference's: give the block more look-back / capacity. */
+int grcuda_clock_recovery_mm_ff_counters(grcuda_mm* h, long long* clamped, long long* overflow);
 /* Which build of the clock-recovery kernel runs (all produce identical bits; tests/test_gpu_blocks.py checks them
  * against the oracle).  -1 (default) = automatic: the quad-ring kernel (kernel_mm_quad.cuh, 198 KB of shared memory,
  * one CTA per SM) when the channel count is a multiple of 4 and the input 16-byte aligned, else the per-lane loader.
@@ -367,7 +372,12 @@ typedef struct {
   int max_sym;
   int nrows;
 } grcuda_dmr_chain_result;
+/* NOTE: process_host cuts a block into sub-blocks that reuse the symbol buffers; after it, d_soft / d_symbols /
+ * d_sym_counts / d_channels / nrows describe the LAST sub-block only (hits accumulate over the whole block).  A caller
+ * that wants every symbol creates the chain with keep_bytes (one sub-block) or drives process_device itself. */
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r);
+/* error counters of the chain (see grcuda_clock_recovery_mm_ff_counters) + sync hits that did not fit the hit list */
+int grcuda_dmr_chain_counters(grcuda_dmr_chain* h, long long* clamped, long long* overflow, long long* hits_dropped);
 /* copy the compacted sync hits of the last block to the host; returns their number */
 int grcuda_dmr_chain_read_hits(grcuda_dmr_chain* h, grcuda_hit* hits, int max_hits);
 /* smallest block process_* accepts (the carries of one block must not overlap the next) */

@@ -24,3 +24,18 @@ def test_two_time_shards_equal_one_chain():
            "--master-port", "29541", os.path.join(ROOT, "tools", "shard_parity.py"), "--steps", "2"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "shard parity ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ngpus() < 2, reason="needs two CUDA devices")
+def test_bench_sharded_run_checks_itself_against_one_chain():
+    """bench.py --gpus 2: ONE stream time-sharded over two ranks (ShardedChain: zero-copy state rings, correlator on its
+    own chain), every sync hit gathered to rank 0 and compared with a single chain there; the run asserts the equality."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29542", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3", "--warmup", "3",
+           "--rows", "2500", "--sustain-seconds", "0", "--no-cpu", "--e2e-steps", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["parity"]["identical_to_single_chain"] is True and line["parity"]["sync_hits"] > 1000
