@@ -32,7 +32,7 @@ SRCS=(
   "$CORE/filter/gri_mmse_fir_interpolator.cc"
   "$CORE/general/gr_reverse.cc" "$CORE/general/gr_fast_atan2f.cc" "$CORE/general/gr_count_bits.cc"
   "$CORE/general/gr_quadrature_demod_cf.cc" "$CORE/general/gr_fft_vcc.cc" "$CORE/general/gr_fft_vcc_fftw.cc"
-  "$CORE/general/gr_firdes.cc" "$CORE/general/gr_stream_to_streams.cc" "$CORE/general/gr_vector_to_streams.cc" "$CORE/general/gr_map_bb.cc" "$CORE/general/gr_unpack_k_bits_bb.cc"
+  "$CORE/general/gr_firdes.cc" "$CORE/general/gr_remez.cc" "$CORE/general/gr_stream_to_streams.cc" "$CORE/general/gr_vector_to_streams.cc" "$CORE/general/gr_map_bb.cc" "$CORE/general/gr_unpack_k_bits_bb.cc"
   "$REF/gr-digital/lib/digital_clock_recovery_mm_ff.cc" "$REF/gr-digital/lib/digital_clock_recovery_mm_cc.cc"
   "$CORE/filter/gri_mmse_fir_interpolator_cc.cc"
   "$REF/gr-digital/lib/digital_correlate_access_code_bb.cc"

@@ -23,6 +23,7 @@
 #include <gr_math.h>
 #include <gr_count_bits.h>
 #include <gr_firdes.h>
+#include <gr_remez.h>
 #include <gr_rotator.h>
 #include <gr_map_bb.h>
 #include <gr_unpack_k_bits_bb.h>
@@ -300,4 +301,17 @@ int grref_firdes_window(int win, int ntaps, double beta, float* out, int cap) {
   catch (const std::exception& e) { g_err = e.what(); return 0; }
 }
 
+
+// gr_remez (general/gr_remez.cc:792-877): returns the number of taps written, or -1 when the reference throws
+int ref_remez(int order, const double* bands, int nbands2, const double* ampl, const double* weight, int nweight,
+              const char* type, int grid_density, double* out) {
+  try {
+    std::vector<double> t = gr_remez(order, std::vector<double>(bands, bands + nbands2), std::vector<double>(ampl, ampl + nbands2),
+                                     std::vector<double>(weight, weight + nweight), type, grid_density);
+    for (size_t i = 0; i < t.size(); i++) out[i] = t[i];
+    return (int)t.size();
+  } catch (std::exception&) {
+    return -1;
+  }
+}
 }  // extern "C"

@@ -474,3 +474,20 @@ def bench_chain(M, pfb_taps, quad_gain, rrc_taps, omega, gain_omega, mu, gain_mu
         L.grref_set_fft_fast(0)
     assert rc == 0
     return secs[0], secs[1], nh.value, (y.reshape(rows, M) if keep_y else None)
+
+
+def remez(order, bands, ampl, weight=(), filter_type="bandpass", grid_density=16):
+    """The reference's gr_remez (general/gr_remez.cc:792-877), compiled in place.  Returns float64 taps or raises
+    RuntimeError like gr.remez does."""
+    b = np.ascontiguousarray(bands, np.float64)
+    a = np.ascontiguousarray(ampl, np.float64)
+    w = np.ascontiguousarray(weight if len(weight) else [], np.float64)
+    out = np.zeros(order + 8, np.float64)
+    L = lib()
+    L.ref_remez.restype = C.c_int
+    n = L.ref_remez(int(order), b.ctypes.data_as(C.POINTER(C.c_double)), len(b), a.ctypes.data_as(C.POINTER(C.c_double)),
+                    w.ctypes.data_as(C.POINTER(C.c_double)), len(w), filter_type.encode(), int(grid_density),
+                    out.ctypes.data_as(C.POINTER(C.c_double)))
+    if n < 0:
+        raise RuntimeError("gr_remez failed")
+    return out[:n].copy()

@@ -236,7 +236,44 @@ def fixtures_next():
     return fx
 
 
+def fixtures_optfir():
+    """Host-side design fixtures: taps of the reference's gr_remez (compiled in place) for the specs
+    optfir.low_pass / high_pass / band_pass hand it, and the reference's own window.blackmanharris (the Python source of
+    gnuradio/window.py:152-166 executed as it stands)."""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200"))
+    import refharness as R
+    from grb200 import optfir
+    out = {}
+    specs = {"lp8": ("low", 1, 8, 0.4, 0.6, 0.1, 60), "lp32": ("low", 1, 32, 0.4, 0.6, 0.1, 100),
+             "lp48k": ("low", 2.0, 48000.0, 3000.0, 4500.0, 0.2, 70), "hp": ("high", 1, 1.0, 0.2, 0.3, 0.1, 60)}
+    for name, sp in specs.items():
+        kind, gain, fs, f1, f2, rip, att = sp
+        pd, sd = optfir.passband_ripple_to_dev(rip), optfir.stopband_atten_to_dev(att)
+        if kind == "low":
+            n, fo, ao, w = optfir.remezord([f1, f2], (gain, 0), [pd, sd], fs)
+        else:
+            n, fo, ao, w = optfir.remezord([f1, f2], (0, 1), [sd, pd], fs)
+            if (n + 2) % 2 == 1:
+                n += 1
+        out["remez_" + name] = R.remez(n + 2, fo, ao, w)
+        out["spec_" + name] = np.array([{"low": 0, "high": 1}[kind], gain, fs, f1, f2, rip, att], np.float64)
+    src = rd("gnuradio-core/src/python/gnuradio/window.py")
+    m = re.search(r"def coswindow\(coeffs\):.*?return closure\n", src, re.S)
+    ns = {"math": __import__("math")}
+    exec(m.group(0), ns)
+    coeffs = re.search(r"blackmanharris = coswindow\(\((.*?)\)\)", src).group(1)
+    bh = ns["coswindow"](tuple(float(v) for v in coeffs.split(",")))
+    out["blackmanharris_64"] = np.array(bh(64), np.float64)
+    out["blackmanharris_4096"] = np.array(bh(4096), np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_fixtures_optfir.npz"), **out)
+    print("wrote ref_fixtures_optfir.npz:", sorted(out))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "optfir":
+        fixtures_optfir()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "next":
         np.savez_compressed(os.path.join(HERE, "ref_fixtures_next.npz"), **fixtures_next())
         print("wrote ref_fixtures_next.npz", os.path.getsize(os.path.join(HERE, "ref_fixtures_next.npz")) // 1024, "KiB")
