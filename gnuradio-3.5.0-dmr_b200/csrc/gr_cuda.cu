@@ -14,6 +14,7 @@
 #include "kernel_mm.cuh"
 #include "kernel_mm_quad.cuh"
 #include "kernels_fir.cuh"
+#include "kernel_fft_filter.cuh"
 
 using namespace grb;
 
@@ -812,37 +813,139 @@ int grcuda_pfb_decimator_ccf_work(grcuda_pfb_decim* h, int noutput_items, const 
 // =============================================================================================
 // 8f rank 4: gr_fft_filter_ccc (complex taps, history 1, output in blocks of nsamples)
 // =============================================================================================
-// The reference convolves by overlap-add in the frequency domain (gri_fft_filter_ccc_generic.cc:120-165) because
-// that is the cheap way on a CPU; what it computes is y[n] = sum_k taps[k] x[n - k] (x[<0] = 0), decimated, and
-// its own QA checks it against gr_fir_filter_ccc (qa_fft_filter.py).  On the GPU the same block is the direct-form
-// decimating FIR with complex taps (fir_decim_kernel: shared-memory window, register-tiled outputs) plus what the
-// block interface requires: history 1 (the plan carries the last ntaps-1 input samples itself, as the reference
-// carries its overlap-add tail), output_multiple = nsamples = fftsize - ntaps + 1 with
-// fftsize = 2 * 2^ceil(log2 ntaps) (:103-118), set_taps deferred to the next work(), which returns 0 and clears the
-// carried state (:62-69).  Direct form costs ntaps MACs per input sample: filters beyond the kernel's shared-memory
-// tile (a few thousand taps) are refused with GRCUDA_EUNSUPPORTED rather than run slowly.
+// What the block computes is y[n] = sum_k taps[k] x[n - k] (x[<0] = 0), decimated; the reference does it by
+// overlap-add in the frequency domain (gri_fft_filter_ccc_generic.cc:120-165) and its own QA checks it against
+// gr_fir_filter_ccc (qa_fft_filter.py).  Three device paths behind the one block contract -- history 1 (the plan
+// carries the last ntaps-1 input items itself, where the reference carries its overlap-add tail), output_multiple =
+// nsamples = fftsize - ntaps + 1 with fftsize = 2 * 2^ceil(log2 ntaps) (:103-118), set_taps deferred to the next
+// work(), which returns 0 and clears the carried state (:62-69):
+//   * ntaps <= kDirectMax: the direct-form decimating FIR (fir_decim_kernel) -- fewer operations than two FFTs;
+//   * fftsize <= kFusedMax: overlap-save with both FFTs and the product inside one CTA (kernel_fft_filter.cuh);
+//   * longer filters: the same overlap-save on the batched FFT engine (pack, forward, product, inverse, unpack).
 struct grcuda_fft_filter : PlanBase {
-  int decim = 1, ntaps = 0, nsamples = 1;
+  static const int kDirectMax = 32, kFusedMax = 8192;
+  int decim = 1, ntaps = 0, nsamples = 1, fftsize = 2;
+  int path = 0;                 // 0 direct, 1 fused overlap-save, 2 FFT engine
+  int force_path = -1;          // tests: pin the path (-1 = automatic)
   bool updated = false;
   std::vector<float> new_taps;  // interleaved re, im
+  std::vector<float> cur_taps;
   FirCore core;
   DevBuf d_buf, d_carry;        // [carry | new input] contiguous; the last ntaps-1 samples seen
-  static int nsamples_for(int nt) {
-    const int fftsize = (int)(2 * pow(2.0, ceil(log((double)nt) / log(2.0))));  // :106
-    return fftsize - nt + 1;
-  }
+  DevBuf d_H, d_tw, d_rows;
+  FftFiltArgs fa;
+  FftPlan* fwd = nullptr;
+  FftPlan* inv = nullptr;
+  ~grcuda_fft_filter() { if (fwd) fft_plan_destroy(fwd); if (inv) fft_plan_destroy(inv); }
+  static int fftsize_for(int nt) { return (int)(2 * pow(2.0, ceil(log((double)nt) / log(2.0)))); }  // :106
   int build(const std::vector<float>& t_ri) {
     cudaDeviceSynchronize();
+    cur_taps = t_ri;
     ntaps = (int)t_ri.size() / 2;
-    nsamples = nsamples_for(ntaps);
-    std::vector<float> rev(t_ri.size());
-    for (int k = 0; k < ntaps; k++) { rev[2 * k] = t_ri[2 * (ntaps - 1 - k)]; rev[2 * k + 1] = t_ri[2 * (ntaps - 1 - k) + 1]; }
-    core.decim = decim;
-    int rc = core.upload(rev.data(), ntaps, true);
-    if (rc) return rc;
+    fftsize = fftsize_for(ntaps);
+    nsamples = fftsize - ntaps + 1;
+    path = force_path >= 0 ? force_path : (ntaps <= kDirectMax ? 0 : (fftsize <= kFusedMax ? 1 : 2));
+    if (path == 1 && fftsize > kFusedMax) path = 2;
+    int rc;
     const size_t cb = (size_t)std::max(ntaps - 1, 1) * sizeof(float2);
     if ((rc = d_carry.reserve(cb))) return rc;
     GRB_CUDA(cudaMemset(d_carry.p, 0, cb));  // the tail is cleared by set_taps (:67-69)
+    if (path == 0) {
+      std::vector<float> rev(t_ri.size());
+      for (int k = 0; k < ntaps; k++) { rev[2 * k] = t_ri[2 * (ntaps - 1 - k)]; rev[2 * k + 1] = t_ri[2 * (ntaps - 1 - k) + 1]; }
+      core.decim = decim;
+      return core.upload(rev.data(), ntaps, true);
+    }
+    // H = FFT(taps) / fftsize (:80-94), evaluated in double on the host: a plain radix-2 transform of the padded taps
+    const int n = fftsize;
+    std::vector<std::complex<double>> H(n, 0.0);
+    for (int k = 0; k < ntaps; k++) H[k] = std::complex<double>(t_ri[2 * k], t_ri[2 * k + 1]) / (double)n;
+    for (int i = 1, j = 0; i < n; i++) {  // bit reversal
+      int bit = n >> 1;
+      for (; j & bit; bit >>= 1) j ^= bit;
+      j ^= bit;
+      if (i < j) std::swap(H[i], H[j]);
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+      for (int i = 0; i < n; i += len)
+        for (int k = 0; k < len / 2; k++) {
+          const double ang = -2.0 * M_PI * k / len;
+          const std::complex<double> w(cos(ang), sin(ang)), u = H[i + k], v = H[i + k + len / 2] * w;
+          H[i + k] = u + v;
+          H[i + k + len / 2] = u - v;
+        }
+    }
+    std::vector<float2> Hf(n);
+    for (int i = 0; i < n; i++) Hf[i] = make_float2((float)H[i].real(), (float)H[i].imag());
+    if ((rc = d_H.reserve((size_t)n * sizeof(float2)))) return rc;
+    GRB_CUDA(cudaMemcpy(d_H.p, Hf.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+    if (path == 1) {
+      memset(&fa, 0, sizeof fa);
+      int m = 0;
+      while ((1 << m) < n) m++;
+      std::vector<float2> tw;
+      int Ns = 1;
+      fa.npass = 0;
+      while (m > 0) {
+        const int lr = m >= 4 ? 4 : m, R = 1 << lr;
+        fa.radix[fa.npass] = R;
+        fa.tw_off[fa.npass] = (int)tw.size();
+        for (int k = 0; k < Ns; k++) {
+          const double ang = -2.0 * M_PI * k / ((double)Ns * R);
+          tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+        }
+        Ns *= R;
+        m -= lr;
+        fa.npass++;
+      }
+      if ((rc = d_tw.reserve(tw.size() * sizeof(float2)))) return rc;
+      GRB_CUDA(cudaMemcpy(d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+      fa.H = d_H.as<float2>();
+      fa.tw = d_tw.as<float2>();
+      fa.n = n; fa.ntaps = ntaps; fa.nsamples = nsamples; fa.decim = decim;
+      const size_t smem = (size_t)(n + n / 16 + 1) * sizeof(float2);
+      if (cudaError_t e = raise_dynamic_smem((const void*)fft_filter_ols_kernel<512>, smem))
+        return set_error(GRCUDA_ECUDA, "fft_filter_ccc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    } else {
+      if (fwd) fft_plan_destroy(fwd);
+      if (inv) fft_plan_destroy(inv);
+      fwd = fft_plan_create(n, -1);
+      inv = fft_plan_create(n, +1);
+      if (!fwd || !inv) return g_last_error_code;
+    }
+    return GRCUDA_OK;
+  }
+  // buf = [ntaps-1 carried | nblk * nsamples new] -> out (nblk * nsamples / decim items)
+  int run_freq(const float2* buf, float2* out, long nblk, cudaStream_t s) {
+    if (path == 1) {
+      FftFiltArgs a = fa;
+      a.x = buf; a.out = out; a.nblk = nblk;
+      const int threads = std::max(32, fftsize / FFTF_ELEMS);
+      const size_t smem = (size_t)(fftsize + fftsize / 16 + 1) * sizeof(float2);
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (200u << 10) / std::max<size_t>(smem, 1)));
+      const int grid = (int)std::min<long>(nblk, (long)sm_count() * per_sm);
+      fft_filter_ols_kernel<512><<<grid, threads, smem, s>>>(a);
+      GRB_LAUNCH_CHECK();
+      return GRCUDA_OK;
+    }
+    // FFT engine, a bounded number of blocks at a time (two row buffers of <= 256 MB)
+    const long per = std::max<long>(1, (long)((256u << 20) / ((size_t)fftsize * sizeof(float2))));
+    int rc;
+    if ((rc = d_rows.reserve((size_t)std::min(per, nblk) * fftsize * sizeof(float2) * 2))) return rc;
+    float2* r0 = d_rows.as<float2>();
+    float2* r1 = r0 + (size_t)std::min(per, nblk) * fftsize;
+    for (long b0 = 0; b0 < nblk; b0 += per) {
+      const long nb = std::min(per, nblk - b0);
+      const int g = grid_for(nb * fftsize, 256);
+      fftf_pack_kernel<<<g, 256, 0, s>>>(buf + b0 * nsamples, r0, fftsize, nsamples, nb);
+      GRB_LAUNCH_CHECK();
+      if ((rc = fft_plan_exec(fwd, r0, r1, nb, nullptr, 0, 0, s))) return rc;
+      fftf_mul_kernel<<<g, 256, 0, s>>>(r1, d_H.as<float2>(), fftsize, nb);
+      GRB_LAUNCH_CHECK();
+      if ((rc = fft_plan_exec(inv, r1, r0, nb, nullptr, 0, 0, s))) return rc;
+      fftf_unpack_kernel<<<grid_for(nb * nsamples, 256), 256, 0, s>>>(r0, out, fftsize, ntaps, nsamples, decim, nb, b0 * nsamples);
+      GRB_LAUNCH_CHECK();
+    }
     return GRCUDA_OK;
   }
 };
@@ -866,6 +969,14 @@ int grcuda_fft_filter_ccc_set_taps(grcuda_fft_filter* h, const grcuda_complex* t
   return GRCUDA_OK;
 }
 int grcuda_fft_filter_ccc_output_multiple(grcuda_fft_filter* h) { return h->nsamples; }  // :66
+int grcuda_fft_filter_ccc_path(grcuda_fft_filter* h) { return h->path; }
+int grcuda_fft_filter_ccc_set_path(grcuda_fft_filter* h, int path) {
+  if (path < -1 || path > 2) return set_error(GRCUDA_EINVAL, "fft_filter_ccc: unknown path %d", path);
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->force_path = path;
+  if (!h->updated) { h->new_taps = h->cur_taps; h->updated = true; }   // rebuilt at the next work(), like set_taps
+  return GRCUDA_OK;
+}
 int grcuda_fft_filter_ccc_decimation(grcuda_fft_filter* h) { return h->decim; }
 unsigned grcuda_fft_filter_ccc_history(grcuda_fft_filter* h) { (void)h; return 1; }        // :58
 // d_in: noutput_items * decimation NEW items (history 1); noutput_items must be a multiple of output_multiple()
@@ -888,7 +999,9 @@ int grcuda_fft_filter_ccc_work_device(grcuda_fft_filter* h, int noutput_items, c
   float2* buf = h->d_buf.as<float2>();
   if (nc) GRB_CUDA(cudaMemcpyAsync(buf, h->d_carry.p, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync(buf + nc, d_in, nin * sizeof(float2), cudaMemcpyDeviceToDevice, s));
-  if ((rc = h->core.launch(buf, (float2*)d_out, noutput_items, false, 0.0, 0, s))) return rc;
+  if (h->path == 0) rc = h->core.launch(buf, (float2*)d_out, noutput_items, false, 0.0, 0, s);
+  else rc = h->run_freq(buf, (float2*)d_out, (long)(nin / h->nsamples), s);
+  if (rc) return rc;
   if (nc) GRB_CUDA(cudaMemcpyAsync(h->d_carry.p, buf + nin, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   return noutput_items;
 }

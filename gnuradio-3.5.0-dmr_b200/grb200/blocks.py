@@ -355,6 +355,14 @@ class fft_filter_ccc(_Block):
     def decimation(self):
         return self.decim
 
+    def path(self):
+        """0 direct form, 1 fused overlap-save (one CTA per block), 2 overlap-save on the batched FFT engine."""
+        return int(self.L.grcuda_fft_filter_ccc_path(self.h))
+
+    def set_path(self, path):
+        """Pins a device path (-1: automatic); deferred like set_taps (the next work() returns 0)."""
+        _l.check(self.L.grcuda_fft_filter_ccc_set_path(self.h, int(path)))
+
     def work(self, noutput_items, in_items):
         x = _c64(in_items)
         out = np.empty(max(noutput_items, 0), np.complex64)
@@ -607,3 +615,185 @@ def run(block, x, chunk=None, vlen=1):
         outs.append(y.copy())
         done += len(y)
     return np.concatenate(outs) if outs else np.empty(0, block.out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class map_bb(_Block):
+    """gr_make_map_bb(const std::vector<int>& map) (gr_map_bb.cc:35-61)."""
+    _destroy = "grcuda_map_bb_destroy"
+    in_dtype, out_dtype = np.uint8, np.uint8
+
+    def __init__(self, map):
+        m = np.ascontiguousarray(map, dtype=np.int32)
+        self.L = _l.load()
+        self.h = _l.check_handle(self.L.grcuda_map_bb_create(_p(m), len(m)))
+
+    def work(self, noutput_items, in_items):
+        x = _u8(in_items)
+        out = np.empty(max(noutput_items, 0), np.uint8)
+        n = _l.check(self.L.grcuda_map_bb_work(self.h, int(noutput_items), _p(x), _p(out)))
+        return out[:n]
+
+    def work_device(self, noutput_items, d_in, d_out):
+        return _l.check(self.L.grcuda_map_bb_work_device(self.h, C.c_long(int(noutput_items)), _dp(d_in), _dp(d_out), _torch_stream()))
+
+
+class unpack_k_bits_bb(_Block):
+    """gr_make_unpack_k_bits_bb(unsigned k) (gr_unpack_k_bits_bb.cc:38-70); IndexError (std::out_of_range) for k == 0."""
+    _destroy = "grcuda_unpack_k_bits_bb_destroy"
+    in_dtype, out_dtype = np.uint8, np.uint8
+
+    def __init__(self, k):
+        self.L = _l.load()
+        self.k = int(k)
+        self.h = _l.check_handle(self.L.grcuda_unpack_k_bits_bb_create(C.c_uint(self.k)))
+
+    def interpolation(self):
+        return int(self.L.grcuda_unpack_k_bits_bb_interpolation(self.h))
+
+    def work(self, noutput_items, in_items):
+        x = _u8(in_items)
+        out = np.empty(max(noutput_items, 0), np.uint8)
+        n = _l.check(self.L.grcuda_unpack_k_bits_bb_work(self.h, int(noutput_items), _p(x), _p(out)))
+        return out[:n]
+
+    def work_device(self, noutput_items, d_in, d_out):
+        return _l.check(self.L.grcuda_unpack_k_bits_bb_work_device(self.h, C.c_long(int(noutput_items)), _dp(d_in), _dp(d_out),
+                                                                   _torch_stream()))
+
+
+class _streams(_Block):
+    _destroy = "grcuda_streams_destroy"
+    _create = None
+
+    def __init__(self, item_size, nstreams):
+        self.L = _l.load()
+        self.item_size, self.nstreams = int(item_size), int(nstreams)
+        self.h = _l.check_handle(getattr(self.L, self._create)(self.item_size, self.nstreams))
+
+    def work(self, noutput_items, in_items):
+        """in_items: noutput_items * nstreams items (any dtype of item_size bytes, or uint8 bytes).  Returns the list of
+        nstreams output arrays (as bytes viewed back to the input dtype)."""
+        x = np.ascontiguousarray(in_items)
+        raw = x.view(np.uint8).reshape(-1)
+        n = int(noutput_items)
+        outs = [np.empty(n * self.item_size, np.uint8) for _ in range(self.nstreams)]
+        ptrs = (C.c_void_p * self.nstreams)(*[o.ctypes.data for o in outs])
+        _l.check(self.L.grcuda_streams_work(self.h, n, _p(raw), ptrs))
+        if x.dtype.itemsize == self.item_size:
+            return [o.view(x.dtype) for o in outs]
+        return outs
+
+    def work_device(self, noutput_items, d_in, d_out, out_stride_items=None):
+        st = int(noutput_items) if out_stride_items is None else int(out_stride_items)
+        return _l.check(self.L.grcuda_streams_work_device(self.h, C.c_long(int(noutput_items)), _dp(d_in), _dp(d_out), C.c_long(st),
+                                                          _torch_stream()))
+
+
+class stream_to_streams(_streams):
+    """gr_make_stream_to_streams(size_t item_size, size_t nstreams) (gr_stream_to_streams.cc:37-66)."""
+    _create = "grcuda_stream_to_streams_create"
+
+
+class vector_to_streams(_streams):
+    """gr_make_vector_to_streams(size_t item_size, size_t nstreams) (gr_vector_to_streams.cc:37-70)."""
+    _create = "grcuda_vector_to_streams_create"
+
+
+class framer_sink_1(_Block):
+    """gr_make_framer_sink_1(gr_msg_queue_sptr target_queue) (gr_framer_sink_1.cc:75-196), batched over nchan streams.
+    The target queue is the block's own device-side queue: messages() drains it as
+    [(channel, whitener_offset, payload bytes)] in arrival order."""
+    _destroy = "grcuda_framer_sink_1_destroy"
+
+    def __init__(self, nchan=1, max_msgs=1 << 16, payload_capacity=1 << 24):
+        self.L = _l.load()
+        self.nchan, self.max_msgs, self.cap = int(nchan), int(max_msgs), int(payload_capacity)
+        self.h = _l.check_handle(self.L.grcuda_framer_sink_1_create(self.nchan, self.max_msgs, self.cap))
+
+    def work(self, in_items):
+        x = _u8(in_items)
+        return _l.check(self.L.grcuda_framer_sink_1_work(self.h, len(x), _p(x)))
+
+    def work_device(self, nitems, d_in, item_stride, chan_stride, d_counts=None, count_scale=1):
+        return _l.check(self.L.grcuda_framer_sink_1_work_device(
+            self.h, C.c_long(int(nitems)), _dp(d_in), C.c_long(int(item_stride)), C.c_long(int(chan_stride)),
+            _dp(d_counts) if d_counts is not None else None, int(count_scale), _torch_stream()))
+
+    def messages(self, with_meta=False):
+        msgs = (_l.FramerMsg * self.max_msgs)()
+        payload = np.empty(self.cap, np.uint8)
+        dropped = C.c_int(0)
+        n = _l.check(self.L.grcuda_framer_sink_1_read(self.h, msgs, self.max_msgs, _p(payload), C.c_size_t(self.cap), C.byref(dropped)))
+        self.dropped = dropped.value
+        out = []
+        for m in msgs[:n]:
+            data = bytes(payload[m.payload_offset: m.payload_offset + m.length]) if m.payload_offset >= 0 else None
+            out.append((m.channel, m.whitener_offset, data, m.end_index, m.seq) if with_meta else (m.channel, m.whitener_offset, data))
+        return out
+
+
+class clock_recovery_mm_cc(_Block):
+    """digital_make_clock_recovery_mm_cc(omega, gain_omega, mu, gain_mu, omega_relative_limit)
+    (digital_clock_recovery_mm_cc.cc:37-75), + nchan for the batched device form.  IndexError (std::out_of_range) for
+    omega <= 0 or negative gains."""
+    _destroy = "grcuda_clock_recovery_mm_cc_destroy"
+
+    def __init__(self, omega, gain_omega, mu, gain_mu, omega_relative_limit=0.001, nchan=1):
+        self.L = _l.load()
+        self.nchan = int(nchan)
+        self.h = _l.check_handle(self.L.grcuda_clock_recovery_mm_cc_create(
+            self.nchan, C.c_float(omega), C.c_float(gain_omega), C.c_float(mu), C.c_float(gain_mu), C.c_float(omega_relative_limit)))
+
+    def history(self):
+        return 3
+
+    def forecast(self, noutput_items):
+        return _l.check(self.L.grcuda_clock_recovery_mm_cc_forecast(self.h, int(noutput_items)))
+
+    def state(self, chan=0):
+        mu, om = C.c_float(0), C.c_float(0)
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_get_state(self.h, int(chan), C.byref(mu), C.byref(om)))
+        return mu.value, om.value
+
+    def mu(self):
+        return self.state()[0]
+
+    def omega(self):
+        return self.state()[1]
+
+    def set_mu(self, mu):
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_set_mu(self.h, C.c_float(mu)))
+
+    def set_omega(self, omega):
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_set_omega(self.h, C.c_float(omega)))
+
+    def set_gain_mu(self, g):
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_set_gain_mu(self.h, C.c_float(g)))
+
+    def set_gain_omega(self, g):
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_set_gain_omega(self.h, C.c_float(g)))
+
+    def counters(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        _l.check(self.L.grcuda_clock_recovery_mm_cc_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def general_work(self, noutput_items, in_items, with_error=False):
+        """Returns (symbols, error signal or None, consumed)."""
+        x = _c64(in_items)
+        out = np.empty(max(noutput_items, 1), np.complex64)
+        err = np.empty(max(noutput_items, 1), np.float32) if with_error else None
+        consumed = C.c_int(0)
+        n = _l.check(self.L.grcuda_clock_recovery_mm_cc_work(self.h, int(noutput_items), len(x), _p(x), _p(out),
+                                                             _p(err) if with_error else None, C.byref(consumed)))
+        return out[:n], (err[:n] if with_error else None), consumed.value
+
+    def work_device(self, ninput_rows, abs_row0, d_in, d_out, d_err, max_out, d_counts):
+        return _l.check(self.L.grcuda_clock_recovery_mm_cc_work_device(
+            self.h, C.c_long(int(ninput_rows)), C.c_long(int(abs_row0)), _dp(d_in), _dp(d_out),
+            _dp(d_err) if d_err is not None else None, int(max_out), _dp(d_counts) if d_counts is not None else None, _torch_stream()))

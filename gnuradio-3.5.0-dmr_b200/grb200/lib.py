@@ -24,6 +24,11 @@ class Hit(C.Structure):
     _fields_ = [("channel", C.c_int), ("pad", C.c_int), ("bit_index", C.c_longlong)]
 
 
+class FramerMsg(C.Structure):
+    _fields_ = [("channel", C.c_int), ("whitener_offset", C.c_int), ("length", C.c_int), ("seq", C.c_int),
+                ("payload_offset", C.c_longlong), ("end_index", C.c_longlong)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [
         ("numchans", C.c_uint), ("pfb_taps", C.POINTER(C.c_float)), ("pfb_ntaps", C.c_int),
@@ -50,7 +55,8 @@ _PTR_RETURNING = [
     "grcuda_clock_recovery_mm_ff_create", "grcuda_pager_slicer_fb_create", "grcuda_binary_slicer_fb_create",
     "grcuda_correlate_access_code_bb_create", "grcuda_dmr_chain_create", "grcuda_malloc_device",
     "grcuda_pfb_arb_resampler_ccf_create", "grcuda_pfb_decimator_ccf_create", "grcuda_fft_filter_ccc_create",
-    "grcuda_malloc_pinned",
+    "grcuda_malloc_pinned", "grcuda_map_bb_create", "grcuda_unpack_k_bits_bb_create", "grcuda_stream_to_streams_create",
+    "grcuda_vector_to_streams_create", "grcuda_framer_sink_1_create", "grcuda_clock_recovery_mm_cc_create",
 ]
 
 
@@ -82,6 +88,10 @@ def load():
     L.grcuda_pfb_arb_resampler_ccf_history.restype = C.c_uint
     L.grcuda_pfb_decimator_ccf_history.restype = C.c_uint
     L.grcuda_pfb_arb_resampler_ccf_relative_rate.restype = C.c_double
+    L.grcuda_unpack_k_bits_bb_interpolation.restype = C.c_uint
+    L.grcuda_stream_to_streams_create.argtypes = [C.c_size_t, C.c_size_t]
+    L.grcuda_vector_to_streams_create.argtypes = [C.c_size_t, C.c_size_t]
+    L.grcuda_framer_sink_1_create.argtypes = [C.c_int, C.c_int, C.c_size_t]
     _lib = L
     return L
 

@@ -303,18 +303,116 @@ int grcuda_pfb_decimator_ccf_work_device(grcuda_pfb_decim* h, long noutput_items
  * gri_fft_filter_ccc_generic.cc:62-165): y[n] = sum_k taps[k] x[n-k], decimated, complex taps.  Same
  * block contract: history 1 (the plan carries the last ntaps-1 samples, as the reference carries its
  * overlap-add tail), output_multiple = nsamples = fftsize - ntaps + 1, set_taps deferred to the next work()
- * which returns 0 and clears the carried state.  Computed in direct form on the GPU (see gr_cuda.cu);
- * within 1e-6 of the reference (bar 1e-4).  GRCUDA_EUNSUPPORTED for filters beyond the FIR tile. */
+ * which returns 0 and clears the carried state.  Device paths (path()): 0 = direct form (ntaps <= 32),
+ * 1 = overlap-save with both FFTs and the product inside one CTA (fftsize <= 8192, i.e. up to 4096 taps),
+ * 2 = overlap-save on the batched FFT engine (any length).  Within 1e-6 of the reference (bar 1e-4).
+ * set_path pins one (-1 = automatic); like set_taps it takes effect at the next work(), which returns 0. */
 typedef struct grcuda_fft_filter grcuda_fft_filter;
 grcuda_fft_filter* grcuda_fft_filter_ccc_create(int decimation, const grcuda_complex* taps, int ntaps);
 void grcuda_fft_filter_ccc_destroy(grcuda_fft_filter* h);
 int grcuda_fft_filter_ccc_set_taps(grcuda_fft_filter* h, const grcuda_complex* taps, int ntaps);
 int grcuda_fft_filter_ccc_output_multiple(grcuda_fft_filter* h);
+int grcuda_fft_filter_ccc_path(grcuda_fft_filter* h);
+int grcuda_fft_filter_ccc_set_path(grcuda_fft_filter* h, int path);
 int grcuda_fft_filter_ccc_decimation(grcuda_fft_filter* h);
 unsigned grcuda_fft_filter_ccc_history(grcuda_fft_filter* h);
 int grcuda_fft_filter_ccc_work(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* in, grcuda_complex* out);
 int grcuda_fft_filter_ccc_work_device(grcuda_fft_filter* h, int noutput_items, const grcuda_complex* d_in,
                                       grcuda_complex* d_out, void* stream);
+
+/* ---- a12 as blocks of their own: gr_map_bb, gr_unpack_k_bits_bb ---------------------------------
+ * replaces gr_map_bb::work (gr_map_bb.cc:35-61: identity table overwritten by the first min(256, nmap) entries) and
+ * gr_unpack_k_bits_bb::work (gr_unpack_k_bits_bb.cc:38-70: k output bytes per input byte, bit k-1 first;
+ * k == 0 -> GRCUDA_ERANGE like the reference's std::out_of_range).  The chain runs both fused into the tail
+ * kernel; these are for flowgraphs that keep the blocks between GPU blocks. */
+typedef struct grcuda_map_bb grcuda_map_bb;
+grcuda_map_bb* grcuda_map_bb_create(const int* map, int nmap);
+void grcuda_map_bb_destroy(grcuda_map_bb* h);
+int grcuda_map_bb_work(grcuda_map_bb* h, int noutput_items, const unsigned char* in, unsigned char* out);
+int grcuda_map_bb_work_device(grcuda_map_bb* h, long noutput_items, const unsigned char* d_in, unsigned char* d_out, void* stream);
+typedef struct grcuda_unpack_k_bits grcuda_unpack_k_bits;
+grcuda_unpack_k_bits* grcuda_unpack_k_bits_bb_create(unsigned k);
+void grcuda_unpack_k_bits_bb_destroy(grcuda_unpack_k_bits* h);
+unsigned grcuda_unpack_k_bits_bb_interpolation(grcuda_unpack_k_bits* h);
+/* noutput_items counts OUTPUT bytes (a sync interpolator: noutput_items / k input bytes are read) */
+int grcuda_unpack_k_bits_bb_work(grcuda_unpack_k_bits* h, int noutput_items, const unsigned char* in, unsigned char* out);
+int grcuda_unpack_k_bits_bb_work_device(grcuda_unpack_k_bits* h, long noutput_items, const unsigned char* d_in,
+                                        unsigned char* d_out, void* stream);
+
+/* ---- a14 as blocks of their own: gr_stream_to_streams, gr_vector_to_streams ----------------------
+ * replaces gr_stream_to_streams::work / gr_vector_to_streams::work (gr_stream_to_streams.cc:52-66,
+ * gr_vector_to_streams.cc:53-70 -- the same loop: item i of output stream j = input item i * nstreams + j).
+ * The channelizer takes the interleaved stream as it is (_work_interleaved); these are for flowgraphs that split it
+ * for other consumers.  _work: `out` = nstreams host pointers, noutput_items items each.  _work_device: one device
+ * buffer, stream j at d_out + j * out_stride_items items. */
+typedef struct grcuda_streams grcuda_streams;
+grcuda_streams* grcuda_stream_to_streams_create(size_t item_size, size_t nstreams);
+grcuda_streams* grcuda_vector_to_streams_create(size_t item_size, size_t nstreams);
+void grcuda_streams_destroy(grcuda_streams* h);
+int grcuda_streams_nstreams(grcuda_streams* h);
+int grcuda_streams_work(grcuda_streams* h, int noutput_items, const void* in, void* const* out);
+int grcuda_streams_work_device(grcuda_streams* h, long noutput_items, const void* d_in, void* d_out, long out_stride_items,
+                               void* stream);
+
+/* ---- 8f rank 4  gr_framer_sink_1 -----------------------------------------------------------------
+ * replaces gr_framer_sink_1::work and its state machine (gr_framer_sink_1.cc:36-72, 90-196; header checks
+ * gr_framer_sink_1.h:88-103): consumes the correlator's byte stream (bit 0 data, bit 1 sync flag), reads the 32-bit
+ * header after a flag (two identical 16-bit halves: whitener offset << 12 | payload length), assembles the payload
+ * MSB first and posts one message per packet.  Batched over nchan independent streams, one state machine per
+ * channel, state carried from call to call like the block's members.  The reference's gr_msg_queue is a device-side
+ * queue (records + payload arena) drained by _read: messages come back ordered by the stream position that
+ * completed them, then by channel -- the arrival order of one shared queue.  gr_message(type 0, arg1 =
+ * whitener_offset, arg2 = 0, length) is the record's {whitener_offset, length}. */
+typedef struct grcuda_framer grcuda_framer;
+typedef struct {
+  int channel;
+  int whitener_offset;      /* gr_message arg1 */
+  int length;               /* payload bytes */
+  int seq;                  /* n-th message of its channel */
+  long long payload_offset; /* into the payload buffer _read fills; -1: the device arena was full, bytes lost */
+  long long end_index;      /* position in the channel's stream of the byte that completed the packet */
+} grcuda_framer_msg;
+grcuda_framer* grcuda_framer_sink_1_create(int nchan, int max_msgs, size_t payload_capacity);
+void grcuda_framer_sink_1_destroy(grcuda_framer* h);
+/* single stream (nchan == 1), host pointer; returns noutput_items (a sync block consumes all it is given) */
+int grcuda_framer_sink_1_work(grcuda_framer* h, int noutput_items, const unsigned char* in);
+/* batched device form: item t of channel c = d_in[t * item_stride + c * chan_stride].  The chain's correlator bytes
+ * are [bit][channel] (item_stride = nchan, chan_stride = 1); item_stride == 1 selects the warp-per-channel kernel
+ * for stream-major data.  Channel c has d_counts[c] * count_scale valid items (d_counts == NULL: nitems each). */
+int grcuda_framer_sink_1_work_device(grcuda_framer* h, long nitems, const unsigned char* d_in, long item_stride, long chan_stride,
+                                     const int* d_counts, int count_scale, void* stream);
+/* messages waiting (synchronises); *dropped = messages or payloads that did not fit since the last read */
+int grcuda_framer_sink_1_count(grcuda_framer* h, int* dropped);
+/* drains the queue: returns the number of messages copied to msgs (payloads packed into `payload` in that order) */
+int grcuda_framer_sink_1_read(grcuda_framer* h, grcuda_framer_msg* msgs, int max_msgs, unsigned char* payload,
+                              size_t payload_cap, int* dropped);
+
+/* ---- 8f rank 4  digital_clock_recovery_mm_cc -------------------------------------------------------
+ * replaces digital_clock_recovery_mm_cc::general_work (digital_clock_recovery_mm_cc.cc:117-213; set_omega .h:75-80)
+ * and gri_mmse_fir_interpolator_cc::interpolate (gri_mmse_fir_interpolator_cc.cc:61-71), batched over nchan
+ * channels laid out [time][channel].  create() fails with GRCUDA_ERANGE for omega <= 0 or negative gains (:65-68).
+ * history 3, forecast = ceil(noutput * omega + 8) + 16.  Bit identical to the reference built with the generic-order
+ * gr_fir_ccf.  err_out / d_err != NULL is the block with its second output connected: the error is clipped to +-4
+ * instead of +-1 (:146 vs :178), which changes the loop. */
+typedef struct grcuda_mm_cc grcuda_mm_cc;
+grcuda_mm_cc* grcuda_clock_recovery_mm_cc_create(int nchan, float omega, float gain_omega, float mu, float gain_mu,
+                                                 float omega_relative_limit);
+void grcuda_clock_recovery_mm_cc_destroy(grcuda_mm_cc* h);
+int grcuda_clock_recovery_mm_cc_forecast(grcuda_mm_cc* h, int noutput_items);
+int grcuda_clock_recovery_mm_cc_get_state(grcuda_mm_cc* h, int chan, float* mu, float* omega);
+int grcuda_clock_recovery_mm_cc_set_mu(grcuda_mm_cc* h, float mu);
+int grcuda_clock_recovery_mm_cc_set_omega(grcuda_mm_cc* h, float omega);
+int grcuda_clock_recovery_mm_cc_set_gain_mu(grcuda_mm_cc* h, float gain_mu);
+int grcuda_clock_recovery_mm_cc_set_gain_omega(grcuda_mm_cc* h, float gain_omega);
+int grcuda_clock_recovery_mm_cc_counters(grcuda_mm_cc* h, long long* clamped, long long* overflow);
+/* single-stream general_work (nchan == 1): returns produced, *consumed = what the reference passes to consume_each */
+int grcuda_clock_recovery_mm_cc_work(grcuda_mm_cc* h, int noutput_items, int ninput_items, const grcuda_complex* in,
+                                     grcuda_complex* out, float* err_out, int* consumed);
+/* batched device form, like grcuda_clock_recovery_mm_ff_work_device: rows [time][channel], row 0 = absolute index
+ * abs_row0, every channel continues at its own carried position and stops 24 rows before the end (:124) or at
+ * max_out symbols; d_out [max_out][nchan], d_counts[c] = symbols produced (NULL: kept inside the plan). */
+int grcuda_clock_recovery_mm_cc_work_device(grcuda_mm_cc* h, long ninput_rows, long abs_row0, const grcuda_complex* d_in,
+                                            grcuda_complex* d_out, float* d_err, int max_out, int* d_counts, void* stream);
 
 /* ---- flagship pipeline: wideband -> PFB -> batched 4FSK demod -> sync search ---------------
  * One object that owns the HBM-resident intermediates and per-channel loop state and runs

@@ -95,6 +95,35 @@ def test_gpu_vs_oracle_and_time_domain(B, orc, dec, nt, n):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+@pytest.mark.parametrize("dec,nt,n,path", [(1, 1, 300, 1), (1, 2, 500, 1), (1, 5, 2000, 1), (3, 17, 4000, 1), (2, 33, 60000, 1),
+                                          (1, 129, 70000, 1), (4, 1000, 90000, 1), (1, 4096, 200000, 1), (5, 2049, 200000, 1),
+                                          (1, 5, 2000, 2), (2, 100, 30000, 2), (1, 4097, 300000, 2), (3, 20000, 600000, 2),
+                                          (1, 4097, 300000, -1), (1, 600, 50000, -1), (1, 20, 5000, -1)])
+def test_gpu_frequency_domain_paths(B, orc, dec, nt, n, path):
+    """The long filters that are the block's reason to exist, on both frequency-domain paths (and the automatic choice),
+    against the time-domain convolution in float64 and (small cases) the oracle's overlap-add."""
+    rng = np.random.default_rng(nt + 7 * dec)
+    taps = crandn(rng, nt) * np.float32(1.0 / np.sqrt(nt))
+    x = crandn(rng, n)
+    blk = B.fft_filter_ccc(dec, taps)
+    if path >= 0:
+        blk.set_path(path)
+        assert blk.work(blk.output_multiple(), x).size == 0       # deferred like set_taps
+        assert blk.path() == path
+    else:
+        assert blk.path() == (0 if nt <= 32 else (1 if nt <= 4096 else 2))
+    y = blk.run(x, blocks_per_call=3)
+    ns = blk.output_multiple()
+    assert len(y) == (n // dec) // ns * ns and len(y) > 0
+    from scipy.signal import fftconvolve
+    want = fftconvolve(x.astype(np.complex128), taps.astype(np.complex128))[: len(y) * dec: dec]
+    assert relerr(y, want) < 5e-6
+    if n <= 10000:
+        assert relerr(y, orc.FftFilter(dec, taps).run(x)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
 def test_gpu_contract_set_taps_and_errors(B, orc):
     rng = np.random.default_rng(4)
     t1, t2 = crandn(rng, 20) * np.float32(0.1), crandn(rng, 70) * np.float32(0.1)
