@@ -27,21 +27,45 @@ M = 8000
 T = 16
 FS_CHANNEL = 12500.0
 WORKLOAD = "cfg5: 100 MS/s -> 8000 x 12.5 kHz PFB channelizer (16 taps/branch) + batched DMR 4FSK demod + sync search"
-STAGE_BYTES = {  # algorithmic HBM bytes per input sample, per stage
-    "pfb_fir": 16.0, "pfb_fft": 16.0, "quad_demod": 12.0, "rrc_fir": 8.0,
-    "mm_slicer": 4.0 + (4.0 + 1.0) / (FS_CHANNEL / 4800.0), "map_unpack_corr": (1.0 + 2.0) / (FS_CHANNEL / 4800.0),
+SYMBOLS_PER_ROW = 4800.0 / FS_CHANNEL   # 4800 baud at 12.5 kS/s: one symbol per 2.604 rows
+# Per stage: algorithmic HBM bytes per input sample (SURVEY 8d / DESIGN.md section 4) and the roofline that really bounds
+# it.  "rrc_fir" is the chain's name for the FUSED discriminator + matched filter kernel (demod_front_kernel:
+# 8 B of channelizer output in, 4 B of filtered soft samples out = 12 B); the stand-alone discriminator stage
+# ("quad_demod") only runs in the unfused lab build.
+STAGE_BYTES = {
+    "pfb_fir": 16.0, "pfb_fft": 16.0, "quad_demod": 12.0, "rrc_fir": 12.0,
+    "mm_slicer": 4.0 + (4.0 + 1.0) * SYMBOLS_PER_ROW, "map_unpack_corr": (1.0 + 2.0) * SYMBOLS_PER_ROW,
 }
+STAGE_KERNEL = {"pfb_fir": "pfb_fir_tma_kernel", "pfb_fft": "fft_fixed_kernel", "quad_demod": "quad_demod_kernel",
+                "rrc_fir": "demod_front_kernel (quadrature_demod_cf + fir_filter_fff fused)",
+                "mm_slicer": "mm_quad_kernel / mm_ws_kernel (clock_recovery_mm_ff + slicer)",
+                "map_unpack_corr": "corr_par_kernel (map_bb + unpack_k_bits_bb + correlate_access_code_bb)"}
+STAGE_BOUND = {"pfb_fir": "hbm", "pfb_fft": "hbm", "quad_demod": "hbm", "rrc_fir": "fp32_issue", "mm_slicer": "latency",
+               "map_unpack_corr": "issue"}
+# The clock-recovery recursion: the dependent chain from one symbol's mu to the next (DESIGN.md section 4 lists the
+# operations): 23 dependent FP32/integer operations + one shared-memory round trip, at the latencies measured on this
+# pool's B200 (profiles/r2_fp32_peaks.json: 4.11 cycles per dependent FADD/FMUL/FFMA, 23 per dependent LDS).
+MM_CHAIN_OPS, MM_CHAIN_LDS = 23, 1
 
 
 ROOFLINE_NOTES = {   # which roofline really bounds each stage (ncu evidence under profiles/)
     "pfb_fir": "HBM stream (TMA staged)",
     "pfb_fft": "HBM and latency at one 400-thread CTA per SM (46 instructions per point; ncu: issue active 32 %, dram 46 %)",
     "rrc_fir": "FP32-issue bound, not HBM bound: the reference's SSE summation order forbids FMA (separate IEEE multiply "
-               "and add per tap) and the table arctangent needs a correctly rounded division; ncu: issue active 55 %, "
-               "dram 17 % of peak; DRAM traffic = algorithmic bytes",
-    "mm_slicer": "latency bound: one sequential recursion per channel, 250 warps at single-warp instruction latency; runs "
-                 "concurrently with the next block's front",
+               "and add per tap) and the table arctangent needs a correctly rounded division; DRAM traffic = algorithmic bytes",
+    "mm_slicer": "latency bound: one sequential recursion per channel (8000 channels = 250 warps at single-warp "
+                 "instruction latency); its own roofline is the dependent-chain floor, see own_bound",
+    "map_unpack_corr": "integer issue (popcount windows over packed dibits), off the serial chain",
 }
+
+
+def measured_fp32():
+    """FP32 / issue / latency peaks measured on this pool's B200 by tools/measure_fp32_peaks.cu (committed result)."""
+    p = os.path.join(ROOT, "profiles", "r2_fp32_peaks.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def chain_config(max_rows, keep_bytes=False):
@@ -372,34 +396,56 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (device time share inside the timed region) --------------
+    # ---- roofline of the dominant kernel = the one with the largest device time inside the timed region -------------
     hbm_peak, peak_kind = peaks()
+    fp = measured_fp32()
     stage_ms = {k: v[0] for k, v in prof.items()}
     stage_ln = {k: v[1] for k, v in prof.items()}
     busy = sum(stage_ms.values()) or 1.0
     stages = {}
     rows_done = (halo + R) * args.steps
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    inst = {}
+    ip = os.path.join(ROOT, "profiles", "instructions.json")   # warp instructions per cfg5 block from the committed ncu capture
+    if os.path.exists(ip):
+        try:
+            inst = json.load(open(ip))
+        except Exception:
+            inst = {}
     for k in STAGE_BYTES:
-        if stage_ms[k] <= 0:
+        if stage_ms.get(k, 0) <= 0:
             continue
         bytes_total = STAGE_BYTES[k] * rows_done * M
         gbs = bytes_total / (stage_ms[k] * 1e-3) / 1e9
-        stages[k] = {"ms_per_step": stage_ms[k] / args.steps, "launches_per_step": stage_ln[k] / args.steps,
-                     "share": stage_ms[k] / busy, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
-    # dominant kernel = the longest one on the critical path: the tail (mm_slicer) runs on its own stream underneath the
-    # next block's front, so it only counts when it is longer than the whole front
-    front = [k for k in stages if k != "mm_slicer"]
-    front_ms = sum(stages[k]["ms_per_step"] for k in front)
-    if front and stages.get("mm_slicer", {"ms_per_step": 0})["ms_per_step"] <= front_ms:
-        dom = max(front, key=lambda k: stages[k]["ms_per_step"])
-    else:
-        dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+        st = {"kernel": STAGE_KERNEL[k], "ms_per_step": stage_ms[k] / args.steps, "launches_per_step": stage_ln[k] / args.steps,
+              "share": stage_ms[k] / busy, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "bound": STAGE_BOUND[k]}
+        per_launch_ms = stage_ms[k] / max(stage_ln[k], 1)
+        if STAGE_BOUND[k] == "latency" and fp:
+            # cycles one symbol takes vs the dependent-chain floor at the measured instruction latencies
+            syms = (halo + R) * SYMBOLS_PER_ROW * (args.steps / max(stage_ln[k], 1))
+            cyc = per_launch_ms * 1e-3 * sm_mhz * 1e6 / syms
+            floor = MM_CHAIN_OPS * fp["lat_w1"]["fadd"] + MM_CHAIN_LDS * fp["lds_dependent_cycles_w1"]
+            st["own_bound"] = {"kind": "latency", "achieved": cyc, "floor": floor, "unit": "cycles/symbol", "frac": floor / cyc,
+                               "peak_source": "profiles/r2_fp32_peaks.json"}
+        elif STAGE_BOUND[k] in ("fp32_issue", "issue") and fp and inst.get(k):
+            # warp instructions per second vs the measured issue rate (one instruction per scheduler per cycle)
+            wi = inst[k] * (halo + R) / 12500.0
+            rate = wi / (per_launch_ms * 1e-3) / 1e9
+            st["own_bound"] = {"kind": STAGE_BOUND[k], "achieved": rate, "peak": fp["issue_ginst_s"], "unit": "G warp-instructions/s",
+                               "frac": rate / fp["issue_ginst_s"], "warp_instructions_per_launch": wi,
+                               "peak_source": "profiles/r2_fp32_peaks.json", "count_source": "profiles/instructions.json (ncu)"}
+        stages[k] = st
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     d = stages[dom]
     per_launch_bytes = STAGE_BYTES[dom] * rows_done * M / max(stage_ln[dom], 1)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": None,
+    roofline = {"bound": "hbm", "kernel": dom, "kernel_name": STAGE_KERNEL[dom], "achieved": d["algorithmic_GBps"], "peak": hbm_peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": None,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "avg_launch_ms": stage_ms[dom] / max(stage_ln[dom], 1), "stages": stages,
+                "avg_launch_ms": stage_ms[dom] / max(stage_ln[dom], 1), "real_bound": STAGE_BOUND[dom],
+                "own_bound": d.get("own_bound"), "stages": stages,
+                "chain": {"algorithmic_bytes_per_sample": sum(STAGE_BYTES[k] for k in stages),
+                          "GBps_over_step": sum(STAGE_BYTES[k] for k in stages) * R * M / (ms_max / args.steps * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": sum(STAGE_BYTES[k] for k in stages) * R * M / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak},
                 "note": ROOFLINE_NOTES.get(dom, "")}
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp):
@@ -437,6 +483,18 @@ def run_ours(args):
         except Exception as e:  # the baseline must never take the bench down
             cpu = {"value": None, "unit": "MS/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
 
+    # ---- the other BASELINE.json configs and the blocks either side of the path (N = 1 only), each with its own fraction
+    extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            del x
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_blocks.py")], stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True, timeout=240)
+            extra = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"failed": r.stderr[-400:]}
+        except Exception as e:
+            extra = {"failed": repr(e)}
+
     line = {
         "metric": "input MS/s, PFB channelizer+DMR demod", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -448,7 +506,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": (Th + R) * M * 8, "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps, "api": "grcuda_dmr_chain_process_host + grcuda_dmr_chain_read_hits (pinned host input)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "parity": parity, "sustained": sustained,
+        "parity": parity, "sustained": sustained, "extra": extra,
     }
     if json_fd is not None:
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -483,6 +541,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of one pass of the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work to time for the baseline beside the GPU number")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other configs / single blocks (tools/bench_blocks.py) at N = 1")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra, separately timed steady-state region (0: none)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the comparison of all sync hits with a single chain")
     ap.add_argument("--tail-variant", type=int, default=None, help="build of the clock-recovery kernel (default: the chain's choice)")

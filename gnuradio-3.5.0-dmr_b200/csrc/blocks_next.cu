@@ -76,6 +76,27 @@ __global__ void __launch_bounds__(256) map_bb_kernel(const unsigned char* __rest
 // gr_unpack_k_bits_bb: byte i -> k bytes, most significant of the k low bits first (gr_unpack_k_bits_bb.cc:53-70).
 // A thread makes 4 consecutive output bytes (one 32-bit store); (1 + 1/k) B of HBM per output item.
 // =====================================================================================================================
+// k in {1, 2, 4, 8}: a thread expands 16 / k input bytes into one 16-byte store
+template <int K>
+__global__ void __launch_bounds__(256) unpack_pow2_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                                                          long nvec) {
+  constexpr int NIN = 16 / K;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    unsigned char t[NIN];
+    if (NIN == 16) *reinterpret_cast<uint4*>(t) = __ldg(reinterpret_cast<const uint4*>(in) + v);
+    else if (NIN == 8) *reinterpret_cast<uint2*>(t) = __ldg(reinterpret_cast<const uint2*>(in) + v);
+    else if (NIN == 4) *reinterpret_cast<unsigned*>(t) = __ldg(reinterpret_cast<const unsigned*>(in) + v);
+    else *reinterpret_cast<unsigned short*>(t) = __ldg(reinterpret_cast<const unsigned short*>(in) + v);
+    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int o = 0; o < 16; o++) {
+      const unsigned bit = (t[o / K] >> (K - 1 - (o % K))) & 1u;
+      w[o >> 2] |= bit << (8 * (o & 3));
+    }
+    reinterpret_cast<uint4*>(out)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) unpack_k_bits_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
                                                             long nout, unsigned k) {
   const bool al = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
@@ -245,6 +266,12 @@ __global__ void __launch_bounds__(128) framer_rows_kernel(const FramerArgs a) {
     unsigned b[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) b[i] = __ldg(p + (t + i) * a.t_stride);
+    if (s.state == 0) {                     // searching and no flag in these 16 items: nothing happens (:104-112)
+      unsigned any = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) any |= b[i];
+      if (!(any & 2)) continue;
+    }
 #pragma unroll
     for (int i = 0; i < 16; i++) framer_byte(a, c, s, pkt, b[i], s.consumed + t + i);
   }
@@ -343,51 +370,97 @@ struct MMCCArgs {
   const float* mmse;         // [129][8], coefficient applied to in[ii + i]
 };
 
-__global__ void __launch_bounds__(64) mm_cc_kernel(const MMCCArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// The loop feeds floor(mu) back into the next input index, so a channel is one thread; what the kernel can do is keep
+// HBM latency out of the recursion: a CTA owns 64 neighbouring channels and walks the rows in tiles of MMCC_TR rows
+// (8 rows of overlap = the interpolator's window) that arrive in shared memory through cp.async one tile ahead of the
+// one being consumed.  Inside a tile every thread runs its own recursion on LDS.64 reads until its window would leave
+// the tile.  HBM sees each input row once (8 B per item) plus the symbols.
+#define MMCC_TR 40
+#define MMCC_CH 64
+__device__ __forceinline__ void mmcc_load_tile(const MMCCArgs& a, float2* __restrict__ buf, long t0, int c0) {
+  const int c = c0 + threadIdx.x;
   if (c >= a.nchan) return;
-  MMCCChan s = a.chan[c];
-  const long M = a.nchan;
-  long ii = (long)(s.next_abs - a.abs_row0);
-  if (ii < 0) { ii = 0; s.clamped++; }
+  const float2* src = a.in + t0 * (long)a.nchan + c;
+  for (int r = 0; r < MMCC_TR; r++) {
+    if (t0 + r < a.ninput) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + r * MMCC_CH + threadIdx.x);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + (long)r * a.nchan) : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MMCC_CH) mm_cc_kernel(const MMCCArgs a) {
+  __shared__ __align__(16) float2 tiles[2][MMCC_TR * MMCC_CH];
+  __shared__ float tab[129 * 8];
+  for (int i = threadIdx.x; i < 129 * 8; i += MMCC_CH) tab[i] = a.mmse[i];
+  const int c0 = blockIdx.x * MMCC_CH;
+  const int c = c0 + threadIdx.x;
+  const bool live = c < a.nchan;
+  MMCCChan s;
+  if (live) s = a.chan[c];
+  long ii = 0;
+  if (live) {
+    ii = (long)(s.next_abs - a.abs_row0);
+    if (ii < 0) { ii = 0; s.clamped++; }
+  }
   const long ni = a.ninput - 8 - 16;                 // ntaps() and FUDGE (:124)
   const float lim = a.err ? 4.0f : 1.0f;             // :146 vs :178
+  const long M = a.nchan;
+  constexpr int S = MMCC_TR - 8;                     // rows a tile is responsible for
+  const long ntiles = ni > 0 ? (ni + S - 1) / S : 0;
   int oo = 0;
-  while (oo < a.max_out && ii < ni) {
-    s.p_2T = s.p_1T;
-    s.p_1T = s.p_0T;
-    const float* e = a.mmse + mm_imu(s.mu) * 8;
-    const float2* x = a.in + ii * M + c;
-    float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;   // gr_fir_ccf_generic::filter (gr_fir_XXX_generic.cc.t:28-55)
+  if (ntiles > 0) mmcc_load_tile(a, tiles[0], 0, c0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (long k = 0; k < ntiles; k++) {
+    if (k + 1 < ntiles) mmcc_load_tile(a, tiles[(k + 1) & 1], (k + 1) * S, c0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float2* __restrict__ tile = tiles[k & 1] + threadIdx.x;
+    const long t0 = k * S;
+    const long stop = (k + 1) * S < ni ? (k + 1) * S : ni;
+    while (live && oo < a.max_out && ii < stop) {
+      s.p_2T = s.p_1T;
+      s.p_1T = s.p_0T;
+      const float* e = tab + mm_imu(s.mu) * 8;
+      const float2* x = tile + (ii - t0) * MMCC_CH;
+      float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;   // gr_fir_ccf_generic::filter (gr_fir_XXX_generic.cc.t:28-55)
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      const float2 v0 = __ldg(x + (long)i * M), v1 = __ldg(x + (long)(i + 1) * M);
-      const float t0 = __ldg(e + i), t1 = __ldg(e + i + 1);
-      a0r = GR_FADD(a0r, GR_FMUL(t0, v0.x)); a0i = GR_FADD(a0i, GR_FMUL(t0, v0.y));
-      a1r = GR_FADD(a1r, GR_FMUL(t1, v1.x)); a1i = GR_FADD(a1i, GR_FMUL(t1, v1.y));
+      for (int i = 0; i < 8; i += 2) {
+        const float2 v0 = x[i * MMCC_CH], v1 = x[(i + 1) * MMCC_CH];
+        const float t0c = e[i], t1c = e[i + 1];
+        a0r = GR_FADD(a0r, GR_FMUL(t0c, v0.x)); a0i = GR_FADD(a0i, GR_FMUL(t0c, v0.y));
+        a1r = GR_FADD(a1r, GR_FMUL(t1c, v1.x)); a1i = GR_FADD(a1i, GR_FMUL(t1c, v1.y));
+      }
+      s.p_0T = make_float2(GR_FADD(a0r, a1r), GR_FADD(a0i, a1i));
+      s.c_2T = s.c_1T;
+      s.c_1T = s.c_0T;
+      s.c_0T = make_float2(s.p_0T.x > 0 ? 1.0f : 0.0f, s.p_0T.y > 0 ? 1.0f : 0.0f);   // slicer_0deg (:93-103)
+      // x = (c_0T - c_2T) * conj(p_1T); y = (p_0T - p_2T) * conj(c_1T); mm_val = real(y - x)   (:137-140)
+      const float ar = GR_FSUB(s.c_0T.x, s.c_2T.x), ai = GR_FSUB(s.c_0T.y, s.c_2T.y);
+      const float xr = GR_FSUB(GR_FMUL(ar, s.p_1T.x), GR_FMUL(ai, -s.p_1T.y));
+      const float br = GR_FSUB(s.p_0T.x, s.p_2T.x), bi = GR_FSUB(s.p_0T.y, s.p_2T.y);
+      const float yr = GR_FSUB(GR_FMUL(br, s.c_1T.x), GR_FMUL(bi, -s.c_1T.y));
+      float mm_val = GR_FSUB(yr, xr);
+      a.out[(long)oo * M + c] = s.p_0T;
+      mm_val = branchless_clip(mm_val, lim);
+      s.omega = GR_FADD(s.omega, GR_FMUL(a.gain_omega, mm_val));
+      s.omega = GR_FADD(a.omega_mid, branchless_clip(GR_FSUB(s.omega, a.omega_mid), a.omega_relative_limit));
+      s.mu = GR_FADD(GR_FADD(s.mu, s.omega), GR_FMUL(a.gain_mu, mm_val));
+      const float fl = floorf(s.mu);
+      ii += (long)(int)fl;
+      s.mu = GR_FSUB(s.mu, fl);
+      if (a.err) a.err[(long)oo * M + c] = mm_val;
+      oo++;
+      if (ii < t0) {                                   // a step BACK out of the tile: only bogus input does that (:166)
+        if (ii < 0) { ii = 0; s.clamped++; }
+        if (ii < t0) { ii = t0; s.clamped++; }         // (the tile's first row is the oldest one still on chip)
+      }
     }
-    s.p_0T = make_float2(GR_FADD(a0r, a1r), GR_FADD(a0i, a1i));
-    s.c_2T = s.c_1T;
-    s.c_1T = s.c_0T;
-    s.c_0T = make_float2(s.p_0T.x > 0 ? 1.0f : 0.0f, s.p_0T.y > 0 ? 1.0f : 0.0f);   // slicer_0deg (:93-103)
-    // x = (c_0T - c_2T) * conj(p_1T); y = (p_0T - p_2T) * conj(c_1T); mm_val = real(y - x)   (:137-140)
-    const float ar = GR_FSUB(s.c_0T.x, s.c_2T.x), ai = GR_FSUB(s.c_0T.y, s.c_2T.y);
-    const float xr = GR_FSUB(GR_FMUL(ar, s.p_1T.x), GR_FMUL(ai, -s.p_1T.y));
-    const float br = GR_FSUB(s.p_0T.x, s.p_2T.x), bi = GR_FSUB(s.p_0T.y, s.p_2T.y);
-    const float yr = GR_FSUB(GR_FMUL(br, s.c_1T.x), GR_FMUL(bi, -s.c_1T.y));
-    float mm_val = GR_FSUB(yr, xr);
-    a.out[(long)oo * M + c] = s.p_0T;
-    mm_val = branchless_clip(mm_val, lim);
-    s.omega = GR_FADD(s.omega, GR_FMUL(a.gain_omega, mm_val));
-    s.omega = GR_FADD(a.omega_mid, branchless_clip(GR_FSUB(s.omega, a.omega_mid), a.omega_relative_limit));
-    s.mu = GR_FADD(GR_FADD(s.mu, s.omega), GR_FMUL(a.gain_mu, mm_val));
-    const float fl = floorf(s.mu);
-    ii += (long)(int)fl;
-    s.mu = GR_FSUB(s.mu, fl);
-    if (a.err) a.err[(long)oo * M + c] = mm_val;
-    oo++;
-    if (ii < 0) { ii = 0; s.clamped++; }             // "This should only happen with bogus input" (:166)
+    __syncthreads();                                   // tile k's buffer is refilled with tile k + 2 next
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!live) return;
   if (oo >= a.max_out && ii < ni) s.overflow++;
   s.next_abs = a.abs_row0 + ii;
   a.counts[c] = oo;
@@ -452,7 +525,7 @@ struct grcuda_mm_cc : Plan {
     a.in = d_in; a.ninput = ninput; a.abs_row0 = abs_row0; a.out = d_out; a.err = d_err; a.max_out = max_out; a.nchan = nchan;
     a.counts = d_cnt; a.chan = d_chan.as<MMCCChan>(); a.gain_omega = gain_omega; a.gain_mu = gain_mu; a.omega_mid = omega_mid;
     a.omega_relative_limit = lim; a.mmse = tables.mmse_eff;
-    mm_cc_kernel<<<(nchan + 63) / 64, 64, 0, s>>>(a);
+    mm_cc_kernel<<<(nchan + MMCC_CH - 1) / MMCC_CH, MMCC_CH, 0, s>>>(a);
     GRB_LAUNCH_CHECK();
     return GRCUDA_OK;
   }
@@ -502,8 +575,24 @@ unsigned grcuda_unpack_k_bits_bb_interpolation(grcuda_unpack_k_bits* h) { return
 int grcuda_unpack_k_bits_bb_work_device(grcuda_unpack_k_bits* h, long noutput_items, const unsigned char* d_in, unsigned char* d_out, void* stream) {
   const long nout = noutput_items / h->k * h->k;     // :60: noutput_items / d_k input bytes
   if (nout <= 0) return GRCUDA_OK;
-  unpack_k_bits_kernel<<<grid_of((nout + 3) / 4, 256), 256, 0, h->pick(stream)>>>(d_in, d_out, nout, h->k);
-  GRB_LAUNCH_CHECK();
+  cudaStream_t s = h->pick(stream);
+  const unsigned k = h->k;
+  long done = 0;   // output bytes made by the 16-byte kernel
+  if ((k == 1 || k == 2 || k == 4 || k == 8) && !(reinterpret_cast<uintptr_t>(d_out) & 15) && !(reinterpret_cast<uintptr_t>(d_in) & (16 / k - 1)) &&
+      nout >= 16) {
+    const long nvec = nout / 16;
+    const int g = grid_of(nvec, 256);
+    if (k == 1) unpack_pow2_kernel<1><<<g, 256, 0, s>>>(d_in, d_out, nvec);
+    else if (k == 2) unpack_pow2_kernel<2><<<g, 256, 0, s>>>(d_in, d_out, nvec);
+    else if (k == 4) unpack_pow2_kernel<4><<<g, 256, 0, s>>>(d_in, d_out, nvec);
+    else unpack_pow2_kernel<8><<<g, 256, 0, s>>>(d_in, d_out, nvec);
+    GRB_LAUNCH_CHECK();
+    done = nvec * 16;
+  }
+  if (done < nout) {
+    unpack_k_bits_kernel<<<grid_of((nout - done + 3) / 4, 256), 256, 0, s>>>(d_in + done / k, d_out + done, nout - done, k);
+    GRB_LAUNCH_CHECK();
+  }
   return GRCUDA_OK;
 }
 int grcuda_unpack_k_bits_bb_work(grcuda_unpack_k_bits* h, int noutput_items, const unsigned char* in, unsigned char* out) {

@@ -821,45 +821,27 @@ int grcuda_pfb_decimator_ccf_work(grcuda_pfb_decim* h, int noutput_items, const 
 // work(), which returns 0 and clears the carried state (:62-69):
 //   * ntaps <= kDirectMax: the direct-form decimating FIR (fir_decim_kernel) -- fewer operations than two FFTs;
 //   * fftsize <= kFusedMax: overlap-save with both FFTs and the product inside one CTA (kernel_fft_filter.cuh);
-//   * longer filters: the same overlap-save on the batched FFT engine (pack, forward, product, inverse, unpack).
+//   * longer filters: uniformly partitioned overlap-save -- the same kernel once per 4096-tap partition, reading
+//     further back in the carried input and accumulating into the output; no FFT longer than 8192 points.
 struct grcuda_fft_filter : PlanBase {
-  static const int kDirectMax = 32, kFusedMax = 8192;
+  static const int kDirectMax = 32, kFusedMax = 8192, kPartTaps = 4096;
   int decim = 1, ntaps = 0, nsamples = 1, fftsize = 2;
-  int path = 0;                 // 0 direct, 1 fused overlap-save, 2 FFT engine
+  int path = 0;                 // 0 direct, 1 fused overlap-save, 2 partitioned fused overlap-save
   int force_path = -1;          // tests: pin the path (-1 = automatic)
+  int kfft = 2, ptaps = 1, hop = 1, nparts = 1;   // kernel geometry of paths 1 / 2
+  size_t carry_len = 0;         // input items kept in front of the new ones
   bool updated = false;
   std::vector<float> new_taps;  // interleaved re, im
   std::vector<float> cur_taps;
   FirCore core;
-  DevBuf d_buf, d_carry;        // [carry | new input] contiguous; the last ntaps-1 samples seen
-  DevBuf d_H, d_tw, d_rows;
+  DevBuf d_buf, d_carry;        // [carry | new input] contiguous
+  DevBuf d_H, d_tw;
   FftFiltArgs fa;
-  FftPlan* fwd = nullptr;
-  FftPlan* inv = nullptr;
-  ~grcuda_fft_filter() { if (fwd) fft_plan_destroy(fwd); if (inv) fft_plan_destroy(inv); }
   static int fftsize_for(int nt) { return (int)(2 * pow(2.0, ceil(log((double)nt) / log(2.0)))); }  // :106
-  int build(const std::vector<float>& t_ri) {
-    cudaDeviceSynchronize();
-    cur_taps = t_ri;
-    ntaps = (int)t_ri.size() / 2;
-    fftsize = fftsize_for(ntaps);
-    nsamples = fftsize - ntaps + 1;
-    path = force_path >= 0 ? force_path : (ntaps <= kDirectMax ? 0 : (fftsize <= kFusedMax ? 1 : 2));
-    if (path == 1 && fftsize > kFusedMax) path = 2;
-    int rc;
-    const size_t cb = (size_t)std::max(ntaps - 1, 1) * sizeof(float2);
-    if ((rc = d_carry.reserve(cb))) return rc;
-    GRB_CUDA(cudaMemset(d_carry.p, 0, cb));  // the tail is cleared by set_taps (:67-69)
-    if (path == 0) {
-      std::vector<float> rev(t_ri.size());
-      for (int k = 0; k < ntaps; k++) { rev[2 * k] = t_ri[2 * (ntaps - 1 - k)]; rev[2 * k + 1] = t_ri[2 * (ntaps - 1 - k) + 1]; }
-      core.decim = decim;
-      return core.upload(rev.data(), ntaps, true);
-    }
-    // H = FFT(taps) / fftsize (:80-94), evaluated in double on the host: a plain radix-2 transform of the padded taps
-    const int n = fftsize;
+  // FFT(taps[0..nt) zero padded to n) / n in double (:80-94), as float2
+  static void transform_taps(const float* t_ri, int nt, int n, float2* out) {
     std::vector<std::complex<double>> H(n, 0.0);
-    for (int k = 0; k < ntaps; k++) H[k] = std::complex<double>(t_ri[2 * k], t_ri[2 * k + 1]) / (double)n;
+    for (int k = 0; k < nt; k++) H[k] = std::complex<double>(t_ri[2 * k], t_ri[2 * k + 1]) / (double)n;
     for (int i = 1, j = 0; i < n; i++) {  // bit reversal
       int bit = n >> 1;
       for (; j & bit; bit >>= 1) j ^= bit;
@@ -875,75 +857,78 @@ struct grcuda_fft_filter : PlanBase {
           H[i + k + len / 2] = u - v;
         }
     }
-    std::vector<float2> Hf(n);
-    for (int i = 0; i < n; i++) Hf[i] = make_float2((float)H[i].real(), (float)H[i].imag());
-    if ((rc = d_H.reserve((size_t)n * sizeof(float2)))) return rc;
-    GRB_CUDA(cudaMemcpy(d_H.p, Hf.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
-    if (path == 1) {
-      memset(&fa, 0, sizeof fa);
-      int m = 0;
-      while ((1 << m) < n) m++;
-      std::vector<float2> tw;
-      int Ns = 1;
-      fa.npass = 0;
-      while (m > 0) {
-        const int lr = m >= 4 ? 4 : m, R = 1 << lr;
-        fa.radix[fa.npass] = R;
-        fa.tw_off[fa.npass] = (int)tw.size();
-        for (int k = 0; k < Ns; k++) {
-          const double ang = -2.0 * M_PI * k / ((double)Ns * R);
-          tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
-        }
-        Ns *= R;
-        m -= lr;
-        fa.npass++;
-      }
-      if ((rc = d_tw.reserve(tw.size() * sizeof(float2)))) return rc;
-      GRB_CUDA(cudaMemcpy(d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-      fa.H = d_H.as<float2>();
-      fa.tw = d_tw.as<float2>();
-      fa.n = n; fa.ntaps = ntaps; fa.nsamples = nsamples; fa.decim = decim;
-      const size_t smem = (size_t)(n + n / 16 + 1) * sizeof(float2);
-      if (cudaError_t e = raise_dynamic_smem((const void*)fft_filter_ols_kernel<512>, smem))
-        return set_error(GRCUDA_ECUDA, "fft_filter_ccc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    } else {
-      if (fwd) fft_plan_destroy(fwd);
-      if (inv) fft_plan_destroy(inv);
-      fwd = fft_plan_create(n, -1);
-      inv = fft_plan_create(n, +1);
-      if (!fwd || !inv) return g_last_error_code;
+    for (int i = 0; i < n; i++) out[i] = make_float2((float)H[i].real(), (float)H[i].imag());
+  }
+  int build(const std::vector<float>& t_ri) {
+    cudaDeviceSynchronize();
+    cur_taps = t_ri;
+    ntaps = (int)t_ri.size() / 2;
+    fftsize = fftsize_for(ntaps);
+    nsamples = fftsize - ntaps + 1;
+    path = force_path >= 0 ? force_path : (ntaps <= kDirectMax ? 0 : (fftsize <= kFusedMax ? 1 : 2));
+    if (path == 1 && fftsize > kFusedMax) path = 2;
+    if (path == 1) { kfft = fftsize; ptaps = ntaps; nparts = 1; }
+    else if (path == 2) { ptaps = std::min(ntaps, (int)kPartTaps); kfft = fftsize_for(ptaps); nparts = (ntaps + ptaps - 1) / ptaps; }
+    hop = kfft - ptaps + 1;
+    carry_len = path == 0 ? (size_t)(ntaps - 1) : (size_t)nparts * ptaps - 1;
+    int rc;
+    const size_t cb = std::max<size_t>(carry_len, 1) * sizeof(float2);
+    if ((rc = d_carry.reserve(cb))) return rc;
+    GRB_CUDA(cudaMemset(d_carry.p, 0, cb));  // the tail is cleared by set_taps (:67-69)
+    if (path == 0) {
+      std::vector<float> rev(t_ri.size());
+      for (int k = 0; k < ntaps; k++) { rev[2 * k] = t_ri[2 * (ntaps - 1 - k)]; rev[2 * k + 1] = t_ri[2 * (ntaps - 1 - k) + 1]; }
+      core.decim = decim;
+      return core.upload(rev.data(), ntaps, true);
     }
+    const int n = kfft;
+    std::vector<float2> Hf((size_t)n * nparts);
+    for (int p = 0; p < nparts; p++)
+      transform_taps(t_ri.data() + 2 * (size_t)p * ptaps, std::min(ptaps, ntaps - p * ptaps), n, Hf.data() + (size_t)p * n);
+    if ((rc = d_H.reserve(Hf.size() * sizeof(float2)))) return rc;
+    GRB_CUDA(cudaMemcpy(d_H.p, Hf.data(), Hf.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    memset(&fa, 0, sizeof fa);
+    int m = 0;
+    while ((1 << m) < n) m++;
+    std::vector<float2> tw;
+    int Ns = 1;
+    fa.npass = 0;
+    while (m > 0) {
+      const int lr = m >= 4 ? 4 : m, R = 1 << lr;
+      fa.radix[fa.npass] = R;
+      fa.tw_off[fa.npass] = (int)tw.size();
+      for (int k = 0; k < Ns; k++) {
+        const double ang = -2.0 * M_PI * k / ((double)Ns * R);
+        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+      }
+      Ns *= R;
+      m -= lr;
+      fa.npass++;
+    }
+    if ((rc = d_tw.reserve(tw.size() * sizeof(float2)))) return rc;
+    GRB_CUDA(cudaMemcpy(d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    fa.tw = d_tw.as<float2>();
+    fa.n = n; fa.ntaps = ptaps; fa.nsamples = hop; fa.decim = decim;
+    const size_t smem = (size_t)(n + n / 16 + 1) * sizeof(float2);
+    if (cudaError_t e = raise_dynamic_smem((const void*)fft_filter_ols_kernel<512>, smem))
+      return set_error(GRCUDA_ECUDA, "fft_filter_ccc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     return GRCUDA_OK;
   }
-  // buf = [ntaps-1 carried | nblk * nsamples new] -> out (nblk * nsamples / decim items)
-  int run_freq(const float2* buf, float2* out, long nblk, cudaStream_t s) {
-    if (path == 1) {
+  // buf = [carry_len carried | nin new] -> out (nin / decim items)
+  int run_freq(const float2* buf, float2* out, long nin, cudaStream_t s) {
+    const int threads = std::max(32, kfft / FFTF_ELEMS);
+    const size_t smem = (size_t)(kfft + kfft / 16 + 1) * sizeof(float2);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (200u << 10) / std::max<size_t>(smem, 1)));
+    const long nblk = (nin + hop - 1) / hop;
+    const int grid = (int)std::min<long>(nblk, (long)sm_count() * per_sm);
+    for (int p = 0; p < nparts; p++) {
       FftFiltArgs a = fa;
-      a.x = buf; a.out = out; a.nblk = nblk;
-      const int threads = std::max(32, fftsize / FFTF_ELEMS);
-      const size_t smem = (size_t)(fftsize + fftsize / 16 + 1) * sizeof(float2);
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (200u << 10) / std::max<size_t>(smem, 1)));
-      const int grid = (int)std::min<long>(nblk, (long)sm_count() * per_sm);
+      const long start = (long)carry_len - (ptaps - 1) - (long)p * ptaps;   // >= 0 by the choice of carry_len
+      a.x = buf + start;
+      a.x_limit = (long)carry_len + nin - start;
+      a.out = out; a.nblk = nblk; a.total_items = nin; a.accumulate = p > 0;
+      a.H = d_H.as<float2>() + (size_t)p * kfft;
       fft_filter_ols_kernel<512><<<grid, threads, smem, s>>>(a);
-      GRB_LAUNCH_CHECK();
-      return GRCUDA_OK;
-    }
-    // FFT engine, a bounded number of blocks at a time (two row buffers of <= 256 MB)
-    const long per = std::max<long>(1, (long)((256u << 20) / ((size_t)fftsize * sizeof(float2))));
-    int rc;
-    if ((rc = d_rows.reserve((size_t)std::min(per, nblk) * fftsize * sizeof(float2) * 2))) return rc;
-    float2* r0 = d_rows.as<float2>();
-    float2* r1 = r0 + (size_t)std::min(per, nblk) * fftsize;
-    for (long b0 = 0; b0 < nblk; b0 += per) {
-      const long nb = std::min(per, nblk - b0);
-      const int g = grid_for(nb * fftsize, 256);
-      fftf_pack_kernel<<<g, 256, 0, s>>>(buf + b0 * nsamples, r0, fftsize, nsamples, nb);
-      GRB_LAUNCH_CHECK();
-      if ((rc = fft_plan_exec(fwd, r0, r1, nb, nullptr, 0, 0, s))) return rc;
-      fftf_mul_kernel<<<g, 256, 0, s>>>(r1, d_H.as<float2>(), fftsize, nb);
-      GRB_LAUNCH_CHECK();
-      if ((rc = fft_plan_exec(inv, r1, r0, nb, nullptr, 0, 0, s))) return rc;
-      fftf_unpack_kernel<<<grid_for(nb * nsamples, 256), 256, 0, s>>>(r0, out, fftsize, ntaps, nsamples, decim, nb, b0 * nsamples);
       GRB_LAUNCH_CHECK();
     }
     return GRCUDA_OK;
@@ -993,14 +978,14 @@ int grcuda_fft_filter_ccc_work_device(grcuda_fft_filter* h, int noutput_items, c
   if (noutput_items <= 0) return 0;
   if (noutput_items % h->nsamples) return set_error(GRCUDA_EINVAL, "fft_filter_ccc: noutput_items %d is not a multiple of %d (:92)", noutput_items, h->nsamples);
   cudaStream_t s = h->pick(stream);
-  const size_t nin = (size_t)noutput_items * h->decim, nc = (size_t)h->ntaps - 1;
+  const size_t nin = (size_t)noutput_items * h->decim, nc = h->carry_len;
   int rc;
   if ((rc = h->d_buf.reserve((nc + nin) * sizeof(float2)))) return rc;
   float2* buf = h->d_buf.as<float2>();
   if (nc) GRB_CUDA(cudaMemcpyAsync(buf, h->d_carry.p, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   GRB_CUDA(cudaMemcpyAsync(buf + nc, d_in, nin * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   if (h->path == 0) rc = h->core.launch(buf, (float2*)d_out, noutput_items, false, 0.0, 0, s);
-  else rc = h->run_freq(buf, (float2*)d_out, (long)(nin / h->nsamples), s);
+  else rc = h->run_freq(buf, (float2*)d_out, (long)nin, s);
   if (rc) return rc;
   if (nc) GRB_CUDA(cudaMemcpyAsync(h->d_carry.p, buf + nin, nc * sizeof(float2), cudaMemcpyDeviceToDevice, s));
   return noutput_items;

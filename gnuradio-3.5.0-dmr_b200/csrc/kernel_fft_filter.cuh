@@ -23,12 +23,15 @@ namespace grb {
 #define FFTF_ELEMS 16
 
 struct FftFiltArgs {
-  const float2* x;    // [ntaps-1 carried items | nblk * nsamples new items]
-  float2* out;        // nblk * nsamples / decim items
-  const float2* H;    // [n] FFT(taps) / n, natural order
+  const float2* x;    // block b reads x[b * nsamples + i], i < n (items at or beyond x_limit read as zero)
+  float2* out;        // total_items / decim items
+  const float2* H;    // [n] FFT(taps of this partition) / n, natural order
   const float2* tw;   // forward twiddles e^{-2 pi i k / (Ns R)}, k < Ns, pass after pass (the inverse conjugates them)
-  int n, ntaps, nsamples, decim;
+  int n, ntaps, nsamples, decim;   // ntaps: taps per partition (n - nsamples + 1); nsamples: hop = kept items per block
   long nblk;
+  long x_limit;       // items readable behind x
+  long total_items;   // input-rate items this call produces (the last block may be partial)
+  int accumulate;     // 1: out += (partitions after the first)
   int npass;
   int radix[FFTF_MAX_PASSES];
   int tw_off[FFTF_MAX_PASSES];
@@ -37,7 +40,9 @@ struct FftFiltArgs {
 struct FftFiltPass {  // what a pass needs of the arguments, by value (registers, not a pointer into local memory)
   const float2* H;
   float2* out;
-  int n, ntaps, decim;
+  int n, ntaps, decim, accumulate;
+  long total_items;
+  long in_left;       // readable items from this block's first one on
 };
 
 __device__ __forceinline__ int fftf_phys(int i) { return i + (i >> 4); }
@@ -59,7 +64,7 @@ __device__ __noinline__ void fftf_pass(const FftFiltPass a, float2* __restrict__
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const int i = j + r * nb;
-        if (SRC == 0) v[b][r] = __ldg(gin + i);
+        if (SRC == 0) v[b][r] = i < a.in_left ? __ldg(gin + i) : make_float2(0.f, 0.f);
         else if (SRC == 1) v[b][r] = s[fftf_phys(i)];
         else v[b][r] = cmul(s[fftf_phys(i)], __ldg(a.H + i));
       }
@@ -85,8 +90,10 @@ __device__ __noinline__ void fftf_pass(const FftFiltPass a, float2* __restrict__
           s[fftf_phys(o)] = v[b][r];
         } else if (o >= a.ntaps - 1) {        // the first ntaps-1 items are the circular wrap-around
           const long i = item0 + (o - (a.ntaps - 1));
-          if (a.decim == 1) a.out[i] = v[b][r];
-          else if (i % a.decim == 0) a.out[i / a.decim] = v[b][r];
+          if (i < a.total_items && (a.decim == 1 || i % a.decim == 0)) {
+            float2* dst = a.out + (a.decim == 1 ? i : i / a.decim);
+            *dst = a.accumulate ? cadd(*dst, v[b][r]) : v[b][r];
+          }
         }
       }
     }
@@ -111,9 +118,11 @@ __global__ void __launch_bounds__(MAXT, 1) fft_filter_ols_kernel(const FftFiltAr
   extern __shared__ float2 fftf_smem[];
   float2* s = fftf_smem;
   FftFiltPass pa;
-  pa.H = a.H; pa.out = a.out; pa.n = a.n; pa.ntaps = a.ntaps; pa.decim = a.decim;
+  pa.H = a.H; pa.out = a.out; pa.n = a.n; pa.ntaps = a.ntaps; pa.decim = a.decim; pa.accumulate = a.accumulate;
+  pa.total_items = a.total_items;
   for (long b = blockIdx.x; b < a.nblk; b += gridDim.x) {
     const float2* gin = a.x + b * (long)a.nsamples;
+    pa.in_left = a.x_limit - b * (long)a.nsamples;
     const long item0 = b * (long)a.nsamples;
     int Ns = 1;
     // forward
@@ -135,35 +144,6 @@ __global__ void __launch_bounds__(MAXT, 1) fft_filter_ols_kernel(const FftFiltAr
       Ns *= a.radix[p];
     }
     __syncthreads();   // the next block's first pass writes the row this block's last pass has just read
-  }
-}
-
-// ---- long filters (fftsize beyond one CTA's shared memory): the same overlap-save on the batched FFT engine ---------
-// rows[b][i] = x[b * nsamples + i]
-__global__ void __launch_bounds__(256) fftf_pack_kernel(const float2* __restrict__ x, float2* __restrict__ rows, int n,
-                                                        int nsamples, long nblk) {
-  const long total = nblk * n;
-  for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long)gridDim.x * blockDim.x) {
-    const long b = id / n;
-    const int i = (int)(id - b * n);
-    rows[id] = __ldg(x + b * nsamples + i);
-  }
-}
-__global__ void __launch_bounds__(256) fftf_mul_kernel(float2* __restrict__ rows, const float2* __restrict__ H, int n,
-                                                       long nblk) {
-  const long total = nblk * n;
-  for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long)gridDim.x * blockDim.x)
-    rows[id] = cmul(rows[id], __ldg(H + (int)(id % n)));
-}
-// out item (item_base + b * nsamples + j) / decim = rows[b][ntaps - 1 + j] for the items the decimation keeps
-__global__ void __launch_bounds__(256) fftf_unpack_kernel(const float2* __restrict__ rows, float2* __restrict__ out, int n,
-                                                          int ntaps, int nsamples, int decim, long nblk, long item_base) {
-  const long total = nblk * nsamples;
-  for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long)gridDim.x * blockDim.x) {
-    const long b = id / nsamples;
-    const int j = (int)(id - b * nsamples);
-    const long i = item_base + id;
-    if (i % decim == 0) out[i / decim] = rows[b * n + ntaps - 1 + j];
   }
 }
 

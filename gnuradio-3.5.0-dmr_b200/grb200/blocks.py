@@ -356,7 +356,7 @@ class fft_filter_ccc(_Block):
         return self.decim
 
     def path(self):
-        """0 direct form, 1 fused overlap-save (one CTA per block), 2 overlap-save on the batched FFT engine."""
+        """0 direct form, 1 fused overlap-save (one CTA per block), 2 the same per 4096-tap partition (long filters)."""
         return int(self.L.grcuda_fft_filter_ccc_path(self.h))
 
     def set_path(self, path):

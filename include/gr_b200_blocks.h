@@ -16,6 +16,10 @@
  *     digital_make_clock_recovery_mm_ff                      gr-digital/include/digital_clock_recovery_mm_ff.h:37-40
  *     pager_make_slicer_fb, digital_make_binary_slicer_fb    gr-pager/lib/pager_slicer_fb.h, gr-digital/include/digital_binary_slicer_fb.h
  *     digital_make_correlate_access_code_bb                  gr-digital/include/digital_correlate_access_code_bb.h:37-38
+ *     digital_make_clock_recovery_mm_cc                      gr-digital/include/digital_clock_recovery_mm_cc.h:36-40
+ *     gr_make_framer_sink_1                                  general/gr_framer_sink_1.h:33-34
+ *     gr_make_map_bb, gr_make_unpack_k_bits_bb               general/gr_map_bb.h, gr_unpack_k_bits_bb.h
+ *     gr_make_stream_to_streams, gr_make_vector_to_streams   general/gr_stream_to_streams.h, gr_vector_to_streams.h
  *   }
  * The names live in namespace gr_b200 so that they can be linked next to the CPU blocks; a flowgraph
  * switches over with `using namespace gr_b200;` or per block.
@@ -32,6 +36,9 @@
 #include <gr_io_signature.h>
 #include <gr_sync_block.h>
 #include <gr_sync_decimator.h>
+#include <gr_sync_interpolator.h>
+#include <gr_msg_queue.h>
+#include <gr_message.h>
 #include <gr_complex.h>
 #define GR_B200_SPTR(T) boost::shared_ptr<T>
 #define GR_B200_INITIAL_SPTR(p) gnuradio::get_initial_sptr(p)
@@ -42,6 +49,7 @@
 #endif
 
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -494,6 +502,188 @@ class digital_correlate_access_code_bb : public gr_sync_block {
 };
 inline digital_correlate_access_code_bb_sptr digital_make_correlate_access_code_bb(const std::string& access_code, int threshold) {
   return GR_B200_INITIAL_SPTR(new digital_correlate_access_code_bb(access_code, threshold));
+}
+
+/* ---- digital_clock_recovery_mm_cc (gr-digital/lib/digital_clock_recovery_mm_cc.cc:36-218) -------------- */
+class digital_clock_recovery_mm_cc;
+typedef GR_B200_SPTR(digital_clock_recovery_mm_cc) digital_clock_recovery_mm_cc_sptr;
+digital_clock_recovery_mm_cc_sptr digital_make_clock_recovery_mm_cc(float omega, float gain_omega, float mu, float gain_mu,
+                                                                    float omega_relative_limit = 0.001);
+class digital_clock_recovery_mm_cc : public gr_block {
+  friend digital_clock_recovery_mm_cc_sptr digital_make_clock_recovery_mm_cc(float, float, float, float, float);
+  grcuda_mm_cc* d_plan;
+  float d_gain_mu, d_gain_omega;
+  digital_clock_recovery_mm_cc(float omega, float gain_omega, float mu, float gain_mu, float omega_relative_limit)
+      : gr_block("clock_recovery_mm_cc", gr_make_io_signature(1, 1, sizeof(gr_complex)),
+                 gr_make_io_signature(1, 2, sizeof(gr_complex))),   /* second output: float error signal (:55-56) */
+        d_plan(grcuda_clock_recovery_mm_cc_create(1, omega, gain_omega, mu, gain_mu, omega_relative_limit)),
+        d_gain_mu(gain_mu), d_gain_omega(gain_omega) {
+    if (!d_plan) throw_last_error("digital_clock_recovery_mm_cc");   /* std::out_of_range (:65-68) */
+    set_relative_rate(1.0 / omega);                                   /* :71 */
+    set_history(3);                                                   /* :72 */
+  }
+  float state(int which) const {
+    float mu = 0, omega = 0;
+    check_rc(grcuda_clock_recovery_mm_cc_get_state(d_plan, 0, &mu, &omega), "get_state");
+    return which == 0 ? mu : omega;
+  }
+ public:
+  ~digital_clock_recovery_mm_cc() { grcuda_clock_recovery_mm_cc_destroy(d_plan); }
+  void forecast(int noutput_items, gr_vector_int& ninput_items_required) {  /* :84-91 */
+    const int n = grcuda_clock_recovery_mm_cc_forecast(d_plan, noutput_items);
+    for (size_t i = 0; i < ninput_items_required.size(); i++) ninput_items_required[i] = n;
+  }
+  float mu() const { return state(0); }
+  float omega() const { return state(1); }
+  float gain_mu() const { return d_gain_mu; }
+  float gain_omega() const { return d_gain_omega; }
+  void set_verbose(bool) {}
+  void set_gain_mu(float g) { d_gain_mu = g; check_rc(grcuda_clock_recovery_mm_cc_set_gain_mu(d_plan, g), "set_gain_mu"); }
+  void set_gain_omega(float g) { d_gain_omega = g; check_rc(grcuda_clock_recovery_mm_cc_set_gain_omega(d_plan, g), "set_gain_omega"); }
+  void set_mu(float mu) { check_rc(grcuda_clock_recovery_mm_cc_set_mu(d_plan, mu), "set_mu"); }
+  void set_omega(float omega) { check_rc(grcuda_clock_recovery_mm_cc_set_omega(d_plan, omega), "set_omega"); }
+  int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                   gr_vector_void_star& output_items) {
+    int consumed = 0;
+    float* err = output_items.size() >= 2 ? (float*)output_items[1] : 0;   /* :131 */
+    int r = check_rc(grcuda_clock_recovery_mm_cc_work(d_plan, noutput_items, ninput_items[0], cin(input_items[0]),
+                                                      cout_(output_items[0]), err, &consumed),
+                     "general_work");
+    if (consumed > 0) consume_each(consumed);                        /* :207-214 */
+    return r;
+  }
+};
+inline digital_clock_recovery_mm_cc_sptr digital_make_clock_recovery_mm_cc(float omega, float gain_omega, float mu, float gain_mu,
+                                                                           float omega_relative_limit) {
+  return GR_B200_INITIAL_SPTR(new digital_clock_recovery_mm_cc(omega, gain_omega, mu, gain_mu, omega_relative_limit));
+}
+
+/* ---- gr_framer_sink_1 (general/gr_framer_sink_1.cc:75-196) ------------------------------------------------ */
+class gr_framer_sink_1;
+typedef GR_B200_SPTR(gr_framer_sink_1) gr_framer_sink_1_sptr;
+gr_framer_sink_1_sptr gr_make_framer_sink_1(gr_msg_queue_sptr target_queue);
+class gr_framer_sink_1 : public gr_sync_block {
+  friend gr_framer_sink_1_sptr gr_make_framer_sink_1(gr_msg_queue_sptr target_queue);
+  grcuda_framer* d_plan;
+  gr_msg_queue_sptr d_target_queue;
+  std::vector<grcuda_framer_msg> d_msgs;
+  std::vector<unsigned char> d_payload;
+  gr_framer_sink_1(gr_msg_queue_sptr target_queue)
+      : gr_sync_block("framer_sink_1", gr_make_io_signature(1, 1, sizeof(unsigned char)), gr_make_io_signature(0, 0, 0)),
+        d_plan(grcuda_framer_sink_1_create(1, 4096, 1 << 22)), d_target_queue(target_queue), d_msgs(4096), d_payload(1 << 22) {
+    if (!d_plan) throw_last_error("gr_framer_sink_1");
+  }
+ public:
+  ~gr_framer_sink_1() { grcuda_framer_sink_1_destroy(d_plan); }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star&) {
+    /* at most noutput_items / 32 packets can complete in one call: bound the chunk by the device queue */
+    int done = 0;
+    while (done < noutput_items) {
+      const int n = noutput_items - done < 4096 * 32 ? noutput_items - done : 4096 * 32;
+      check_rc(grcuda_framer_sink_1_work(d_plan, n, (const unsigned char*)input_items[0] + done), "work");
+      int dropped = 0;
+      const int k = check_rc(grcuda_framer_sink_1_read(d_plan, d_msgs.data(), (int)d_msgs.size(), d_payload.data(), d_payload.size(),
+                                                       &dropped), "read");
+      for (int i = 0; i < k; i++) {   /* gr_make_message(0, whitener_offset, 0, len) + insert_tail (:139-146, :170-178) */
+        gr_message_sptr msg = gr_make_message(0, d_msgs[i].whitener_offset, 0, d_msgs[i].length);
+        if (d_msgs[i].length > 0 && d_msgs[i].payload_offset >= 0)
+          memcpy(msg->msg(), d_payload.data() + d_msgs[i].payload_offset, d_msgs[i].length);
+        d_target_queue->insert_tail(msg);
+      }
+      if (dropped) fprintf(stderr, "gr_b200::gr_framer_sink_1: %d message(s) did not fit the device queue\n", dropped);
+      done += n;
+    }
+    return noutput_items;
+  }
+};
+inline gr_framer_sink_1_sptr gr_make_framer_sink_1(gr_msg_queue_sptr target_queue) {
+  return GR_B200_INITIAL_SPTR(new gr_framer_sink_1(target_queue));
+}
+
+/* ---- gr_map_bb (general/gr_map_bb.cc:35-61) / gr_unpack_k_bits_bb (general/gr_unpack_k_bits_bb.cc:38-70) ------ */
+class gr_map_bb;
+typedef GR_B200_SPTR(gr_map_bb) gr_map_bb_sptr;
+gr_map_bb_sptr gr_make_map_bb(const std::vector<int>& map);
+class gr_map_bb : public gr_sync_block {
+  friend gr_map_bb_sptr gr_make_map_bb(const std::vector<int>& map);
+  grcuda_map_bb* d_plan;
+  gr_map_bb(const std::vector<int>& map)
+      : gr_sync_block("map_bb", gr_make_io_signature(1, 1, sizeof(unsigned char)), gr_make_io_signature(1, 1, sizeof(unsigned char))),
+        d_plan(grcuda_map_bb_create(map.data(), (int)map.size())) {
+    if (!d_plan) throw_last_error("gr_map_bb");
+  }
+ public:
+  ~gr_map_bb() { grcuda_map_bb_destroy(d_plan); }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    return check_rc(grcuda_map_bb_work(d_plan, noutput_items, (const unsigned char*)input_items[0], (unsigned char*)output_items[0]), "work");
+  }
+};
+inline gr_map_bb_sptr gr_make_map_bb(const std::vector<int>& map) { return GR_B200_INITIAL_SPTR(new gr_map_bb(map)); }
+
+class gr_unpack_k_bits_bb;
+typedef GR_B200_SPTR(gr_unpack_k_bits_bb) gr_unpack_k_bits_bb_sptr;
+gr_unpack_k_bits_bb_sptr gr_make_unpack_k_bits_bb(unsigned k);
+class gr_unpack_k_bits_bb : public gr_sync_interpolator {
+  friend gr_unpack_k_bits_bb_sptr gr_make_unpack_k_bits_bb(unsigned k);
+  grcuda_unpack_k_bits* d_plan;
+  gr_unpack_k_bits_bb(unsigned k)
+      : gr_sync_interpolator("unpack_k_bits_bb", gr_make_io_signature(1, 1, sizeof(unsigned char)),
+                             gr_make_io_signature(1, 1, sizeof(unsigned char)), k ? k : 1),
+        d_plan(grcuda_unpack_k_bits_bb_create(k)) {
+    if (!d_plan) throw_last_error("gr_unpack_k_bits_bb");   /* std::out_of_range("interpolation must be > 0") (:44-45) */
+  }
+ public:
+  ~gr_unpack_k_bits_bb() { grcuda_unpack_k_bits_bb_destroy(d_plan); }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    check_rc(grcuda_unpack_k_bits_bb_work(d_plan, noutput_items, (const unsigned char*)input_items[0], (unsigned char*)output_items[0]), "work");
+    return noutput_items;
+  }
+};
+inline gr_unpack_k_bits_bb_sptr gr_make_unpack_k_bits_bb(unsigned k) { return GR_B200_INITIAL_SPTR(new gr_unpack_k_bits_bb(k)); }
+
+/* ---- gr_stream_to_streams / gr_vector_to_streams (general/gr_stream_to_streams.cc:37-66, gr_vector_to_streams.cc:37-70) */
+class gr_stream_to_streams;
+typedef GR_B200_SPTR(gr_stream_to_streams) gr_stream_to_streams_sptr;
+gr_stream_to_streams_sptr gr_make_stream_to_streams(size_t item_size, size_t nstreams);
+class gr_stream_to_streams : public gr_sync_decimator {
+  friend gr_stream_to_streams_sptr gr_make_stream_to_streams(size_t item_size, size_t nstreams);
+  grcuda_streams* d_plan;
+  gr_stream_to_streams(size_t item_size, size_t nstreams)
+      : gr_sync_decimator("stream_to_streams", gr_make_io_signature(1, 1, (int)item_size),
+                          gr_make_io_signature((int)nstreams, (int)nstreams, (int)item_size), (unsigned)nstreams),
+        d_plan(grcuda_stream_to_streams_create(item_size, nstreams)) {
+    if (!d_plan) throw_last_error("gr_stream_to_streams");
+  }
+ public:
+  ~gr_stream_to_streams() { grcuda_streams_destroy(d_plan); }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    return check_rc(grcuda_streams_work(d_plan, noutput_items, input_items[0], output_items.data()), "work");
+  }
+};
+inline gr_stream_to_streams_sptr gr_make_stream_to_streams(size_t item_size, size_t nstreams) {
+  return GR_B200_INITIAL_SPTR(new gr_stream_to_streams(item_size, nstreams));
+}
+
+class gr_vector_to_streams;
+typedef GR_B200_SPTR(gr_vector_to_streams) gr_vector_to_streams_sptr;
+gr_vector_to_streams_sptr gr_make_vector_to_streams(size_t item_size, size_t nstreams);
+class gr_vector_to_streams : public gr_sync_block {
+  friend gr_vector_to_streams_sptr gr_make_vector_to_streams(size_t item_size, size_t nstreams);
+  grcuda_streams* d_plan;
+  gr_vector_to_streams(size_t item_size, size_t nstreams)
+      : gr_sync_block("vector_to_streams", gr_make_io_signature(1, 1, (int)(nstreams * item_size)),
+                      gr_make_io_signature((int)nstreams, (int)nstreams, (int)item_size)),
+        d_plan(grcuda_vector_to_streams_create(item_size, nstreams)) {
+    if (!d_plan) throw_last_error("gr_vector_to_streams");
+  }
+ public:
+  ~gr_vector_to_streams() { grcuda_streams_destroy(d_plan); }
+  int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    return check_rc(grcuda_streams_work(d_plan, noutput_items, input_items[0], output_items.data()), "work");
+  }
+};
+inline gr_vector_to_streams_sptr gr_make_vector_to_streams(size_t item_size, size_t nstreams) {
+  return GR_B200_INITIAL_SPTR(new gr_vector_to_streams(item_size, nstreams));
 }
 
 }  // namespace gr_b200

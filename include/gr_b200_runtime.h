@@ -145,4 +145,63 @@ class gr_sync_decimator : public gr_sync_block {              /* runtime/gr_sync
   }
 };
 
+class gr_sync_interpolator : public gr_sync_block {           /* runtime/gr_sync_interpolator.cc:30-70 */
+  unsigned d_interpolation;
+ protected:
+  gr_sync_interpolator(const std::string& name, gr_io_signature_sptr in, gr_io_signature_sptr out, unsigned interpolation)
+      : gr_sync_block(name, in, out) {
+    set_interpolation(interpolation);
+  }
+ public:
+  unsigned interpolation() const { return d_interpolation; }
+  void set_interpolation(unsigned interpolation) {
+    d_interpolation = interpolation;
+    set_relative_rate(1.0 * interpolation);
+    set_output_multiple(interpolation);
+  }
+  void forecast(int noutput_items, gr_vector_int& ninput_items_required) {
+    for (size_t i = 0; i < ninput_items_required.size(); i++)
+      ninput_items_required[i] = noutput_items / interpolation() + history() - 1;
+  }
+  int general_work(int noutput_items, gr_vector_int&, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items) {
+    int r = work(noutput_items, input_items, output_items);
+    if (r > 0) consume_each(r / interpolation());
+    return r;
+  }
+};
+
+/* gr_message / gr_msg_queue as far as gr_framer_sink_1 uses them (runtime/gr_message.h:35-92, gr_msg_queue.h:34-88):
+ * gr_make_message(type, arg1, arg2, length), msg(), insert_tail(), delete_head_nowait(), count(). */
+class gr_message;
+typedef std::shared_ptr<gr_message> gr_message_sptr;
+class gr_message {
+  long d_type;
+  double d_arg1, d_arg2;
+  std::vector<unsigned char> d_buf;
+  friend gr_message_sptr gr_make_message(long type, double arg1, double arg2, size_t length);
+  gr_message(long type, double arg1, double arg2, size_t length) : d_type(type), d_arg1(arg1), d_arg2(arg2), d_buf(length) {}
+ public:
+  long type() const { return d_type; }
+  double arg1() const { return d_arg1; }
+  double arg2() const { return d_arg2; }
+  unsigned char* msg() { return d_buf.data(); }
+  size_t length() const { return d_buf.size(); }
+  std::string to_string() const { return std::string(d_buf.begin(), d_buf.end()); }
+};
+inline gr_message_sptr gr_make_message(long type, double arg1 = 0, double arg2 = 0, size_t length = 0) {
+  return gr_message_sptr(new gr_message(type, arg1, arg2, length));
+}
+class gr_msg_queue {
+  std::vector<gr_message_sptr> d_q;
+  size_t d_head;
+ public:
+  gr_msg_queue() : d_head(0) {}
+  void insert_tail(gr_message_sptr msg) { d_q.push_back(msg); }
+  gr_message_sptr delete_head_nowait() { return d_head < d_q.size() ? d_q[d_head++] : gr_message_sptr(); }
+  bool empty_p() const { return d_head >= d_q.size(); }
+  unsigned count() const { return (unsigned)(d_q.size() - d_head); }
+};
+typedef std::shared_ptr<gr_msg_queue> gr_msg_queue_sptr;
+inline gr_msg_queue_sptr gr_make_msg_queue(unsigned limit = 0) { (void)limit; return gr_msg_queue_sptr(new gr_msg_queue()); }
+
 #endif /* INCLUDED_GR_B200_RUNTIME_H */

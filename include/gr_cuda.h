@@ -305,7 +305,8 @@ int grcuda_pfb_decimator_ccf_work_device(grcuda_pfb_decim* h, long noutput_items
  * overlap-add tail), output_multiple = nsamples = fftsize - ntaps + 1, set_taps deferred to the next work()
  * which returns 0 and clears the carried state.  Device paths (path()): 0 = direct form (ntaps <= 32),
  * 1 = overlap-save with both FFTs and the product inside one CTA (fftsize <= 8192, i.e. up to 4096 taps),
- * 2 = overlap-save on the batched FFT engine (any length).  Within 1e-6 of the reference (bar 1e-4).
+ * 2 = the same kernel once per 4096-tap partition of a longer filter, accumulating (any length, cost linear in
+ * ntaps).  Within 5e-6 of the float64 convolution (bar 1e-4).
  * set_path pins one (-1 = automatic); like set_taps it takes effect at the next work(), which returns 0. */
 typedef struct grcuda_fft_filter grcuda_fft_filter;
 grcuda_fft_filter* grcuda_fft_filter_ccc_create(int decimation, const grcuda_complex* taps, int ntaps);

@@ -6,6 +6,7 @@
 //   block_harness run <block spec...> <in.bin> <out.bin> <max_noutput>
 //   block_harness errors      argument-error -> exception-type mapping (no GPU needed)
 //   block_harness contract    scheduler-visible contracts (needs a GPU)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -141,6 +142,52 @@ static int cmd_run(int argc, char** argv) {
   } else if (kind == "corr") {
     auto b = digital_make_correlate_access_code_bb(argv[3], atoi(argv[4]));
     out = run_block(*b, streams, max_noutput);
+  } else if (kind == "map") {
+    std::vector<float> m = floats(argv[3]);
+    auto b = gr_make_map_bb(std::vector<int>(m.begin(), m.end()));
+    out = run_block(*b, streams, max_noutput);
+  } else if (kind == "unpack") {
+    auto b = gr_make_unpack_k_bits_bb((unsigned)atoi(argv[3]));
+    out = run_block(*b, streams, max_noutput);
+  } else if (kind == "mmcc") {
+    auto b = digital_make_clock_recovery_mm_cc((float)atof(argv[3]), (float)atof(argv[4]), (float)atof(argv[5]), (float)atof(argv[6]),
+                                               (float)atof(argv[7]));
+    out = run_block(*b, streams, max_noutput);
+    fprintf(stderr, "mmcc final mu %.9g omega %.9g\n", b->mu(), b->omega());
+  } else if (kind == "framer") {
+    // a sink: the scheduler hands it whatever is there, max_noutput items at a time; the messages are what comes out
+    gr_msg_queue_sptr q = gr_make_msg_queue();
+    auto b = gr_make_framer_sink_1(q);
+    gr_vector_void_star none;
+    for (size_t pos = 0; pos < in.size(); pos += (size_t)max_noutput) {
+      const int n = (int)std::min<size_t>((size_t)max_noutput, in.size() - pos);
+      gr_vector_const_void_star iv(1, in.data() + pos);
+      if (b->work(n, iv, none) != n) return 3;
+    }
+    while (q->count()) {   // record: arg1 (1 byte), length (2 bytes, little endian), payload
+      gr_message_sptr m = q->delete_head_nowait();
+      const unsigned len = (unsigned)m->length();
+      out.push_back((char)(int)m->arg1());
+      out.push_back((char)(len & 255));
+      out.push_back((char)(len >> 8));
+      out.insert(out.end(), (const char*)m->msg(), (const char*)m->msg() + len);
+    }
+  } else if (kind == "s2s" || kind == "v2s") {
+    const size_t isz = (size_t)atoi(argv[3]), ns = (size_t)atoi(argv[4]);
+    const size_t n = in.size() / isz / ns;
+    std::vector<std::vector<char> > outs(ns, std::vector<char>(n * isz));
+    gr_vector_const_void_star iv(1);
+    gr_vector_void_star ov(ns);
+    for (size_t pos = 0; pos < n; pos += (size_t)max_noutput) {
+      const int k = (int)std::min<size_t>((size_t)max_noutput, n - pos);
+      iv[0] = in.data() + pos * ns * isz;
+      for (size_t j = 0; j < ns; j++) ov[j] = outs[j].data() + pos * isz;
+      int r;
+      if (kind == "s2s") { auto b = gr_make_stream_to_streams(isz, ns); r = b->work(k, iv, ov); }
+      else { auto b = gr_make_vector_to_streams(isz, ns); r = b->work(k, iv, ov); }
+      if (r != k) return 3;
+    }
+    for (size_t j = 0; j < ns; j++) out.insert(out.end(), outs[j].begin(), outs[j].end());   // stream after stream
   } else {
     fprintf(stderr, "unknown block %s\n", kind.c_str());
     return 2;
@@ -166,6 +213,9 @@ static int cmd_errors() {
   printf("corr_code_too_long %s\n", what_throws([&] { digital_make_correlate_access_code_bb(std::string(65, '1'), 0); }));  // out_of_range
   printf("fft_size_zero %s\n", what_throws([&] { gr_make_fft_vcc(0, true, std::vector<float>(), false); }));   // out_of_range (gri_fft.cc:104-105)
   printf("io_signature %s\n", what_throws([&] { gr_make_io_signature(2, 1, 4); }));
+  printf("unpack_k_zero %s\n", what_throws([&] { gr_make_unpack_k_bits_bb(0); }));                           // out_of_range (:44-45)
+  printf("mmcc_omega_zero %s\n", what_throws([&] { digital_make_clock_recovery_mm_cc(0.f, 0.1f, 0.5f, 0.1f, 0.001f); }));  // out_of_range (:65-66)
+  printf("mmcc_negative_gain %s\n", what_throws([&] { digital_make_clock_recovery_mm_cc(2.f, 0.1f, 0.5f, -0.1f, 0.001f); }));
   return 0;
 }
 

@@ -46,6 +46,9 @@ def test_header_compiles_and_maps_argument_errors(harness):
         "corr_code_too_long": "out_of_range",       # digital_correlate_access_code_bb.cc:54-57
         "fft_size_zero": "out_of_range",            # gri_fft.cc:104-105
         "io_signature": "invalid_argument",
+        "unpack_k_zero": "out_of_range",            # gr_unpack_k_bits_bb.cc:44-45
+        "mmcc_omega_zero": "out_of_range",          # digital_clock_recovery_mm_cc.cc:65-66
+        "mmcc_negative_gain": "out_of_range",       # :67-68
     }
 
 
@@ -204,3 +207,39 @@ def test_demod_tail_blocks_bit_exact(harness, tmp_path, orc):
     c = run(harness, tmp_path, ["corr", code, 1], bits, np.uint8, max_noutput=640)
     wc = orc.corr_work(orc.corr_new(code, 1), bits)
     assert np.array_equal(c, wc) and np.any(c & 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_next_blocks_through_the_cpp_mirror(harness, tmp_path, orc, golden_next):
+    """gr_map_bb, gr_unpack_k_bits_bb, gr_stream_to_streams / gr_vector_to_streams, digital_clock_recovery_mm_cc and
+    gr_framer_sink_1 (into a gr_msg_queue) as C++ blocks under the scheduler loop, against the oracle / fixtures."""
+    rng = np.random.default_rng(12)
+    x = rng.integers(0, 4, 5001).astype(np.uint8)
+    m = np.array([0, 1, 3, 2], np.float32)
+    y = run(harness, tmp_path, ["map", m], x, np.uint8, max_noutput=777)
+    assert np.array_equal(y, orc.map_bb([0, 1, 3, 2], x))
+    u = run(harness, tmp_path, ["unpack", 2], y, np.uint8, max_noutput=1001)       # the scheduler rounds to multiples of k
+    assert np.array_equal(u, orc.unpack_k_bits_bb(2, y))
+    z = (rng.standard_normal(160 * 50) + 1j * rng.standard_normal(160 * 50)).astype(np.complex64)
+    for kind in ("s2s", "v2s"):
+        o = run(harness, tmp_path, [kind, 8, 160], z, np.complex64, max_noutput=17)
+        assert np.array_equal(o.reshape(160, 50), z.reshape(50, 160).T)
+    fx = golden_next
+    args = [repr(float(v)) for v in fx["mmcc_args"]]
+    s = run(harness, tmp_path, ["mmcc"] + args, fx["mmcc_x"], np.complex64, max_noutput=300)
+    # history 3: the runtime presents two zero items in front of the stream (gr_buffer.cc:201-214)
+    st = orc.mmcc_new(*[float(v) for v in fx["mmcc_args"]])
+    want, _, _ = orc.mmcc_work(st, np.concatenate([np.zeros(2, np.complex64), fx["mmcc_x"]]))
+    assert len(s) >= len(want) - 8 and np.array_equal(s.view(np.uint32), want[:len(s)].view(np.uint32))
+    rec = run(harness, tmp_path, ["framer"], fx["framer_stream"], np.uint8, max_noutput=1500)
+    got, pos = [], 0
+    while pos < len(rec):
+        n = int(rec[pos + 1]) | (int(rec[pos + 2]) << 8)
+        got.append((int(rec[pos]), bytes(rec[pos + 3: pos + 3 + n])))
+        pos += 3 + n
+    want, p = [], 0
+    for off, n in zip(fx["framer_offsets"], fx["framer_lengths"]):
+        want.append((int(off), bytes(fx["framer_payloads"][p:p + n])))
+        p += n
+    assert got == want

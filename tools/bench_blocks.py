@@ -123,6 +123,85 @@ def main():
         byt = 8.0 * nrow * Md + 8.0 * nrow
         out[tag] = {"ms": ms, "MSps_in": nrow * Md / ms / 1e3, "alg_GBps": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / peak}
         del xr, yo
+    # cfg3: 2 MS/s -> 160 x 12.5 kHz channels (16 taps/branch) + batched DMR demod + sync search, 10 s of signal per launch
+    from grb200 import chain as _chain
+    M3, T3, rows3 = 160, 16, 125000
+    t3 = firdes.low_pass_2(1.0, M3 * 12500.0, 5500.0, 1500.0, 60.0, firdes.WIN_BLACKMAN_hARRIS)
+    c3 = len(t3) // 2
+    t3 = (np.asarray(t3[c3 - M3 * T3 // 2: c3 - M3 * T3 // 2 + M3 * T3]) * M3).astype(np.float32)
+    ch3 = _chain.DmrChain(_chain.DmrChainConfig(M3, t3, max_rows_per_block=rows3))
+    x3 = torch.view_as_complex(torch.randn((ch3.history_rows() + rows3, M3, 2), generator=g, device=dev))
+    s3 = torch.cuda.current_stream().cuda_stream
+
+    def run3():
+        ch3.process_device(x3, rows3, s3)
+        ch3.join(s3)
+    ms = timeit(run3, 5, flush)
+    out["cfg3_pfb160_dmr_chain_20M"] = {"ms": ms, "MSps_in": rows3 * M3 / ms / 1e3, "seconds_of_signal_per_second": 10.0 / (ms * 1e-3),
+                                        "alg_GBps": 49.9 * rows3 * M3 / ms / 1e6, "frac_hbm": 49.9 * rows3 * M3 / ms / 1e6 / peak}
+    del x3, ch3
+    # ---- blocks of SURVEY 8f rank 4 + the stand-alone a12 / a14 forms ---------------------------------------------------
+    # fft_filter_ccc: 1025 and 4096 complex taps on 16 M samples (fused overlap-save), 20 000 taps (FFT engine)
+    for nt, nblk_target, tag in ((129, 16_000_000, "fft_filter_ccc_129taps"), (1025, 16_000_000, "fft_filter_ccc_1025taps"),
+                                 (4096, 16_000_000, "fft_filter_ccc_4096taps"), (20000, 16_000_000, "fft_filter_ccc_20000taps")):
+        rngt = np.random.default_rng(nt)
+        ct = ((rngt.standard_normal(nt) + 1j * rngt.standard_normal(nt)) / np.sqrt(nt)).astype(np.complex64)
+        ff = B.fft_filter_ccc(1, ct)
+        ns = ff.output_multiple()
+        n = nblk_target // ns * ns
+        xin = torch.view_as_complex(torch.randn((n, 2), generator=g, device=dev))
+        yo = torch.empty(n, dtype=torch.complex64, device=dev)
+        ms = timeit(lambda: ff.work_device(n, xin, yo), 5, flush)
+        out[tag] = {"ms": ms, "path": ff.path(), "MSps_in": n / ms / 1e3, "alg_GBps": 16.0 * n / ms / 1e6, "frac_hbm": 16.0 * n / ms / 1e6 / peak,
+                    "direct_form_GMACs_equiv": n * nt / ms / 1e6}
+        del xin, yo
+    # clock_recovery_mm_cc batched: 8000 channels x 12 500 rows (a cfg5 block of complex baseband), 2.604 samples/symbol
+    rows, M = 12500, 8000
+    xin = torch.view_as_complex(torch.randn((rows, M, 2), generator=g, device=dev))
+    mm = B.clock_recovery_mm_cc(2.6041667, 0.25 * 0.175 * 0.175, 0.5, 0.175, 0.005, nchan=M)
+    mo = torch.empty((6000, M), dtype=torch.complex64, device=dev)
+    cnt = torch.zeros(M, dtype=torch.int32, device=dev)
+    # simple timing: one launch over the whole block from a fresh state each time
+    def run_mmcc_fresh():
+        blk = run_mmcc_fresh.blk
+        blk.work_device(rows, run_mmcc_fresh.base, xin, mo, None, 6000, cnt)
+        run_mmcc_fresh.base += rows - 24
+    run_mmcc_fresh.blk = mm
+    run_mmcc_fresh.base = 0
+    ms = timeit(run_mmcc_fresh, 5, flush)
+    nsym = float(cnt.float().mean().item())
+    out["clock_recovery_mm_cc_8000ch"] = {"ms": ms, "symbols_per_channel": nsym, "MSps_in": rows * M / ms / 1e3,
+                                          "alg_GBps": (8.0 * rows * M + 8.0 * nsym * M) / ms / 1e6,
+                                          "frac_hbm": (8.0 * rows * M + 8.0 * nsym * M) / ms / 1e6 / peak,
+                                          "cycles_per_symbol_at_1965MHz": ms * 1e-3 * 1965e6 / max(nsym, 1)}
+    del xin, mo
+    # framer_sink_1 batched behind the correlator's bytes: 8000 channels x 9600 bits, a flag every ~600 bits
+    nbits = 9600
+    by = (torch.rand((nbits, M), generator=g, device=dev) < 0.5).to(torch.uint8)
+    by |= ((torch.rand((nbits, M), generator=g, device=dev) < 1.0 / 600).to(torch.uint8) << 1)
+    fr = B.framer_sink_1(M, max_msgs=1 << 18, payload_capacity=1 << 26)
+    ms = timeit(lambda: fr.work_device(nbits, by, M, 1), 5, flush)
+    nmsg = len(fr.messages())
+    out["framer_sink_1_8000ch"] = {"ms": ms, "bits": nbits * M, "messages_total": nmsg, "alg_GBps": 1.0 * nbits * M / ms / 1e6,
+                                   "frac_hbm": 1.0 * nbits * M / ms / 1e6 / peak}
+    # map_bb / unpack_k_bits_bb / stream_to_streams on 256 M items
+    nb = 1 << 28
+    xb = torch.randint(0, 4, (nb,), dtype=torch.uint8, device=dev)
+    yb = torch.empty(nb, dtype=torch.uint8, device=dev)
+    mp = B.map_bb([0, 1, 3, 2])
+    ms = timeit(lambda: mp.work_device(nb, xb, yb), 5, flush)
+    out["map_bb_256M"] = {"ms": ms, "alg_GBps": 2.0 * nb / ms / 1e6, "frac_hbm": 2.0 * nb / ms / 1e6 / peak}
+    up = B.unpack_k_bits_bb(2)
+    ms = timeit(lambda: up.work_device(nb, xb, yb), 5, flush)
+    out["unpack_k_bits_bb_k2_256M_out"] = {"ms": ms, "alg_GBps": 1.5 * nb / ms / 1e6, "frac_hbm": 1.5 * nb / ms / 1e6 / peak}
+    del xb, yb
+    rows, M = 12500, 8000
+    xin = torch.view_as_complex(torch.randn((rows, M, 2), generator=g, device=dev))
+    yo = torch.empty((M, rows), dtype=torch.complex64, device=dev)
+    st = B.stream_to_streams(8, M)
+    ms = timeit(lambda: st.work_device(rows, xin, yo), 5, flush)
+    out["stream_to_streams_8000x12500_c64"] = {"ms": ms, "alg_GBps": 16.0 * rows * M / ms / 1e6, "frac_hbm": 16.0 * rows * M / ms / 1e6 / peak}
+    del xin, yo
     # raw copy rates of the box (pinned), 800 MB like one bench block
     h = torch.empty(100_000_000, dtype=torch.complex64, pin_memory=True)
     dd = torch.empty(100_000_000, dtype=torch.complex64, device=dev)
