@@ -1,0 +1,2 @@
+#pragma once
+#include "_std_thread.hpp"

@@ -243,3 +243,36 @@ def test_next_blocks_through_the_cpp_mirror(harness, tmp_path, orc, golden_next)
         want.append((int(off), bytes(fx["framer_payloads"][p:p + n])))
         p += n
     assert got == want
+
+
+def test_header_compiles_against_the_reference_runtime(tmp_path):
+    """-DGR_B200_USE_GNURADIO_RUNTIME: every block derives from the reference's REAL gr_block / gr_sync_block /
+    gr_sync_decimator / gr_sync_interpolator and uses its real gr_msg_queue / gr_message, compiled from the headers where
+    they lie under /root/reference (Boost and UHD names come from tests/cpp/gr_shim: they are absent from this image).
+    A signature that did not match the base class's virtual would hide it: -Werror=overloaded-virtual."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("/root/reference is not mounted on this box")
+    core = os.path.join(ref, "gnuradio-core", "src", "lib")
+    src = tmp_path / "real_runtime.cc"
+    src.write_text("""#define GR_B200_USE_GNURADIO_RUNTIME
+#include "gr_b200_blocks.h"
+using namespace gr_b200;
+// every factory is odr-used, so every constructor and member function body is compiled
+void* factories[] = {(void*)&gr_make_fir_filter_ccf, (void*)&gr_make_fir_filter_fff, (void*)&gr_make_freq_xlating_fir_filter_ccf,
+  (void*)&gr_make_pfb_channelizer_ccf, (void*)&gr_make_fft_filter_ccc, (void*)&gr_make_pfb_decimator_ccf,
+  (void*)&gr_make_pfb_arb_resampler_ccf, (void*)&gr_make_fft_vcc, (void*)&gr_make_quadrature_demod_cf,
+  (void*)&digital_make_clock_recovery_mm_ff, (void*)&pager_make_slicer_fb, (void*)&digital_make_binary_slicer_fb,
+  (void*)&digital_make_correlate_access_code_bb, (void*)&digital_make_clock_recovery_mm_cc, (void*)&gr_make_framer_sink_1,
+  (void*)&gr_make_map_bb, (void*)&gr_make_unpack_k_bits_bb, (void*)&gr_make_stream_to_streams, (void*)&gr_make_vector_to_streams};
+gr_block* as_block(gr_pfb_channelizer_ccf* b) { return b; }   // really a gr_block of the reference
+gr_sync_block* as_sync(gr_framer_sink_1* b) { return b; }
+gr_sync_interpolator* as_interp(gr_unpack_k_bits_bb* b) { return b; }
+int main() { return 0; }
+""")
+    cmd = ["g++", "-std=c++17", "-c", "-Wall", "-Werror=overloaded-virtual", "-w", "-Werror=overloaded-virtual",
+           "-I" + os.path.join(ROOT, "tests", "cpp", "gr_shim"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(core, "runtime"), "-I" + os.path.join(core, "general"),
+           "-I" + os.path.join(ref, "gruel", "src", "include"), str(src), "-o", str(tmp_path / "real_runtime.o")]
+    r = subprocess.run(cmd, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr[-3000:]
