@@ -36,6 +36,10 @@ struct grcuda_dmr_chain {
   int T = 0, nrrc = 0, max_rows = 0, max_sym = 0, max_hits = 0, keep_bytes = 0;
   int YH = 1;          // history rows in front of Y
   bool fused = false;  // discriminator + matched filter in one kernel (kernel_demod_front.cuh)
+  bool fft_demod_store_y = false;  // ... and the kernel also stores the transform it computed (parity tests)
+  bool fft_demod = false;  // discriminator inside the channelizer's FFT kernel (kernel_fft_demod.cuh): Y never reaches HBM
+  DevBuf Dd, yl[2];        // that mode's D rows [YH + R][M] (first YH rows carried) and the last Y row of the previous / this block
+  int yl_cur = 0;
   grcuda_pfb* pfb = nullptr;
   grcuda_quad* quad = nullptr;
   grcuda_fir_fff* rrc = nullptr;
@@ -180,6 +184,32 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
 }
 
 void grcuda_dmr_chain_destroy(grcuda_dmr_chain* h) { delete h; }
+// 0: the channelizer output is not kept (result_get's d_channels is NULL): the discriminator runs inside the
+// channelizer's FFT kernel, 16 B per sample less HBM traffic.  Same symbols, same sync hits, bit for bit.
+int grcuda_dmr_chain_set_keep_channels(grcuda_dmr_chain* h, int on) {
+  if (h->front_rows > 0) return set_error(GRCUDA_EINVAL, "dmr_chain: set_keep_channels between process_front and process_tail");
+  if (on == 1) { h->fft_demod = false; h->fft_demod_store_y = false; return GRCUDA_OK; }
+  if (!h->fused || !pfb_demod_supported(h->pfb))
+    return set_error(GRCUDA_EUNSUPPORTED, "dmr_chain: no fused FFT + discriminator kernel for this channel count / summation order");
+  const size_t M = h->M;
+  GRB_CUDA(cudaDeviceSynchronize());
+  int rc;
+  if ((rc = h->Dd.reserve(((size_t)h->YH + h->max_rows) * M * sizeof(float))) || (rc = h->yl[0].reserve(M * sizeof(float2))) ||
+      (rc = h->yl[1].reserve(M * sizeof(float2))))
+    return rc;
+  if (!h->fft_demod) {
+    // continue the stream where the two-kernel path left it: D history = discriminator of the carried Y rows
+    // (only a fresh chain / after seek() is exact without this: the carried Y rows are zero then)
+    GRB_CUDA(cudaMemset(h->Dd.p, 0, (size_t)h->YH * M * sizeof(float)));
+    GRB_CUDA(cudaMemset(h->yl[0].p, 0, M * sizeof(float2)));
+    GRB_CUDA(cudaMemset(h->yl[1].p, 0, M * sizeof(float2)));
+    GRB_CUDA(cudaDeviceSynchronize());
+  }
+  h->fft_demod = true;
+  h->fft_demod_store_y = on == 2;
+  return GRCUDA_OK;
+}
+int grcuda_dmr_chain_keeps_channels(grcuda_dmr_chain* h) { return h->fft_demod ? (h->fft_demod_store_y ? 2 : 0) : 1; }
 int grcuda_dmr_chain_history_rows(grcuda_dmr_chain* h) { return h->T; }
 
 int grcuda_dmr_chain_min_rows(grcuda_dmr_chain* h) { return std::max(std::max(KEEP, h->nrrc - 1), h->YH); }
@@ -194,6 +224,11 @@ int grcuda_dmr_chain_seek(grcuda_dmr_chain* h, long long abs_row) {
   GRB_CUDA(cudaDeviceSynchronize());
   GRB_CUDA(cudaMemset(h->Yb.p, 0, (size_t)h->YH * M * sizeof(float2)));
   if (!h->fused) GRB_CUDA(cudaMemset(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4));
+  if (h->Dd.p) {
+    GRB_CUDA(cudaMemset(h->Dd.p, 0, (size_t)h->YH * M * sizeof(float)));
+    GRB_CUDA(cudaMemset(h->yl[0].p, 0, M * sizeof(float2)));
+    GRB_CUDA(cudaMemset(h->yl[1].p, 0, M * sizeof(float2)));
+  }
   h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
   return GRCUDA_OK;
@@ -204,6 +239,11 @@ int grcuda_dmr_chain_seek_async(grcuda_dmr_chain* h, long long abs_row, void* st
   const size_t M = h->M;
   GRB_CUDA(cudaMemsetAsync(h->Yb.p, 0, (size_t)h->YH * M * sizeof(float2), s));
   if (!h->fused) GRB_CUDA(cudaMemsetAsync(h->D.p, 0, (size_t)(h->nrrc - 1) * M * sizeof(float) + 4, s));
+  if (h->Dd.p) {
+    GRB_CUDA(cudaMemsetAsync(h->Dd.p, 0, (size_t)h->YH * M * sizeof(float), s));
+    GRB_CUDA(cudaMemsetAsync(h->yl[0].p, 0, M * sizeof(float2), s));
+    GRB_CUDA(cudaMemsetAsync(h->yl[1].p, 0, M * sizeof(float2), s));
+  }
   h->prev_rows = 0;  // the next block starts from a zero F carry
   h->abs_row = abs_row;
   return GRCUDA_OK;
@@ -250,7 +290,7 @@ int grcuda_dmr_chain_import_state(grcuda_dmr_chain* h, const void* d_state, void
 
 // front stage: channelizer -> discriminator -> matched filter.  Finite-memory stages: a time shard can run this on
 // its block + halo without waiting for anybody.  One stream, one Y buffer, history carried in place.
-static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, cudaStream_t sA) {
+static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, cudaStream_t sA, bool coresident = false) {
   if (nrows < grcuda_dmr_chain_min_rows(h) || nrows > h->max_rows)
     return set_error(GRCUDA_EINVAL, "dmr_chain: nrows %d outside [%d, %d]", nrows, grcuda_dmr_chain_min_rows(h), h->max_rows);
   if (h->front_rows > 0) return set_error(GRCUDA_EINVAL, "dmr_chain: process_front twice without process_tail");
@@ -280,6 +320,29 @@ static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows
   else
     GRB_CUDA(cudaMemsetAsync(F, 0, (size_t)KEEP * M * sizeof(float), sB));
   h->prof.end(sB, 0);
+  if (h->fft_demod) {
+    // 1+2. channelizer with the discriminator in the last FFT pass: rows -> D rows YH..YH+R (4 B/sample); the
+    //      channelizer output stays in registers.  3. matched filter from D.
+    float* Dd = h->Dd.as<float>();
+    int nt = 0;
+    fir_fff_reversed_taps(h->rrc, &nt, nullptr);
+    if ((rc = pfb_work_device_demod(h->pfb, R, (const float2*)d_in, Dd + YH * M, quad_gain(h->quad), h->yl[h->yl_cur].as<float2>(),
+                                    h->yl[h->yl_cur ^ 1].as<float2>(), coresident, sA, h->fft_demod_store_y ? Y + YH * M : nullptr)))
+      return rc;
+    h->yl_cur ^= 1;
+    h->prof.begin(3, sB);
+    if ((rc = demod_front_launch(nullptr, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad),
+                                 fir_fff_front_taps(h->rrc), nt, sB, Dd)))
+      return rc;
+    h->prof.end(sB);
+    h->prof.begin(6, sB);
+    GRB_CUDA(cudaMemcpyAsync(Dd, Dd + (size_t)R * M, YH * M * sizeof(float), cudaMemcpyDeviceToDevice, sB));
+    h->prof.end(sB, 0);
+    GRB_CUDA(cudaEventRecord(h->ev_front[cur], sB));
+    h->fcur = cur;
+    h->front_rows = nrows;
+    return GRCUDA_OK;
+  }
   // 1. channelizer: [T + R][M] -> Y rows YH..YH+R
   if ((rc = grcuda_pfb_channelizer_ccf_work_device(h->pfb, R, d_in, (grcuda_complex*)(Y + YH * M), sA))) return rc;
   if (h->fused) {
@@ -424,7 +487,7 @@ size_t grcuda_dmr_chain_corr_state_bytes(grcuda_dmr_chain* h) { return corr_stat
 
 int grcuda_dmr_chain_process_device(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows, void* stream_) {
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : h->stream;
-  int rc = front_impl(h, d_in, nrows, s);
+  int rc = front_impl(h, d_in, nrows, s, h->pipeline);   // (pipeline: kernels sized to co-reside with the previous tail)
   if (rc) return rc;
   // the tail goes to the chain's own stream: it overlaps the front of the next block
   h->under_front = h->pipeline;
@@ -528,7 +591,7 @@ int grcuda_dmr_chain_process_host(grcuda_dmr_chain* h, const grcuda_complex* in,
 }
 
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r) {
-  r->d_channels = (const grcuda_complex*)(h->Yb.as<float2>() + (size_t)h->YH * h->M);
+  r->d_channels = (h->fft_demod && !h->fft_demod_store_y) ? nullptr : (const grcuda_complex*)(h->Yb.as<float2>() + (size_t)h->YH * h->M);
   r->d_soft = h->soft.as<float>();
   r->d_symbols = h->sym.as<unsigned char>();
   r->d_sym_counts = h->counts.as<int>();

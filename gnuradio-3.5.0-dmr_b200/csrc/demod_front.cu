@@ -35,15 +35,16 @@ std::vector<float> demod_front_tap_table(const float* rt, int ntaps) {
 
 // y: [hist + nrows][M] complex with hist = demod_front_history(ntaps); d_tp = device copy of
 // demod_front_tap_table().
+// dsrc != nullptr: [hist + nrows][M] floats, the discriminator output made elsewhere (row numbering as y); y unused.
 int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
-                       cudaStream_t s) {
+                       cudaStream_t s, const float* dsrc) {
   if (ntaps < 1 || ntaps > demod_front_max_taps() || !d_tp) return set_error(GRCUDA_EUNSUPPORTED, "demod_front: %d taps", ntaps);
   if (nrows <= 0) return GRCUDA_OK;
   DeviceTables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
   DemodFrontArgs a;
-  a.y = y; a.f = f; a.abs_row0 = abs_row0; a.nrows = nrows; a.M = M; a.hist = demod_front_history(ntaps);
+  a.dsrc = dsrc; a.y = y; a.f = f; a.abs_row0 = abs_row0; a.nrows = nrows; a.M = M; a.hist = demod_front_history(ntaps);
   a.gain = gain; a.one = 1.0f; a.atan_table = tabs.atan; a.ntaps = ntaps; a.tp = d_tp;
   const int n1 = ntaps - 1, rho = n1 & 3;
   a.q = n1 >> 2;

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "fft_engine.cuh"
+#include "kernel_fft_demod.cuh"
 
 namespace grb {
 
@@ -236,6 +237,54 @@ int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, con
       p->kernel<<<grid, p->threads, p->smem, stream>>>(a);
     }
   }
+  GRB_LAUNCH_CHECK();
+  return GRCUDA_OK;
+}
+
+typedef void (*fft_demod_kernel_t)(const FftDemodArgs);
+static fft_demod_kernel_t demod_kernel_for(FftPlan* p, bool coresident) {
+  if (p->kind != 0 || p->dir != 1 || p->npass != 3 || p->rows_per_cta != 1 || (p->n & 1)) return nullptr;
+  // ONE build per length, whatever the caller's co-residency wish: ptxas decides which multiply-adds of the butterflies
+  // become FMAs, so two register caps are two (last-bit) different transforms, and a time shard must reproduce the
+  // single chain bit for bit.  128 registers co-reside with the clock-recovery kernel of the previous block.
+  (void)coresident;
+  if (p->radix[0] == 20 && p->radix[1] == 20 && p->radix[2] == 20) {
+    static const bool wide = getenv("GRCUDA_FFT_DEMOD_WIDE") != nullptr;   // lab switch (tools/): the 152-register build
+    return wide ? fft_demod_kernel<1, 20, 20, 20, 152> : fft_demod_kernel<1, 20, 20, 20, 128>;
+  }
+  if (p->radix[0] == 16 && p->radix[1] == 16 && p->radix[2] == 16) return fft_demod_kernel<1, 16, 16, 16, 152>;
+  return nullptr;
+}
+bool fft_plan_demod_supported(FftPlan* p) { return demod_kernel_for(p, false) != nullptr && p->d_counters != nullptr; }
+
+int fft_plan_exec_demod(FftPlan* p, const float2* d_in, float* d_d, long nrows, float gain, const float* d_atan_table,
+                        const float2* d_prev_y, float2* d_last_y, bool coresident, cudaStream_t stream, float2* d_y_out) {
+  fft_demod_kernel_t k = demod_kernel_for(p, coresident);
+  if (!k || ((uintptr_t)d_in & 15)) return set_error(GRCUDA_EUNSUPPORTED, "fft: no fused discriminator kernel for n = %d", p->n);
+  if (nrows <= 0) return GRCUDA_OK;
+  FftDemodArgs A;
+  memset(&A, 0, sizeof A);
+  FftArgs& a = A.f;
+  a.in = d_in; a.nrows = nrows;
+  for (int q = 0; q < FFT_MAX_PASSES; q++) { a.tw[q] = p->tw[q]; a.radix[q] = p->radix[q]; }
+  a.n = p->n; a.npass = p->npass;
+  a.rows_per_cta = 1; a.threads_per_row = p->threads_per_row;
+  a.row_stride = p->row_stride; a.pad_div = p->pad_div;
+  A.d = d_d; A.y_out = d_y_out; A.prev_y = d_prev_y; A.last_y = d_last_y; A.atan_table = d_atan_table; A.gain = gain;
+  // chunk: consecutive rows per claim; every chunk but the first re-transforms one row (1 / chunk of extra work), and
+  // there should be several chunks per CTA for the claims to balance
+  int chunk = 16;
+  if (const char* e = getenv("GRCUDA_FFT_DEMOD_CHUNK")) chunk = std::max(1, atoi(e));
+  A.chunk = chunk;
+  A.nchunks = (int)((nrows + chunk - 1) / chunk);
+  const size_t smem = (((size_t)p->row_stride * sizeof(float2)) + 127) / 128 * 128 + (size_t)p->n * sizeof(float2) + 16 + 260 * sizeof(float);
+  GRB_CUDA(raise_dynamic_smem((const void*)k, smem));
+  const int grid = std::min(A.nchunks, sm_count());
+  if (p->d_counters) {
+    a.counter = p->d_counters + (p->counter_turn++ % FftPlan::kCounters);
+    if (cudaMemsetAsync(a.counter, 0, sizeof(int), stream) != cudaSuccess) { cudaGetLastError(); a.counter = nullptr; }
+  }
+  k<<<grid, p->threads, smem, stream>>>(A);
   GRB_LAUNCH_CHECK();
   return GRCUDA_OK;
 }

@@ -18,5 +18,11 @@ void fft_plan_destroy(FftPlan* p);
 int fft_plan_exec(FftPlan* p, const float2* d_in, float2* d_out, long nrows, const float* d_window, int in_rot,
                   int out_rot, cudaStream_t stream);
 const char* fft_plan_describe(FftPlan* p);
+// The backward transform with gr_quadrature_demod_cf fused into its last pass (kernel_fft_demod.cuh): rows in,
+// discriminator rows (float) out; the transform itself is never stored.  Exists for the three-pass plans whose last
+// pass gives every thread the same channels in every row (8000 = 20^3, 4096 = 16^3).
+bool fft_plan_demod_supported(FftPlan* p);
+int fft_plan_exec_demod(FftPlan* p, const float2* d_in, float* d_d, long nrows, float gain, const float* d_atan_table,
+                        const float2* d_prev_y, float2* d_last_y, bool coresident, cudaStream_t stream, float2* d_y_out = nullptr);
 
 }  // namespace grb

@@ -510,7 +510,10 @@ struct grcuda_pfb : PlanBase {
   }
 
   // rows in: [T + nin][M]; out: [nout][M].  nout output vectors; os == 1 -> nin == nout.
-  int run(const float2* d_rows_in, float2* d_out, long nout, cudaStream_t s) {
+  // demod != nullptr: the FFT kernel applies gr_quadrature_demod_cf and writes D rows (float) instead of the
+  // channelizer output (kernel_fft_demod.cuh); one pass over the whole call (no row chunking).
+  struct DemodOut { float* d; float gain; const float* atan; const float2* prev_y; float2* last_y; bool coresident; float2* y_out; };
+  int run(const float2* d_rows_in, float2* d_out, long nout, cudaStream_t s, const DemodOut* demod = nullptr) {
     int rc0 = upload_if_dirty();
     if (rc0) return rc0;
     if (nout <= 0) return GRCUDA_OK;
@@ -530,7 +533,7 @@ struct grcuda_pfb : PlanBase {
       if (const char* e = getenv("GRCUDA_PFB_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e));
       crow = std::max<long>(1, (long)(mb << 20) / (long)(M * sizeof(float2)));
     }
-    if (!fast) crow = nout;  // the oversampled path indexes rows through the output number
+    if (!fast || demod) crow = nout;  // the oversampled path indexes rows through the output number
     crow = std::min(crow, nout);
     int rc = d_u.reserve((size_t)crow * M * sizeof(float2));
     if (rc) return rc;
@@ -579,7 +582,10 @@ struct grcuda_pfb : PlanBase {
       GRB_LAUNCH_CHECK();
       prof.end(s);
       prof.begin(1, s);
-      if ((rc = fft_plan_exec(fft, d_u.as<float2>(), d_out + r0 * (long)M, n, nullptr, 0, 0, s))) return rc;
+      if (demod) rc = fft_plan_exec_demod(fft, d_u.as<float2>(), demod->d, n, demod->gain, demod->atan, demod->prev_y, demod->last_y,
+                                          demod->coresident, s, demod->y_out);
+      else rc = fft_plan_exec(fft, d_u.as<float2>(), d_out + r0 * (long)M, n, nullptr, 0, 0, s);
+      if (rc) return rc;
       prof.end(s);
     }
     return GRCUDA_OK;
@@ -1548,6 +1554,16 @@ int pfb_prefer_coresident_fft(grcuda_pfb* h) {
   fft_plan_destroy(h->fft);
   h->fft = p;
   return GRCUDA_OK;
+}
+int pfb_demod_supported(grcuda_pfb* h) { return h->rr == (int)h->M && h->TT && fft_plan_demod_supported(h->fft) ? 1 : 0; }
+int pfb_work_device_demod(grcuda_pfb* h, long nrows, const float2* d_in_rows, float* d_D, float gain, const float2* prev_y,
+                          float2* last_y, bool coresident, cudaStream_t s, float2* y_out) {
+  if (!pfb_demod_supported(h)) return set_error(GRCUDA_EUNSUPPORTED, "pfb_channelizer_ccf: no fused discriminator path for this plan");
+  DeviceTables tabs;
+  int rc = get_tables(&tabs);
+  if (rc) return rc;
+  grcuda_pfb::DemodOut o = {d_D, gain, tabs.atan, prev_y, last_y, coresident, y_out};
+  return h->run(d_in_rows, nullptr, nrows, s, &o);
 }
 int pfb_reserve_rows(grcuda_pfb* h, long rows) { return h->d_u.reserve((size_t)rows * h->M * sizeof(float2)); }
 const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }

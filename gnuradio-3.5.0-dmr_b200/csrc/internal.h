@@ -27,7 +27,13 @@ int demod_front_max_taps();
 int demod_front_history(int ntaps);
 std::vector<float> demod_front_tap_table(const float* rt, int ntaps);  // host image of the kernel's tap store
 int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
-                       cudaStream_t s);
+                       cudaStream_t s, const float* dsrc = nullptr);
+// channelizer with the discriminator inside the FFT kernel (kernel_fft_demod.cuh): rows in -> D rows out (float), the
+// channelizer output itself never reaches HBM.  prev_y: [M] channelizer output of the row before the first one
+// (zeros at stream start); last_y receives that of the last row.  GRCUDA_EUNSUPPORTED when the plan has no such kernel.
+int pfb_demod_supported(grcuda_pfb* h);
+int pfb_work_device_demod(grcuda_pfb* h, long nrows, const float2* d_in_rows, float* d_D, float gain, const float2* prev_y,
+                          float2* last_y, bool coresident, cudaStream_t s, float2* y_out = nullptr);
 const float* fir_fff_front_taps(grcuda_fir_fff* h);  // device copy of demod_front_tap_table (nullptr: too many taps)
 // reversed taps / order / gain of the stand-alone plans (host copies)
 const float* fir_fff_reversed_taps(grcuda_fir_fff* h, int* ntaps, int* order);

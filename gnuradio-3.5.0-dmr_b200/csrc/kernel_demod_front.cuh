@@ -36,6 +36,8 @@ namespace grb {
 #define DF_MAXB 34       // max aligned blocks per output window -> ntaps <= 4*DF_MAXB - 7
 
 struct DemodFrontArgs {
+  const float* dsrc;     // non-null: the discriminator output already exists (the FFT kernel of the channelizer made
+                         // it, kernel_fft_demod.cuh): same row numbering as y, phase 1 is a plain copy into the tile
   const float2* y;       // row 0 of the buffer is absolute row (abs_row0 - hist)
   float* f;              // [nrows][M], row 0 = absolute row abs_row0
   long abs_row0;
@@ -81,7 +83,29 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   __syncthreads();
 
   // ---- phase 1: discriminator into shared memory (gr_quadrature_demod_cf.cc:56-59) -----------
-  {
+  if (a.dsrc) {  // (kernel uniform) the discriminator ran in the channelizer's FFT kernel: fetch its rows
+    constexpr int NW = DF_THREADS / 32;
+    const int per = (drows + NW - 1) / NW;
+    const int r0 = warp * per, r1 = min(drows, r0 + per);
+    const bool cok = c < a.M;
+    const long yi0 = d_row0 + r0 - ybase;
+    const float* __restrict__ dcolumn = a.dsrc + (cok ? c : 0);
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const long yi = yi0 + (r - r0) + u;
+        v[u] = (cok && yi >= 0 && yi < yrows) ? __ldg(dcolumn + yi * a.M) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) dtile[(r + u) * 32 + lane] = v[u];
+    }
+    for (; r < r1; r++) {
+      const long yi = yi0 + (r - r0);
+      dtile[r * 32 + lane] = (cok && yi >= 0 && yi < yrows) ? __ldg(dcolumn + yi * a.M) : 0.f;
+    }
+  } else {
     constexpr int NW = DF_THREADS / 32;
     const int per = (drows + NW - 1) / NW;                  // consecutive rows per warp
     const int r0 = warp * per, r1 = min(drows, r0 + per);

@@ -145,6 +145,14 @@ class DmrChain:
 
     STAGES = ("pfb_fir", "pfb_fft", "quad_demod", "rrc_fir", "mm_slicer", "map_unpack_corr", "carry_copies")
 
+    def set_keep_channels(self, on):
+        """False: the channelizer output is never written to HBM (fetch()["channels"] is absent): the discriminator runs
+        inside the channelizer's FFT kernel.  Same symbols and hits.  NotImplementedError when the plan has no such kernel."""
+        _l.check(self.L.grcuda_dmr_chain_set_keep_channels(self.h, int(on)))   # False/0, True/1, or 2 (fused kernel + stores)
+
+    def keeps_channels(self):
+        return int(self.L.grcuda_dmr_chain_keeps_channels(self.h))
+
     def set_tail_variant(self, variant):
         """Which build of the clock-recovery kernel the tail runs (0 = sized to co-reside with the front kernels)."""
         _l.check(self.L.grcuda_dmr_chain_set_tail_variant(self.h, int(variant)))
@@ -218,11 +226,12 @@ class DmrChain:
         r = self.result()
         M, ms = self.M, r.max_sym
         out = {
-            "channels": self._d2h(r.d_channels, r.nrows * M * 8).view(np.complex64).reshape(r.nrows, M),
             "counts": self._d2h(r.d_sym_counts, M * 4).view(np.int32),
             "soft": self._d2h(r.d_soft, ms * M * 4).view(np.float32).reshape(ms, M),
             "symbols": self._d2h(r.d_symbols, ms * M).reshape(ms, M),
         }
+        if r.d_channels:
+            out["channels"] = self._d2h(r.d_channels, r.nrows * M * 8).view(np.complex64).reshape(r.nrows, M)
         if r.d_bytes:
             out["bytes"] = self._d2h(r.d_bytes, 2 * ms * M).reshape(2 * ms, M)
         return out

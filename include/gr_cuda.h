@@ -475,6 +475,17 @@ typedef struct {
  * d_sym_counts / d_channels / nrows describe the LAST sub-block only (hits accumulate over the whole block).  A caller
  * that wants every symbol creates the chain with keep_bytes (one sub-block) or drives process_device itself. */
 int grcuda_dmr_chain_result_get(grcuda_dmr_chain* h, grcuda_dmr_chain_result* r);
+/* keep_channels = 0: the channelizer output is not materialised (d_channels = NULL); the discriminator then runs inside
+ * the last pass of the channelizer's FFT kernel on values that are still in registers, which removes 16 of the chain's
+ * 50 B of HBM traffic per input sample.  keep_channels = 2 is the same kernel which ALSO stores the transform it computed
+ * (d_channels valid; for parity tests: the tail is bit exact on exactly those values).  1 = default, two kernels.
+ * The fused kernel's transform differs from the plain FFT kernel's in the last bit (different multiply-add contraction;
+ * both within 1e-6 of the float64 DFT), so modes 0/2 and mode 1 agree like two FFT libraries do: dibits only differ
+ * within the slicer epsilon band.  Modes 0 and 2 are bit identical to each other.
+ * GRCUDA_EUNSUPPORTED (and nothing changes) when the channel count has no such kernel (it exists for 8000 and 4096
+ * channels at oversample rate 1, SSE summation order).  Call it on a fresh chain or right after seek(). */
+int grcuda_dmr_chain_set_keep_channels(grcuda_dmr_chain* h, int keep_channels);
+int grcuda_dmr_chain_keeps_channels(grcuda_dmr_chain* h);
 /* error counters of the chain (see grcuda_clock_recovery_mm_ff_counters) + sync hits that did not fit the hit list */
 int grcuda_dmr_chain_counters(grcuda_dmr_chain* h, long long* clamped, long long* overflow, long long* hits_dropped);
 /* copy the compacted sync hits of the last block to the host; returns their number */

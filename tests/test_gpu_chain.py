@@ -68,7 +68,8 @@ def run_chain_blocks(ch, x_rows, block_rows):
         ch.process_device(buf[r0:], n)
         torch.cuda.synchronize()
         res = ch.fetch()
-        chans.append(res["channels"].copy())
+        if "channels" in res:
+            chans.append(res["channels"].copy())
         for c in range(M):
             k = res["counts"][c]
             soft[c].append(res["soft"][:k, c].copy())
@@ -80,7 +81,7 @@ def run_chain_blocks(ch, x_rows, block_rows):
         hits += h
         r0 += n
     cat = lambda l: [np.concatenate(v) if v else np.empty(0) for v in l]
-    return np.concatenate(chans), cat(soft), cat(syms), cat(byts), hits
+    return (np.concatenate(chans) if chans else None), cat(soft), cat(syms), cat(byts), hits
 
 
 @pytest.mark.parametrize("order_name", ["sse", "generic"])
@@ -237,3 +238,108 @@ def test_chain_hits_without_byte_stream(orc, code_bits, threshold):
         assert [b for (cc, b) in hits[False] if cc == c] == want, c
         nh += len(want)
     assert nh > 0 or code_bits == 64
+
+
+@pytest.mark.parametrize("M,T,rows,blocks", [(8000, 16, 1500, (1500,)), (8000, 16, 1500, (400, 513, 587)), (4096, 8, 1200, (450, 750)),
+                                            (8000, 3, 900, (300, 600))])
+def test_chain_without_channelizer_output(orc, M, T, rows, blocks):
+    """keep_channels = 0: the discriminator runs inside the last pass of the channelizer's FFT kernel (kernel_fft_demod.cuh)
+    and the channelizer output never reaches HBM.  Parity, stage isolated like everywhere else: mode 2 is the SAME kernel
+    that also stores the transform it computed -- (1) that transform is within 1e-5 of the oracle channelizer, (2) on exactly
+    those values the oracle's tail gives the chain's soft symbols, decisions and correlator bytes bit for bit (so the
+    in-register discriminator, the chunk starts that re-transform a row and the block starts that take the previous
+    block's last row are all exact), (3) mode 0 equals mode 2 bit for bit, (4) against the default two-kernel path, whose
+    FFT kernel rounds differently in the last bit, more than 99.9 % of the sync hits are common."""
+    import torch
+    from grb200 import chain, synth
+    rng = np.random.default_rng(M + T)
+    active = [0, 1, M // 2, M - 1, 1234, 77]
+    x, _ = synth.wideband_compose(rng, M, rows, active, noise_sigma=1e-3)
+    xr = x.reshape(rows, M)
+    cfg = make_cfg(M, T, max_rows=max(blocks), keep_bytes=True)
+
+    def run(mode):
+        ch = chain.DmrChain(cfg)
+        ch.set_keep_channels(mode)
+        assert ch.keeps_channels() == mode
+        Th = ch.history_rows()
+        buf = torch.from_numpy(np.concatenate([np.zeros((Th, M), np.complex64), xr])).cuda()
+        out, r0 = [], 0
+        for n in blocks:
+            ch.process_device(buf[r0:], n)
+            torch.cuda.synchronize()
+            res = ch.fetch()
+            assert ("channels" in res) == (mode != 0)
+            hits, nh = ch.read_hits()
+            out.append((res["counts"].copy(), res["soft"].copy(), res["symbols"].copy(), res["bytes"].copy(), sorted(hits),
+                        res["channels"].copy() if mode else None))
+            r0 += n
+        assert ch.counters() == {"clamped": 0, "overflow": 0, "hits_dropped": 0}
+        return out
+    a, b, d = run(2), run(0), run(1)
+    # (3) production mode == parity mode, bit for bit
+    for (ca, sa, ya, ba, ha, _), (cb, sb, yb, bb, hb, _) in zip(a, b):
+        assert np.array_equal(ca, cb) and ha == hb
+        mask = np.arange(sa.shape[0])[:, None] < ca[None, :]
+        assert np.array_equal(sa.view(np.uint32)[mask], sb.view(np.uint32)[mask]) and np.array_equal(ya[mask], yb[mask])
+        mask2 = np.arange(ba.shape[0])[:, None] < 2 * ca[None, :]
+        assert np.array_equal(ba[mask2], bb[mask2])
+    # (1) the transform the fused kernel computed
+    y = np.concatenate([blk[5] for blk in a])
+    want, _ = orc.pfb_channelizer_ccf(M, cfg.pfb_taps, x[: M * 40])
+    assert relerr(y[:40], want) < 1e-5
+    assert relerr(y, np.concatenate([blk[5] for blk in d])) < 1e-6          # vs the plain FFT kernel: last-bit differences only
+    # (2) tail bit exact on those values
+    for c in active + [17, M - 2]:
+        m, s, cb = oracle_tail(orc, cfg, y[:, c], orc.ORDER_SSE)
+        soft = np.concatenate([blk[1][:blk[0][c], c] for blk in a])
+        sym = np.concatenate([blk[2][:blk[0][c], c] for blk in a])
+        byts = np.concatenate([blk[3][:2 * blk[0][c], c] for blk in a])
+        n = len(soft)
+        assert len(m) - 8 <= n <= len(m)
+        assert np.array_equal(soft.view(np.uint32), m[:n].view(np.uint32)) and np.array_equal(sym, s[:n]) and np.array_equal(byts, cb[:2 * n]), c
+    # (4) against the two-kernel path
+    ha = set(h for blk in a for h in blk[4])
+    hd = set(h for blk in d for h in blk[4])
+    assert len(ha & hd) >= 0.999 * max(len(ha), len(hd), 1)
+
+
+def test_chain_without_channelizer_output_shard_entry_points(orc):
+    """The same mode through process_front / process_tail_mm / process_tail_corr (a time shard's calls) and after seek()."""
+    import torch
+    from grb200 import chain, synth
+    M, T, rows = 8000, 16, 1000
+    rng = np.random.default_rng(21)
+    x, _ = synth.wideband_compose(rng, M, rows, [5, 4000, 7000], noise_sigma=1e-3)
+    xr = x.reshape(rows, M)
+    cfg = make_cfg(M, T, max_rows=rows, keep_bytes=False)
+    outs = []
+    for keep in (2, 0):
+        ch = chain.DmrChain(cfg)
+        ch.seek(0)
+        ch.set_keep_channels(keep)
+        Th = ch.history_rows()
+        buf = torch.from_numpy(np.concatenate([np.zeros((Th, M), np.complex64), xr])).cuda()
+        s = torch.cuda.current_stream().cuda_stream
+        hits = []
+        for r0, n in ((0, 600), (600, 400)):
+            ch.process_front_device(buf[r0:], n, s)
+            ch.process_tail_mm_device(None, None, s)
+            ch.process_tail_corr_device(None, None, s)
+            torch.cuda.synchronize()
+            h, _ = ch.read_hits()
+            res = ch.fetch()
+            hits.append((sorted(h), res["counts"].copy(), res["symbols"].copy()))
+        outs.append(hits)
+    for (ha, ca, ya), (hb, cb, yb) in zip(*outs):
+        assert ha == hb and np.array_equal(ca, cb)
+        mask = np.arange(ya.shape[0])[:, None] < ca[None, :]
+        assert np.array_equal(ya[mask], yb[mask])
+
+
+def test_keep_channels_unsupported_geometry():
+    from grb200 import chain
+    ch = chain.DmrChain(make_cfg(160, 16, max_rows=600))
+    with pytest.raises(NotImplementedError):
+        ch.set_keep_channels(False)          # 160 = 16 x 10 is a two-pass plan: no fused kernel
+    assert ch.keeps_channels()
