@@ -56,6 +56,7 @@ int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int 
     default: k = pick_qm<3>(a.q & 3); break;
   }
   const int J = a.q + 1 + (rho > 0 ? 1 : 0);
+  if (J == 8 && rho == 0) k = demod_front_kernel<0, 3, 8>;   // ntaps = 29: the chain's matched filter (11 symbols at 2.6 samples + 1)
   const size_t smem = ((size_t)4 * DF_MAXB * 4 + 260 + (size_t)(DF_RT + 4 * (J - 1)) * 32) * sizeof(float);
   if (smem > 48 * 1024) GRB_CUDA(raise_dynamic_smem((const void*)k, (size_t)smem));
   const long A0 = (abs_row0 >> 2) << 2;

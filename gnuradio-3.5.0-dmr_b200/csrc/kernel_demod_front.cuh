@@ -59,12 +59,14 @@ __host__ __device__ constexpr bool df_first(int j, int delta, int P) {
   return true;
 }
 
-template <int RHO, int QM>
+// JFIX != 0: the number of union blocks is a compile-time constant (the instantiation for the chain's 29-tap matched
+// filter: every loop bound, the tile height and the accumulator bookkeeping fold; same arithmetic, fewer instructions)
+template <int RHO, int QM, int JFIX = 0>
 __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   extern __shared__ __align__(16) float df_smem[];  // taps [4][DF_MAXB*4], atan table [260], d tile [drows][32]
   constexpr int DELTA_B = RHO > 0 ? 1 : 0;                 // class B (r >= RHO) starts one union block later
   const int q = a.q;
-  const int J = q + 1 + DELTA_B;                            // union blocks per group of four outputs
+  const int J = JFIX ? JFIX : q + 1 + DELTA_B;              // union blocks per group of four outputs
   const int drows = DF_RT + 4 * (J - 1);                    // d rows the tile touches
   float* taps_s = df_smem;
   float* tab = taps_s + 4 * DF_MAXB * 4;
@@ -174,9 +176,10 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   // ---- phase 2: RRC FIR, four outputs per thread per step --------------------------------------
   const ulonglong2* tp2 = reinterpret_cast<const ulonglong2*>(taps_s);  // tp2[al * DF_MAXB + b] = taps of block b for alignment al
   const df_u64 ones = df_pack(a.one, a.one);
+  const int rel0 = (int)(tile_start - a.abs_row0);          // output row of the tile's first row (negative in the first tile)
   for (int g = warp; g < DF_RT / 4; g += DF_THREADS / 32) {
-    const long a0 = tile_start + 4L * g;
-    if (a0 + 3 < a.abs_row0 || a0 >= a.abs_row0 + a.nrows) continue;  // warp uniform
+    const int rel = rel0 + 4 * g;
+    if (rel + 3 < 0 || rel >= a.nrows) continue;            // warp uniform
     df_u64 acc[4][4][2];  // [output r][slot][lane pair]
     const float* dcol = dtile + (size_t)(4 * g) * 32 + lane;  // union block j lane l -> dcol[(4j+l)*32]
     int j;
@@ -245,6 +248,7 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
 #undef DF_BLOCK
 #undef DF_SLOT_PRO
     // combine: true accumulator a lives in slot (a + P) & 3
+    float outs[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;
@@ -257,9 +261,20 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
                        df_add2(acc[r][(3 + P) & 3][h], acc[r][(2 + P) & 3][h]));
       float e0, e1;
       df_unpack(df_add2(d[0], d[1]), e0, e1);  // (d0 + d2, d1 + d3)
-      const float out = GR_FADD(GR_FADD(e0, e1), 0.0f);  // (-0) + 0 = +0, else unchanged
-      const long row = a0 + r - a.abs_row0;
-      if (c < a.M && row >= 0 && row < a.nrows) a.f[row * a.M + c] = out;
+      outs[r] = GR_FADD(GR_FADD(e0, e1), 0.0f);  // (-0) + 0 = +0, else unchanged
+    }
+    if (c < a.M) {
+      float* __restrict__ fp = a.f + (long)rel * a.M + c;
+      if (rel >= 0 && rel + 3 < a.nrows) {       // all four rows inside the block: one address, three increments
+        fp[0] = outs[0];
+        fp[a.M] = outs[1];
+        fp[2 * (long)a.M] = outs[2];
+        fp[3 * (long)a.M] = outs[3];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (rel + r >= 0 && rel + r < a.nrows) fp[r * (long)a.M] = outs[r];
+      }
     }
   }
 }
