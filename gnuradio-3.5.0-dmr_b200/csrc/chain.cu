@@ -332,7 +332,7 @@ static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows
     h->yl_cur ^= 1;
     h->prof.begin(3, sB);
     if ((rc = demod_front_launch(nullptr, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad),
-                                 fir_fff_front_taps(h->rrc), nt, sB, Dd)))
+                                 fir_fff_front_taps(h->rrc), nt, sB, Dd, fir_fff_front_taps_host(h->rrc))))
       return rc;
     h->prof.end(sB);
     h->prof.begin(6, sB);
@@ -352,7 +352,7 @@ static int front_impl(grcuda_dmr_chain* h, const grcuda_complex* d_in, int nrows
     fir_fff_reversed_taps(h->rrc, &nt, nullptr);
     h->prof.begin(3, sB);
     if ((rc = demod_front_launch(Y, F + (size_t)KEEP * M, (long)h->abs_row, (int)R, (int)M, quad_gain(h->quad),
-                                 fir_fff_front_taps(h->rrc), nt, sB)))
+                                 fir_fff_front_taps(h->rrc), nt, sB, nullptr, fir_fff_front_taps_host(h->rrc))))
       return rc;
     h->prof.end(sB);
   } else {

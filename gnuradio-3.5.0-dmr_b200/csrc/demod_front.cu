@@ -1,5 +1,6 @@
 // Host launcher of the fused discriminator + matched-filter kernel (kernel_demod_front.cuh).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -37,7 +38,7 @@ std::vector<float> demod_front_tap_table(const float* rt, int ntaps) {
 // demod_front_tap_table().
 // dsrc != nullptr: [hist + nrows][M] floats, the discriminator output made elsewhere (row numbering as y); y unused.
 int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
-                       cudaStream_t s, const float* dsrc) {
+                       cudaStream_t s, const float* dsrc, const float* h_tp) {
   if (ntaps < 1 || ntaps > demod_front_max_taps() || !d_tp) return set_error(GRCUDA_EUNSUPPORTED, "demod_front: %d taps", ntaps);
   if (nrows <= 0) return GRCUDA_OK;
   DeviceTables tabs;
@@ -56,7 +57,12 @@ int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int 
     default: k = pick_qm<3>(a.q & 3); break;
   }
   const int J = a.q + 1 + (rho > 0 ? 1 : 0);
-  if (J == 8 && rho == 0) k = demod_front_kernel<0, 3, 8>;   // ntaps = 29: the chain's matched filter (11 symbols at 2.6 samples + 1)
+  memset(a.tpc, 0, sizeof a.tpc);
+  if (J == 8 && rho == 0 && h_tp) {
+    k = demod_front_kernel<0, 3, 8>;
+    for (int al = 0; al < 4; al++)
+      for (int b = 0; b < 8; b++) memcpy(&a.tpc[al][b][0], h_tp + (size_t)al * DF_MAXB * 4 + b * 4, 16);
+  }   // ntaps = 29: the chain's matched filter (11 symbols at 2.6 samples + 1)
   const size_t smem = ((size_t)4 * DF_MAXB * 4 + 260 + (size_t)(DF_RT + 4 * (J - 1)) * 32) * sizeof(float);
   if (smem > 48 * 1024) GRB_CUDA(raise_dynamic_smem((const void*)k, (size_t)smem));
   const long A0 = (abs_row0 >> 2) << 2;
@@ -86,7 +92,7 @@ int grcuda_quad_demod_fir_fff_work_device(grcuda_quad* q, grcuda_fir_fff* f, lon
     return grb::set_error(GRCUDA_EUNSUPPORTED, "quad_demod_fir_fff: only the SSE summation order is fused");
   if (nrows > 0x7fffffffL || nchan < 1) return grb::set_error(GRCUDA_EINVAL, "quad_demod_fir_fff: bad shape");
   return grb::demod_front_launch((const float2*)d_in, d_out, abs_row0, (int)nrows, nchan, grb::quad_gain(q),
-                                 grb::fir_fff_front_taps(f), nt, (cudaStream_t)stream);
+                                 grb::fir_fff_front_taps(f), nt, (cudaStream_t)stream, nullptr, grb::fir_fff_front_taps_host(f));
 }
 
 }  // extern "C"

@@ -355,6 +355,7 @@ __global__ void fir_fff_stream_kernel(const float* __restrict__ in, float* __res
 struct grcuda_fir_fff : PlanBase {
   int decim = 1, ntaps = 0, order = GRCUDA_ORDER_SSE;
   DevBuf d_rt, d_front_tp;
+  std::vector<float> h_front_tp;   // host image of d_front_tp
   bool has_front_tp = false;
   std::vector<float> new_taps, rt_host;
   bool updated = false;
@@ -375,6 +376,7 @@ struct grcuda_fir_fff : PlanBase {
       const std::vector<float> tp = demod_front_tap_table(rt.data(), ntaps);
       if ((rc = d_front_tp.reserve(tp.size() * sizeof(float)))) return rc;
       GRB_CUDA(cudaMemcpy(d_front_tp.p, tp.data(), tp.size() * sizeof(float), cudaMemcpyHostToDevice));
+      h_front_tp = tp;
       has_front_tp = true;
     }
     if ((size_t)ntaps * sizeof(float) > 48 * 1024) {
@@ -1567,6 +1569,7 @@ int pfb_work_device_demod(grcuda_pfb* h, long nrows, const float2* d_in_rows, fl
 }
 int pfb_reserve_rows(grcuda_pfb* h, long rows) { return h->d_u.reserve((size_t)rows * h->M * sizeof(float2)); }
 const float* fir_fff_front_taps(grcuda_fir_fff* h) { return h->has_front_tp ? h->d_front_tp.as<float>() : nullptr; }
+const float* fir_fff_front_taps_host(grcuda_fir_fff* h) { return h->has_front_tp ? h->h_front_tp.data() : nullptr; }
 float quad_gain(grcuda_quad* h) { std::lock_guard<std::mutex> lk(h->mu); return h->gain; }
 void* mm_state_ptr(grcuda_mm* h) { return h->d_state.p; }
 // sums over channels of the two per-channel counters of the loop: steps clamped at the first buffered row, and calls

@@ -27,7 +27,8 @@ int demod_front_max_taps();
 int demod_front_history(int ntaps);
 std::vector<float> demod_front_tap_table(const float* rt, int ntaps);  // host image of the kernel's tap store
 int demod_front_launch(const float2* y, float* f, long abs_row0, int nrows, int M, float gain, const float* d_tp, int ntaps,
-                       cudaStream_t s, const float* dsrc = nullptr);
+                       cudaStream_t s, const float* dsrc = nullptr, const float* h_tp = nullptr);
+const float* fir_fff_front_taps_host(grcuda_fir_fff* h);  // host image of the same table (kernel-parameter taps)
 // channelizer with the discriminator inside the FFT kernel (kernel_fft_demod.cuh): rows in -> D rows out (float), the
 // channelizer output itself never reaches HBM.  prev_y: [M] channelizer output of the row before the first one
 // (zeros at stream start); last_y receives that of the last row.  GRCUDA_EUNSUPPORTED when the plan has no such kernel.

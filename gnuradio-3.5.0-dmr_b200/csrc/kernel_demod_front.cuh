@@ -48,6 +48,9 @@ struct DemodFrontArgs {
   int ntaps, q;          // ntaps - 1 = 4*q + rho
   const float* tp;       // [4][DF_MAXB * 4] device: tp[al][p] = rt[p - al] (reversed taps shifted by al, zero
                          // padded): the reference's four pre-aligned tap copies (gr_fir_fff_simd.cc:69-94)
+  unsigned long long tpc[4][8][2];  // the same for the first 8 blocks as packed pairs IN THE KERNEL PARAMETERS: the JFIX
+                         // instantiation addresses them with compile-time indices, i.e. as constant-bank operands --
+                         // no shared-memory load per tap block (the FIR phase is bound by the LDS pipe, not by issue)
 };
 
 // accumulator slot of union block j (first four blocks: the reference's "first nblocks%4 blocks go to xmm4"
@@ -199,7 +202,9 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
         const int slot = SLOT_OF;                                                          \
         (void)P;                                                                           \
         if ((j_) >= delta) {                                                               \
-          const ulonglong2 t = tp2[al * DF_MAXB + ((j_) - delta)];                         \
+          ulonglong2 t;                                                                    \
+          if (JFIX) t = make_ulonglong2(a.tpc[al][((j_) - delta) & 7][0], a.tpc[al][((j_) - delta) & 7][1]); \
+          else t = tp2[al * DF_MAXB + ((j_) - delta)];                                     \
           const df_u64 p01 = df_mul2(t.x, x01), p23 = df_mul2(t.y, x23);                   \
           if (FIRST_OF) {                                                                  \
             acc[r][slot][0] = p01;                                                         \
