@@ -86,12 +86,15 @@ class ShardedChain:
             ev.record(self.halo_ts)
             self.halo_ev[s % 2] = ev
 
-    def step(self, s, xbuf, last_step):
+    def step(self, s, xbuf, last_step, exchange_halo=True):
+        """exchange_halo = False: the caller has put the block INCLUDING its halo rows into xbuf[s % 2] (host-fed shards:
+        the halo arrives with the rank's own host-to-device copy, no NCCL exchange)."""
         ch, p = self.ch, self.plan
         cur = torch.cuda.current_stream(self.dev)
         stream = cur.cuda_stream
         _dbg("step %d: front" % s)
-        cur.wait_event(self.halo_ev[s % 2])                         # this step's halo has landed
+        if exchange_halo:
+            cur.wait_event(self.halo_ev[s % 2])                     # this step's halo has landed
         ch.seek_async(p.abs_start(s) - self.halo, stream)
         # the front runs after the rank's own previous clock-recovery kernel, not underneath it: both then run at
         # their stand-alone speed, and the device has the neighbours' slots of the serial chain to wait through anyway
@@ -102,7 +105,8 @@ class ShardedChain:
         self.front_ev[s % 2] = ev
         self._mark("front %d" % s, cur)
         _dbg("step %d: halo of the next step" % s)
-        self.post_halo(s + 1, xbuf)                                 # one exchange per step, one step ahead
+        if exchange_halo:
+            self.post_halo(s + 1, xbuf)                             # one exchange per step, one step ahead
         _dbg("step %d: tail" % s)
         k = s % 2
         final = s == last_step and p.rank == p.world - 1            # nobody waits for the last block's state
