@@ -141,8 +141,19 @@ def pin_to_gpu_numa_node(local):
     places the staging buffers there, and N ranks stop sharing one node's memory controllers and PCIe root."""
     try:
         import torch
-        pr = torch.cuda.get_device_properties(local)
-        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        uuid = str(torch.cuda.get_device_properties(local).uuid).lower()
+        out = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+        bus = None
+        for line in out.strip().splitlines():
+            u, _, b = line.partition(",")
+            if u.strip().lower().endswith(uuid):
+                bus = b.strip().lower()
+        if bus is None:
+            return None
+        if len(bus.split(":")[0]) == 8:       # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus
         node = int(open(path).read().strip())
         if node < 0:
             return None
@@ -225,6 +236,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # a time shard runs its front AFTER its own tail (sharding.TimeShardPlan.front_after_own_tail): no kernel has to
+        # co-reside with the clock-recovery kernel, so the chain takes the full-register FFT build (read at chain creation)
+        os.environ.setdefault("GRCUDA_CHAIN_NO_OVERLAP", "1")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
