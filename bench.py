@@ -288,6 +288,8 @@ def run_ours(args):
         ch.set_tail_variant(args.tail_variant)
     if args.fused_correlator:
         ch.set_split_correlator(False)
+    if args.split_correlator:
+        ch.set_split_correlator(True)
     Th = ch.history_rows()
     # ONE stream for the whole job: the same periodic block on every rank (it tiles seamlessly in time), rank r takes
     # blocks r, r + world, ...  The loop state, and therefore every symbol and sync hit, evolves from block to block.
@@ -683,6 +685,7 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra, separately timed steady-state region (0: none)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the comparison of all sync hits with a single chain")
     ap.add_argument("--tail-variant", type=int, default=None, help="build of the clock-recovery kernel (default: the chain's choice)")
+    ap.add_argument("--split-correlator", action="store_true", help="two-kernel tail also underneath the front (single GPU)")
     ap.add_argument("--fused-correlator", action="store_true", help="correlator inside the clock-recovery kernel (round-1 form)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

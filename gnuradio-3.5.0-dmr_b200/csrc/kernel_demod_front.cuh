@@ -134,25 +134,35 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       // phase would otherwise wait for (ncu: 2.3 long-scoreboard stalls per issue with batches of 4 and no overlap).
       constexpr int DF_PB = 6;
       float2 nx[DF_PB];
+      const int nfull = (r1 - r0) / DF_PB;      // whole batches: no per-row predicates (36 rows per warp = 6 x 6 for 29 taps)
+      int r = r0;
+      if (nfull > 0) {
 #pragma unroll
-      for (int u = 0; u < DF_PB; u++)
-        if (r0 + u < r1) nx[u] = __ldg(p + u * M);
-      for (int r = r0; r < r1; r += DF_PB) {
-        float2 v[DF_PB];
+        for (int u = 0; u < DF_PB; u++) nx[u] = __ldg(p + u * M);
+        for (int k = 0; k < nfull; k++) {
+          float2 v[DF_PB];
 #pragma unroll
-        for (int u = 0; u < DF_PB; u++) v[u] = nx[u];
-        p += DF_PB * M;
+          for (int u = 0; u < DF_PB; u++) v[u] = nx[u];
+          p += DF_PB * M;
+          if (k + 1 < nfull) {
 #pragma unroll
-        for (int u = 0; u < DF_PB; u++)
-          if (r + DF_PB + u < r1) nx[u] = __ldg(p + u * M);
+            for (int u = 0; u < DF_PB; u++) nx[u] = __ldg(p + u * M);
+          }
 #pragma unroll
-        for (int u = 0; u < DF_PB; u++) {
-          if (r + u < r1) {
+          for (int u = 0; u < DF_PB; u++) {
             dt[u * 32] = quad_demod(v[u], prev, a.gain, tab);
             prev = v[u];
           }
+          dt += DF_PB * 32;
         }
-        dt += DF_PB * 32;
+        r += nfull * DF_PB;
+      }
+      for (; r < r1; r++) {                     // ragged end of the last warp's share
+        const float2 cur = __ldg(p);
+        p += M;
+        *dt = quad_demod(cur, prev, a.gain, tab);
+        dt += 32;
+        prev = cur;
       }
     } else {
     float2 prev = ld(yi0 - 1);
