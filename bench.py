@@ -140,6 +140,9 @@ def pin_to_gpu_numa_node(local):
     """Binds this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned allocation: first-touch then
     places the staging buffers there, and N ranks stop sharing one node's memory controllers and PCIe root."""
     try:
+        online = open("/sys/devices/system/node/online").read().strip()
+        if online in ("0", ""):
+            return {"nodes_online": 1, "note": "single NUMA node: nothing to bind"}
         import torch
         uuid = str(torch.cuda.get_device_properties(local).uuid).lower()
         out = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE,
@@ -149,6 +152,12 @@ def pin_to_gpu_numa_node(local):
             u, _, b = line.partition(",")
             if u.strip().lower().endswith(uuid):
                 bus = b.strip().lower()
+        if bus is None:       # (UUIDs are redacted on some boxes) fall back to the enumeration order
+            lines = [l for l in out.strip().splitlines() if l.strip()]
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+            if idx < len(lines):
+                bus = lines[idx].partition(",")[2].strip().lower()
         if bus is None:
             return None
         if len(bus.split(":")[0]) == 8:       # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
