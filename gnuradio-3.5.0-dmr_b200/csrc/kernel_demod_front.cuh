@@ -35,6 +35,11 @@ namespace grb {
 #define DF_THREADS 256  // 2 CTAs per SM at 96 registers, and still 2 next to a CTA of the clock-recovery kernel (320 x 320 tiles are 6 % faster alone, slower in the pipelined chain)
 #define DF_MAXB 34       // max aligned blocks per output window -> ntaps <= 4*DF_MAXB - 7
 
+// Discriminator tile layout: four consecutive rows of a channel are one 16-byte quad, element (row r, lane l) at
+// [(r >> 2) * 128 + l * 4 + (r & 3)] -- the FIR phase takes the four samples of a union block with ONE LDS.128 (already a
+// packed register pair for FMUL2), the discriminator phase stores one STS.128 per four rows.
+__device__ __forceinline__ int df_dt(int r, int lane) { return ((r >> 2) << 7) + (lane << 2) + (r & 3); }
+
 struct DemodFrontArgs {
   const float* dsrc;     // non-null: the discriminator output already exists (the FFT kernel of the channelizer made
                          // it, kernel_fft_demod.cuh): same row numbering as y, phase 1 is a plain copy into the tile
@@ -90,8 +95,8 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
   // ---- phase 1: discriminator into shared memory (gr_quadrature_demod_cf.cc:56-59) -----------
   if (a.dsrc) {  // (kernel uniform) the discriminator ran in the channelizer's FFT kernel: fetch its rows
     constexpr int NW = DF_THREADS / 32;
-    const int per = (drows + NW - 1) / NW;
-    const int r0 = warp * per, r1 = min(drows, r0 + per);
+    const int per = ((drows / 4 + NW - 1) / NW) * 4;        // rows per warp: whole quads (drows is a multiple of 4)
+    const int r0 = min(drows, warp * per), r1 = min(drows, r0 + per);
     const bool cok = c < a.M;
     const long yi0 = d_row0 + r0 - ybase;
     const float* __restrict__ dcolumn = a.dsrc + (cok ? c : 0);
@@ -104,16 +109,16 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
         v[u] = (cok && yi >= 0 && yi < yrows) ? __ldg(dcolumn + yi * a.M) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) dtile[(r + u) * 32 + lane] = v[u];
+      for (int u = 0; u < 8; u++) dtile[df_dt(r + u, lane)] = v[u];
     }
     for (; r < r1; r++) {
       const long yi = yi0 + (r - r0);
-      dtile[r * 32 + lane] = (cok && yi >= 0 && yi < yrows) ? __ldg(dcolumn + yi * a.M) : 0.f;
+      dtile[df_dt(r, lane)] = (cok && yi >= 0 && yi < yrows) ? __ldg(dcolumn + yi * a.M) : 0.f;
     }
   } else {
     constexpr int NW = DF_THREADS / 32;
-    const int per = (drows + NW - 1) / NW;                  // consecutive rows per warp
-    const int r0 = warp * per, r1 = min(drows, r0 + per);
+    const int per = ((drows / 4 + NW - 1) / NW) * 4;        // consecutive rows per warp: whole quads
+    const int r0 = min(drows, warp * per), r1 = min(drows, r0 + per);
     const bool cok = c < a.M;
     const float2* __restrict__ ycol = a.y + (cok ? c : 0);
     auto ld = [&](long yi) -> float2 {                      // rows outside the buffer: before the stream / not there yet
@@ -128,13 +133,13 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
       const float2* __restrict__ p = a.y + (size_t)(yi0 - 1) * M + c;
       float2 prev = __ldg(p);
       p += M;
-      float* dt = dtile + r0 * 32 + lane;
-      // Batches of DF_PB rows, the next batch's loads in flight while this one is computed: the rows come straight
-      // from HBM (each is read once), and with 16 warps per SM it is their latency, not the arctangent, that the
-      // phase would otherwise wait for (ncu: 2.3 long-scoreboard stalls per issue with batches of 4 and no overlap).
-      constexpr int DF_PB = 6;
+      float4* dt = reinterpret_cast<float4*>(dtile) + (r0 >> 2) * 32 + lane;   // r0 is a multiple of 4
+      // Batches of DF_PB rows (three quads), the next batch's loads in flight while this one is computed: the rows come
+      // straight from HBM (each is read once), and with 16 warps per SM it is their latency, not the arctangent, that
+      // the phase would otherwise wait for (ncu: 2.3 long-scoreboard stalls per issue with batches of 4 and no overlap).
+      constexpr int DF_PB = 12;
       float2 nx[DF_PB];
-      const int nfull = (r1 - r0) / DF_PB;      // whole batches: no per-row predicates (36 rows per warp = 6 x 6 for 29 taps)
+      const int nfull = (r1 - r0) / DF_PB;      // whole batches (36 rows per warp = 3 x 12 for 29 taps)
       int r = r0;
       if (nfull > 0) {
 #pragma unroll
@@ -149,20 +154,32 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
             for (int u = 0; u < DF_PB; u++) nx[u] = __ldg(p + u * M);
           }
 #pragma unroll
-          for (int u = 0; u < DF_PB; u++) {
-            dt[u * 32] = quad_demod(v[u], prev, a.gain, tab);
-            prev = v[u];
+          for (int qd = 0; qd < DF_PB / 4; qd++) {
+            float4 d4;
+            d4.x = quad_demod(v[4 * qd + 0], prev, a.gain, tab);
+            d4.y = quad_demod(v[4 * qd + 1], v[4 * qd + 0], a.gain, tab);
+            d4.z = quad_demod(v[4 * qd + 2], v[4 * qd + 1], a.gain, tab);
+            d4.w = quad_demod(v[4 * qd + 3], v[4 * qd + 2], a.gain, tab);
+            prev = v[4 * qd + 3];
+            dt[qd * 32] = d4;
           }
-          dt += DF_PB * 32;
+          dt += (DF_PB / 4) * 32;
         }
         r += nfull * DF_PB;
       }
-      for (; r < r1; r++) {                     // ragged end of the last warp's share
-        const float2 cur = __ldg(p);
-        p += M;
-        *dt = quad_demod(cur, prev, a.gain, tab);
+      for (; r < r1; r += 4) {                  // remaining quads of the warp's share
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldg(p + u * M);
+        p += 4 * M;
+        float4 d4;
+        d4.x = quad_demod(v[0], prev, a.gain, tab);
+        d4.y = quad_demod(v[1], v[0], a.gain, tab);
+        d4.z = quad_demod(v[2], v[1], a.gain, tab);
+        d4.w = quad_demod(v[3], v[2], a.gain, tab);
+        prev = v[3];
+        *dt = d4;
         dt += 32;
-        prev = cur;
       }
     } else {
     float2 prev = ld(yi0 - 1);
@@ -177,14 +194,14 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
         // d = 0 where the reference has not produced a sample (before the stream start the history is
         // zeros, gr_buffer.cc:201-214; rows past the end of the buffer only ever meet zero taps)
         const float d = (cok && yi >= 0 && yi < yrows) ? quad_demod(v[u], prev, a.gain, tab) : 0.f;
-        dtile[(r + u) * 32 + lane] = d;
+        dtile[df_dt(r + u, lane)] = d;
         prev = v[u];
       }
     }
     for (; r < r1; r++) {
       const long yi = yi0 + (r - r0);
       const float2 cur = ld(yi);
-      dtile[r * 32 + lane] = (cok && yi >= 0 && yi < yrows) ? quad_demod(cur, prev, a.gain, tab) : 0.f;
+      dtile[df_dt(r, lane)] = (cok && yi >= 0 && yi < yrows) ? quad_demod(cur, prev, a.gain, tab) : 0.f;
       prev = cur;
     }
     }
@@ -199,16 +216,15 @@ __global__ void __maxnreg__(96) demod_front_kernel(const DemodFrontArgs a) {
     const int rel = rel0 + 4 * g;
     if (rel + 3 < 0 || rel >= a.nrows) continue;            // warp uniform
     df_u64 acc[4][4][2];  // [output r][slot][lane pair]
-    const float* dcol = dtile + (size_t)(4 * g) * 32 + lane;  // union block j lane l -> dcol[(4j+l)*32]
+    const float4* dcol = reinterpret_cast<const float4*>(dtile) + g * 32 + lane;  // union block j = the quad dcol[j * 32]
     int j;
     // one union block for all four outputs.  SLOT_OF = accumulator slot of this block, FIRST_OF = the block is the
     // first to touch that slot (its products initialise the accumulator); both fold to constants once the r loop
     // is unrolled
 #define DF_BLOCK(j_, SLOT_OF, FIRST_OF)                                                    \
     {                                                                                      \
-      float x[4];                                                                          \
-      _Pragma("unroll") for (int l = 0; l < 4; l++) x[l] = dcol[(4 * (j_) + l) * 32];      \
-      const df_u64 x01 = df_pack(x[0], x[1]), x23 = df_pack(x[2], x[3]);                   \
+      const float4 xq = dcol[(j_) * 32];                                                   \
+      const df_u64 x01 = df_pack(xq.x, xq.y), x23 = df_pack(xq.z, xq.w);                   \
       _Pragma("unroll") for (int r = 0; r < 4; r++) {                                      \
         const int delta = (RHO > 0 && r >= RHO) ? 1 : 0;                                   \
         const int nbm = (RHO > 0 && r < RHO) ? ((QM + 2) & 3) : ((QM + 1) & 3);            \
