@@ -139,7 +139,8 @@ grcuda_dmr_chain* grcuda_dmr_chain_create(const grcuda_dmr_chain_params* p) {
     return nullptr;
   }
   h->max_sym = (int)std::ceil((double)(KEEP + R) / (double)(p->omega - p->omega_relative_limit) * 1.25) + 64;  // x 1.25: gain_mu * mean(mm) also moves the pace
-  h->max_hits = std::max<int>(4096, (int)(M * (size_t)h->max_sym / 32));
+  // room for the sync hits of many blocks when the caller lets them accumulate (bench.py: a whole timed region per rank)
+  h->max_hits = std::max<int>(4096, (int)std::min<size_t>(M * (size_t)h->max_sym / 8, (size_t)1 << 26));
   int rc = 0;
   rc = rc ? rc : pfb_reserve_rows(h->pfb, (long)R);  // no allocation (= device-wide sync) once blocks are flowing
   rc = rc ? rc : h->Yb.reserve((h->YH + R) * M * sizeof(float2));
