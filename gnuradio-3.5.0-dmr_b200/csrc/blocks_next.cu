@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -479,6 +480,7 @@ struct grcuda_unpack_k_bits : Plan {
   unsigned k = 1;
 };
 struct grcuda_streams : Plan {   // stream_to_streams and vector_to_streams: the same data movement
+  std::vector<unsigned char> h_tmp;
   size_t item_size = 1;
   int nstreams = 1;
   int launch(const void* d_in, void* d_out, long nitems, long out_stride, cudaStream_t s) {
@@ -633,8 +635,14 @@ int grcuda_streams_work(grcuda_streams* h, int noutput_items, const void* in, vo
   if ((rc = h->stager.h2d(h->d_in.p, in, total, h->stream))) return rc;
   if ((rc = h->launch(h->d_in.p, h->d_out.p, noutput_items, noutput_items, h->stream))) return rc;
   const size_t per = (size_t)noutput_items * h->item_size;
-  for (int j = 0; j < h->nstreams; j++)
-    if ((rc = h->stager.d2h(out[j], (const char*)h->d_out.p + (size_t)j * per, per, h->stream))) return rc;
+  if (h->nstreams <= 8) {
+    for (int j = 0; j < h->nstreams; j++)
+      if ((rc = h->stager.d2h(out[j], (const char*)h->d_out.p + (size_t)j * per, per, h->stream))) return rc;
+  } else {   // many streams: ONE device-to-host transfer (each d2h synchronises), then the scatter to the caller's buffers
+    h->h_tmp.resize(total);
+    if ((rc = h->stager.d2h(h->h_tmp.data(), h->d_out.p, total, h->stream))) return rc;
+    for (int j = 0; j < h->nstreams; j++) memcpy(out[j], h->h_tmp.data() + (size_t)j * per, per);
+  }
   return noutput_items;
 }
 

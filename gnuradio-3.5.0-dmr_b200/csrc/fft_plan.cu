@@ -248,10 +248,8 @@ static fft_demod_kernel_t demod_kernel_for(FftPlan* p, bool coresident) {
   // become FMAs, so two register caps are two (last-bit) different transforms, and a time shard must reproduce the
   // single chain bit for bit.  128 registers co-reside with the clock-recovery kernel of the previous block.
   (void)coresident;
-  if (p->radix[0] == 20 && p->radix[1] == 20 && p->radix[2] == 20) {
-    static const bool wide = getenv("GRCUDA_FFT_DEMOD_WIDE") != nullptr;   // lab switch (tools/): the 152-register build
-    return wide ? fft_demod_kernel<1, 20, 20, 20, 152> : fft_demod_kernel<1, 20, 20, 20, 128>;
-  }
+  // (A 152-register build has no spills but cannot launch: 13 warps x 152 registers exceed the register file.)
+  if (p->radix[0] == 20 && p->radix[1] == 20 && p->radix[2] == 20) return fft_demod_kernel<1, 20, 20, 20, 128>;
   if (p->radix[0] == 16 && p->radix[1] == 16 && p->radix[2] == 16) return fft_demod_kernel<1, 16, 16, 16, 152>;
   return nullptr;
 }
