@@ -649,6 +649,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "rows_per_step_per_gpu": R, "samples_per_step_per_gpu": samples_per_step,
                    "active_channels": int(args.active), "halo_rows": halo, "sharding": "time blocks, block = step*N + rank",
                    "front_vs_own_tail": "after" if plan.front_after_own_tail else "overlapped",
+                   "loop_state_handoff": (sc.handoff if world > 1 else None),
                    "channelizer_output": "kept in HBM" if not fused_fft else "not materialised: discriminator fused into the channelizer's FFT kernel (bit identical symbols and hits)",
                    "l2": "input block (%.0f MB) and every intermediate are larger than the 126 MB L2" % (samples_per_step * 8 / 1e6),
                    "host_numa_binding": numa},

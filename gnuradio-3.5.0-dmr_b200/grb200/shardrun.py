@@ -33,8 +33,87 @@ def _dbg(msg):
         sys.stderr.flush()
 
 
+class _Ptr:
+    """A raw device address with the .data_ptr() the chain wrapper asks tensors for."""
+
+    def __init__(self, addr):
+        self.addr = int(addr)
+
+    def data_ptr(self):
+        return self.addr
+
+
+class PeerRing:
+    """The loop-state hand-off between neighbouring ranks WITHOUT NCCL kernels: every rank owns
+    one device allocation [flags | clock-recovery state | correlator registers], exports it with CUDA IPC, and opens its
+    right neighbour's.  The tail kernel writes its final state STRAIGHT INTO the right neighbour's buffer (peer stores over
+    NVLink), a stream memory operation (cuStreamWriteValue32, which fences system-wide first) then publishes the block
+    number in the neighbour's flag, and the neighbour's tail stream holds a cuStreamWaitValue32(flag >= block) in front of
+    its kernel.  No receive has to be posted, nothing spins on an SM, nothing needs a matching call: the ordering problems
+    of the send/recv version (prepost, eager communicator creation for these two rings) do not exist here."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, plan, device, mm_bytes, corr_bytes):
+        from cuda.bindings import driver as cu
+        self.cu, self.plan = cu, plan
+        torch.cuda.synchronize(device)                       # torch's primary context is current on this thread
+        self.mm_off = self.FLAG_BYTES
+        self.corr_off = self.mm_off + ((mm_bytes + 255) // 256) * 256
+        self.nbytes = self.corr_off + ((corr_bytes + 255) // 256) * 256
+        self._ck(cu.cuInit(0))
+        self.base = int(self._ck(cu.cuMemAlloc(self.nbytes)))
+        self._ck(cu.cuMemsetD8(self.base, 0, self.nbytes))
+        handle = self._ck(cu.cuIpcGetMemHandle(self.base))
+        mine = torch.tensor(list(bytes(handle.reserved)), dtype=torch.uint8, device=device)
+        every = [torch.zeros_like(mine) for _ in range(plan.world)]
+        dist.all_gather(every, mine)
+        h = cu.CUipcMemHandle()
+        h.reserved = bytes(every[plan.right].cpu().tolist())
+        self.peer = int(self._ck(cu.cuIpcOpenMemHandle(h, cu.CUipcMem_flags.CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS)))
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def _ck(self, res):
+        err = res[0]
+        if int(err) != 0:
+            raise RuntimeError("CUDA driver call failed: %r" % (err,))
+        return res[1] if len(res) == 2 else (res[1:] if len(res) > 2 else None)
+
+    # own receive buffers / the right neighbour's, as pointers the chain takes
+    def mm_in(self):
+        return _Ptr(self.base + self.mm_off)
+
+    def corr_in(self):
+        return _Ptr(self.base + self.corr_off)
+
+    def mm_out(self):
+        return _Ptr(self.peer + self.mm_off)
+
+    def corr_out(self):
+        return _Ptr(self.peer + self.corr_off)
+
+    def wait(self, stream, which, value):
+        """stream waits until own flag[which] >= value"""
+        cu = self.cu
+        self._ck(cu.cuStreamWaitValue32(cu.CUstream(stream.cuda_stream), self.base + 4 * which, int(value) & 0x7fffffff,
+                                        cu.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ))
+
+    def publish(self, stream, which, value):
+        """(after the kernel on this stream) the right neighbour's flag[which] = value"""
+        cu = self.cu
+        self._ck(cu.cuStreamWriteValue32(cu.CUstream(stream.cuda_stream), self.peer + 4 * which, int(value) & 0x7fffffff, 0))
+
+    def close(self):
+        try:
+            self.cu.cuIpcCloseMemHandle(self.peer)
+            self.cu.cuMemFree(self.base)
+        except Exception:
+            pass
+
+
 class ShardedChain:
-    def __init__(self, ch, plan, device, rows, halo, history_rows):
+    def __init__(self, ch, plan, device, rows, halo, history_rows, handoff=None):
         self.ch, self.plan, self.dev = ch, plan, device
         self.R, self.halo, self.Th = int(rows), int(halo), int(history_rows)
         w = plan.world
@@ -57,6 +136,22 @@ class ShardedChain:
         self.front_ev = [None, None]
         self._pre = None          # (step, mm work, corr work): receives posted ahead of a device-wide synchronisation
         self._marks = []          # GRB_SHARD_DEBUG: (label, event) in launch order
+        # loop-state hand-off: peer memory + stream memory operations when CUDA IPC works on this box, else NCCL send/recv
+        handoff = handoff or os.environ.get("GRB_SHARD_HANDOFF", "peer")
+        self.ring = None
+        if handoff == "peer":
+            ok = torch.zeros(1, dtype=torch.int32, device=device)
+            try:
+                self.ring = PeerRing(plan, device, ch.mm_state_bytes(), ch.corr_state_bytes())
+                ok += 1
+            except Exception as e:      # no IPC in this container, no peer access, ...: every rank must agree on the fallback
+                sys.stderr.write("[shard rank %d] peer hand-off unavailable (%r): NCCL send/recv\n" % (plan.rank, e))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if self.ring is not None:
+                    self.ring.close()
+                self.ring = None
+        self.handoff = "peer memory + stream memory ops" if self.ring is not None else "nccl send/recv"
         ch.set_accumulate_hits(True)
         ch.clear_hits(torch.cuda.current_stream(device).cuda_stream)
         # Create every point-to-point communicator NOW, with one symmetric exchange per group: created lazily by the
@@ -110,6 +205,31 @@ class ShardedChain:
         _dbg("step %d: tail" % s)
         k = s % 2
         final = s == last_step and p.rank == p.world - 1            # nobody waits for the last block's state
+        if self.ring is not None:
+            # block number of this step's block; the left neighbour publishes b (= its block b - 1, plus one) when the state
+            # of block b - 1 is in this rank's buffer, this rank publishes b + 1 to the right
+            b = p.block_index(s)
+            has_left = p.has_left_state(s)
+            with torch.cuda.stream(self.tail_ts):
+                self.tail_ts.wait_event(ev)
+                if has_left:
+                    self.ring.wait(self.tail_ts, 0, b)
+                self._mark("mm state in %d" % s, self.tail_ts)
+                ch.process_tail_mm_device(self.ring.mm_in() if has_left else None, None if final else self.ring.mm_out(),
+                                          self.tail_ts.cuda_stream)
+                self._mark("mm kernel %d" % s, self.tail_ts)
+                if not final:
+                    self.ring.publish(self.tail_ts, 0, b + 1)
+            with torch.cuda.stream(self.corr_ts):
+                if has_left:
+                    self.ring.wait(self.corr_ts, 1, b)
+                ch.process_tail_corr_device(self.ring.corr_in() if has_left else None, None if final else self.ring.corr_out(),
+                                            self.corr_ts.cuda_stream)
+                self._mark("corr kernel %d" % s, self.corr_ts)
+                if not final:
+                    self.ring.publish(self.corr_ts, 1, b + 1)
+            _dbg("step %d: done" % s)
+            return
         with torch.cuda.stream(self.tail_ts):
             ts = self.tail_ts.cuda_stream
             # an NCCL receive spins on an SM until its peer sends: posted before the front is done it takes that SM
@@ -163,6 +283,8 @@ class ShardedChain:
         receive -- a device-wide synchronisation would wait for it for ever.  Every other rank's left neighbour produces
         the state during the step itself."""
         p = self.plan
+        if self.ring is not None:      # flags in memory need no posted receive
+            return
         if p.rank != 0 or not p.has_left_state(next_step) or self._pre is not None:
             return
         with torch.cuda.stream(self.tail_ts):
