@@ -72,7 +72,8 @@ class PeerRing:
         h.reserved = bytes(every[plan.right].cpu().tolist())
         self.peer = int(self._ck(cu.cuIpcOpenMemHandle(h, cu.CUipcMem_flags.CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS)))
         torch.cuda.synchronize(device)
-        dist.barrier()
+        # (no collective from here on: the caller's all_reduce is the next one on EVERY rank, whether this constructor
+        # succeeded or raised after the all_gather)
 
     def _ck(self, res):
         err = res[0]
