@@ -263,10 +263,21 @@ __global__ void __launch_bounds__(128) framer_rows_kernel(const FramerArgs a) {
   const long n = a.counts ? (long)a.counts[c] * a.count_scale : a.nitems;
   const unsigned char* p = a.in + (long)c * a.c_stride;
   long t = 0;
+  // groups of 16 rows, the NEXT group's loads in flight while this one is looked at: with 250 warps on the machine a
+  // group is one DRAM round trip, and nothing else hides it (a warp-load is one 32-byte sector of a row)
+  unsigned nx[16];
+  if (n >= 16) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) nx[i] = __ldg(p + (long)i * a.t_stride);
+  }
   for (; t + 16 <= n; t += 16) {
     unsigned b[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) b[i] = __ldg(p + (t + i) * a.t_stride);
+    for (int i = 0; i < 16; i++) b[i] = nx[i];
+    if (t + 32 <= n) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) nx[i] = __ldg(p + (t + 16 + i) * a.t_stride);
+    }
     if (s.state == 0) {                     // searching and no flag in these 16 items: nothing happens (:104-112)
       unsigned any = 0;
 #pragma unroll
