@@ -123,9 +123,8 @@ class ShardedChain:
         self.halo_group = dist.new_group()
         self.mm_group = dist.new_group()
         self.corr_group = dist.new_group()
-        # the two chains are what every other rank waits for: their kernels go ahead of this rank's own front kernels
-        self.tail_ts = torch.cuda.Stream(device=device, priority=-1)
-        self.corr_ts = torch.cuda.Stream(device=device, priority=-1)
+        self.tail_ts = torch.cuda.Stream(device=device)
+        self.corr_ts = torch.cuda.Stream(device=device)
         self.halo_ts = torch.cuda.Stream(device=device)
         u8 = dict(dtype=torch.uint8, device=device)
         self.mm_in = torch.zeros(ch.mm_state_bytes(), **u8)
