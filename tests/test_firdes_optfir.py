@@ -94,3 +94,24 @@ def test_default_taps_feed_the_gpu_channelizer(orc):
     got, c = blk.general_work_interleaved(rows, inter)
     assert c == wc == rows and got.shape == want.shape
     assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 5e-6
+
+
+@pytest.mark.gpu
+def test_blks2_pfb_channelizer_hier_block(orc):
+    """blks2.pfb_channelizer_ccf(numchans) as a script writes it (no taps): one interleaved stream in, numchans streams
+    out, equal to the oracle channelizer on the taps the reference's design rule gives."""
+    from grb200 import blks2
+    M = 16
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal(M * 400) + 1j * rng.standard_normal(M * 400)).astype(np.complex64)
+    blk = blks2.pfb_channelizer_ccf(M)
+    outs = blk.run(x)
+    assert len(outs) == M
+    want, _ = orc.pfb_channelizer_ccf(M, blk.taps().astype(np.float32), x)
+    got = np.stack(outs, axis=1)
+    n = min(len(got), len(want))
+    assert n >= 390 and np.max(np.abs(got[:n] - want[:n])) / np.max(np.abs(want)) < 5e-6
+    # a tone in channel 3 comes out of stream 3
+    t = np.exp(2j * np.pi * 3 / M * np.arange(M * 200)).astype(np.complex64)
+    p = np.array([np.abs(s[-50:]).mean() for s in blk.run(t)])
+    assert np.argmax(p) == 3 and p[3] > 100 * np.delete(p, 3).max()
