@@ -115,3 +115,20 @@ def test_blks2_pfb_channelizer_hier_block(orc):
     t = np.exp(2j * np.pi * 3 / M * np.arange(M * 200)).astype(np.complex64)
     p = np.array([np.abs(s[-50:]).mean() for s in blk.run(t)])
     assert np.argmax(p) == 3 and p[3] > 100 * np.delete(p, 3).max()
+
+
+def test_optfir_band_pass_and_high_pass_live(ref):
+    """optfir.band_pass / high_pass (optfir.py:75-88, 142-158): remezord's order estimate and band vector handed to the
+    compiled gr_remez give the same taps as our whole design chain."""
+    for args in [(1.0, 48000.0, 2000.0, 3000.0, 9000.0, 10500.0, 0.2, 60.0)]:
+        h = optfir.band_pass(*args)
+        pd, sd = optfir.passband_ripple_to_dev(args[6]), optfir.stopband_atten_to_dev(args[7])
+        n, fo, ao, w = optfir.remezord(list(args[2:6]), (0, args[0], 0), [sd, pd, sd], args[1])
+        r = ref.remez(n + 2, fo, ao, w)
+        assert len(h) == len(r) == n + 3 and np.max(np.abs(h - r)) <= 1e-11 * np.max(np.abs(r))
+        H = np.abs(np.fft.rfft(h, 1 << 14))
+        f = np.arange(len(H)) / (1 << 14) * args[1]
+        assert np.all(np.abs(20 * np.log10(H[(f >= 3000) & (f <= 9000)])) < 0.5)
+        assert np.max(20 * np.log10(H[(f <= 2000) | (f >= 10500)] + 1e-300)) < -55
+    h = optfir.high_pass(1.0, 8000.0, 1000.0, 1500.0, 0.1, 60.0)
+    assert len(h) % 2 == 1                                    # optfir.high_pass forces an odd number of taps (:150-152)
