@@ -82,6 +82,35 @@ def test_argument_errors_of_the_8f_blocks(lib):
     assert lib.grcuda_last_error_code() == -1
 
 
+def test_argument_errors_of_the_round2_blocks(lib):
+    """gr_unpack_k_bits_bb, digital_clock_recovery_mm_cc, gr_framer_sink_1, gr_stream_to_streams, gr_map_bb: the reference's
+    constructor exceptions (std::out_of_range for k == 0, omega <= 0, negative gains) and plain bad arguments come back
+    as error codes before any device is touched."""
+    f = ctypes.c_float
+    for name in ("grcuda_unpack_k_bits_bb_create", "grcuda_clock_recovery_mm_cc_create", "grcuda_framer_sink_1_create",
+                 "grcuda_stream_to_streams_create", "grcuda_vector_to_streams_create", "grcuda_map_bb_create"):
+        getattr(lib, name).restype = ctypes.c_void_p
+    lib.grcuda_stream_to_streams_create.argtypes = [ctypes.c_size_t, ctypes.c_size_t]
+    lib.grcuda_vector_to_streams_create.argtypes = [ctypes.c_size_t, ctypes.c_size_t]
+    lib.grcuda_framer_sink_1_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    assert not lib.grcuda_unpack_k_bits_bb_create(0)                                  # gr_unpack_k_bits_bb.cc:44-45
+    assert lib.grcuda_last_error_code() == -2
+    assert not lib.grcuda_clock_recovery_mm_cc_create(1, f(0.0), f(0.1), f(0.5), f(0.1), f(0.001))   # :65-66
+    assert lib.grcuda_last_error_code() == -2
+    assert not lib.grcuda_clock_recovery_mm_cc_create(1, f(2.0), f(-0.1), f(0.5), f(0.1), f(0.001))  # :67-68
+    assert lib.grcuda_last_error_code() == -2
+    assert not lib.grcuda_clock_recovery_mm_cc_create(0, f(2.0), f(0.1), f(0.5), f(0.1), f(0.001))
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_framer_sink_1_create(0, 16, 1024)
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_stream_to_streams_create(0, 4)
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_vector_to_streams_create(8, 0)
+    assert lib.grcuda_last_error_code() == -1
+    assert not lib.grcuda_map_bb_create(None, 4)
+    assert lib.grcuda_last_error_code() == -1
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gnuradio-3.5.0-dmr_b200")
     for dp, _, files in os.walk(pkg):
